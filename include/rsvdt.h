@@ -1,0 +1,146 @@
+/*
+ * rsvdt.h -- C ABI of the B200-native RSVD-Delta-t time-stepping path (librsvdt_b200.so).
+ *
+ * The reference (AliFarghadan/RSVD-Delta-t) has no plugin/FFI interface: its seam is the set of C
+ * functions that main.c calls (SourceCode/main.c:113-146).  Each entry point below replaces one of
+ * those functions and keeps its argument meaning and error behaviour (int return, 0 = success, first
+ * error unwinds, like PetscErrorCode + CHKERRQ).  The opaque handle plays the role of the reference's
+ * structs of SourceCode/Variables.h (LNS_vars, RSVDt_vars, DFT_matrices, RSVD_matrices,
+ * Resolvent_matrices, TS_matrices): it owns the device copies of A, A^H, Y_hat, U_hat, V_hat, S_hat and
+ * the RK4 work vectors.
+ *
+ * Host buffers use the reference's own memory image: a one-rank PETSc MATDENSE, i.e. column-major
+ * complex double (re, im interleaved), N x (k*Nw_eff), frequency-major columns (col = iw*k + ik;
+ * SourceCode/PermuteMat.c:26-27).  Sparse inputs are CSR with 64-bit indices and complex-double values,
+ * i.e. the content of a PETSc-binary AIJ record (SourceCode/LNSStructure.c:22-27).
+ *
+ * Threading: one host thread per handle; all calls are synchronous on return unless stated.
+ * There is no CPU fallback: every compute entry point runs CUDA kernels for sm_100a or fails.
+ */
+#ifndef RSVDT_H
+#define RSVDT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rsvdt_context *rsvdt_handle;
+
+enum {
+    RSVDT_OK = 0,
+    RSVDT_ERR_ARG = 63,      /* PETSC_ERR_ARG_OUTOFRANGE-like: bad argument / size mismatch */
+    RSVDT_ERR_USER = 83,     /* PETSC_ERR_USER: missing or inconsistent user input */
+    RSVDT_ERR_STATE = 73,    /* PETSC_ERR_ARG_WRONGSTATE: call sequence violated (e.g. action before operator) */
+    RSVDT_ERR_CUDA = 97,     /* PETSC_ERR_GPU: CUDA runtime failure */
+    RSVDT_ERR_MEM = 55,      /* PETSC_ERR_MEM */
+    RSVDT_ERR_NUMERIC = 71   /* PETSC_ERR_MAT_CH_ZRPVT-like: breakdown (rank-deficient block in QR) */
+};
+
+/* Variables.h:5-28 : the members of RSVD_vars / TS_vars that the hot path reads. */
+typedef struct {
+    int64_t k;               /* number of test vectors                        (Variables.h:8)  */
+    int64_t Nw;              /* number of frequencies to resolve              (Variables.h:10) */
+    int64_t Nw_eff;          /* Nw (complex A) or Nw/2 (real A)               (Variables.h:11, LNSStructure.c:44) */
+    int64_t Ns;              /* time steps per steady-state period            (Variables.h:19) */
+    int64_t Nt;              /* transient time steps                          (Variables.h:20) */
+    int64_t ResRatio;        /* Ns / Nw                                       (Variables.h:21) */
+    double dt;               /* time step                                     (Variables.h:23) */
+    double w;                /* base frequency                                (Variables.h:12) */
+    int32_t RealOperator;    /* (Variables.h:24) */
+    int32_t TransientRemoval;/* (Variables.h:25) */
+} rsvdt_grid;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+/* SlepcInitialize / SlepcFinalize (main.c:107,148): binds a CUDA device and creates the stream. */
+int rsvdt_create(int device, rsvdt_handle *h);
+int rsvdt_destroy(rsvdt_handle h);
+const char *rsvdt_last_error(rsvdt_handle h);   /* message of the last failing call (never NULL) */
+const char *rsvdt_version(void);
+
+/* ---- pre-processing ------------------------------------------------------------------------------ */
+/* SetupTimeFreqGrid.c:16-21 (pure host arithmetic, bit-identical formulae). */
+int rsvdt_setup_time_freq_grid(double w, int64_t Nw, double dt_in, double TransientLength,
+                               double *dt, int64_t *Ns, int64_t *Nt, int64_t *ResRatio);
+
+/* LNSStructure.c:23-56 : takes the operator (content of MatLoad), decides real vs complex
+ * (||Im A||_F < 1e-12, :37-40), applies discounting A <- A - beta*I when disc_flg (:53-56), builds the
+ * device CSR of A and of A^H (the adjoint is a gather SpMM on A^H instead of MatMultHermitianTranspose). */
+int rsvdt_set_operator_csr(rsvdt_handle h, int64_t N, const int64_t *rowptr, const int64_t *col,
+                           const double *val_re_im, int disc_flg, double beta, int *real_operator);
+
+/* CreateDFTiDFTMats.c:5-96 + Variables.h: fixes k, Nw, Ns, ... ; twiddles are generated on the device. */
+int rsvdt_set_grid(rsvdt_handle h, const rsvdt_grid *g);
+
+/* ReadWeightMats.c:26-99 : optional sparse B (N x Nb), C (Nc x N), W_f_sqrt_inv (Nb x Nb), W_q_sqrt (Nc x Nc),
+ * W_q_sqrt_inv (Nc x Nc).  which: 0=W_f_sqrt_inv 1=B 2=W_q_sqrt_inv 3=W_q_sqrt 4=C.  Dimension checks as :34-98. */
+int rsvdt_set_weight_csr(rsvdt_handle h, int which, int64_t nrows, int64_t ncols, const int64_t *rowptr,
+                         const int64_t *col, const double *val_re_im);
+
+/* ---- RSVD_mat->Y_hat ----------------------------------------------------------------------------- */
+/* CreateRandomMat.c:23-31 (the InputForcingFlg path): uploads Y_hat, nrows x (k*Nw_eff), reference layout. */
+int rsvdt_set_yhat(rsvdt_handle h, const double *Y_host, int64_t nrows);
+int rsvdt_get_yhat(rsvdt_handle h, double *Y_host, int64_t nrows);
+int64_t rsvdt_yhat_rows(rsvdt_handle h);
+
+/* ---- the hot path -------------------------------------------------------------------------------- */
+/* DirectActionRK4.c:24-28 / AdjointActionRK4.c:24-28 : ApplyWeightMats(before) -> TSActionRK4 -> ApplyWeightMats(after),
+ * Y_hat consumed and replaced (TSActionRK4.c:49-50, DFT.c:21-39 / TransientRemovalStrategy.c:30-40). */
+int rsvdt_direct_action_rk4(rsvdt_handle h);
+int rsvdt_adjoint_action_rk4(rsvdt_handle h);
+
+/* One call with host buffers (upload F_hat, action, download Y_hat): the end-to-end form of TSActionRK4
+ * (TSActionRK4.c:15-164) used for the e2e measurement.  direct != 0 -> A, else A^H. */
+int rsvdt_ts_action_rk4(rsvdt_handle h, int direct, const double *F_hat_host, double *Y_hat_host);
+
+/* QRAllFreqs.c:22-32 : per-frequency thin QR of Y_hat (CholeskyQR2), R discarded, diag(R) > 0. */
+int rsvdt_qr_all_freqs(rsvdt_handle h);
+
+/* PowerIterationRK4.c:20-29 : q x [QR, adjoint, QR, direct]. */
+int rsvdt_power_iteration_rk4(rsvdt_handle h, int64_t q);
+
+/* SVDAllFreqsBeforeAdjoint.c:31-53 : Y_hat_w <- left singular vectors of Y_hat_w. */
+int rsvdt_svd_all_freqs_before_adjoint(rsvdt_handle h);
+/* StoreU.c:15 : U_hat <- copy of Y_hat. */
+int rsvdt_store_u(rsvdt_handle h);
+/* SVDAllFreqs.c:34-64 : V_hat <- left singular vectors of Y_hat_w, S_hat <- singular values; Y_hat destroyed;
+ * optional W^{-1/2} scalings of U_hat / V_hat (:63-64). */
+int rsvdt_svd_all_freqs(rsvdt_handle h);
+/* Resolvent_matrices readers (SaveResults.c reads these): U: Nc x (k*Nw_eff), V: Nb x (k*Nw_eff), S: k x Nw_eff (real). */
+int rsvdt_get_u_hat(rsvdt_handle h, double *U_host);
+int rsvdt_get_v_hat(rsvdt_handle h, double *V_host);
+int rsvdt_get_s_hat(rsvdt_handle h, double *S_host);
+
+/* TSExpADeltaT.c:25-34 : U (N x ncols, column-major, host) <- RK4^ResRatio(U), all columns batched. */
+int rsvdt_ts_exp_a_deltat(rsvdt_handle h, int direct, double *U_host, int64_t ncols);
+
+/* TransientRunRK4.c:128-186 : unforced IVP on one vector.  q0 in/out (host, N complex); norms_out has
+ * floor(rend/TransSaveMod)+1 doubles (norms_out[0] = ||q0||, :106-108).  reason: 0 finished, 1 NaN, 2 diverged,
+ * 3 converged (:143-158).  snapshot_cb (may be NULL) is called with (pos, q_host, N, user) every TransSaveMod
+ * steps when TransSave is requested (:160-164). */
+typedef int (*rsvdt_snapshot_cb)(int64_t pos, const double *q_host, int64_t N, void *user);
+int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t rend, int64_t TransSaveMod,
+                            double TransDivVal, double TransConVal, double *norms_out, int64_t *steps_done,
+                            int *reason, rsvdt_snapshot_cb snapshot_cb, void *user);
+
+/* ---- test / measurement hooks (no reference counterpart) ------------------------------------------ */
+/* snapshots Y_all of the last action: N x (Nstore*k), test-vector-major columns (TSActionRK4.c:62-70,126-130);
+ * only kept when rsvdt_keep_snapshots(h, 1) was called before the action. */
+int rsvdt_keep_snapshots(rsvdt_handle h, int keep);
+int rsvdt_get_snapshots(rsvdt_handle h, double *Yall_host);
+/* Runs `nsteps` forced RK4 steps of TSActionRK4's hot loop (TSActionRK4.c:116-122) on the resident F_hat
+ * (= current Y_hat, not consumed), timed with CUDA events on the launching stream.  Reports the total time, the
+ * time inside the RK4-stage kernels alone and inside the forcing-synthesis kernels alone (ms). */
+int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *ms_total);
+/* number of kernels launched by this handle since creation / since the last reset */
+int64_t rsvdt_kernel_launches(rsvdt_handle h, int reset);
+/* tuning knobs: name in {"chunk_steps","stage_variant","idft_variant","use_graph"}; returns RSVDT_ERR_ARG if unknown */
+int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value);
+/* device-event timing of one kernel family over the last timed window: which in {"stage","idft","dft","all"} */
+int rsvdt_last_kernel_ms(rsvdt_handle h, const char *which, float *ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSVDT_H */

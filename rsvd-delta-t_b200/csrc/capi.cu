@@ -1,0 +1,930 @@
+// capi.cu -- the C ABI of include/rsvdt.h: host orchestration of the CUDA kernels (one stream per handle).
+//
+// Mirrors the reference's call structure (SourceCode/main.c:113-146): every extern "C" function below
+// replaces the reference function named in its comment.  No CPU fallback exists: if a kernel cannot be
+// launched the call fails with RSVDT_ERR_CUDA.
+#include "../../include/rsvdt.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t alloc(size_t n)
+    {
+        release();
+        if (n == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n; else p = nullptr;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    void swap(DevBuf &o) { std::swap(p, o.p); std::swap(bytes, o.bytes); }
+};
+
+struct CsrOwned {
+    CsrDev d;
+    DevBuf rowptr, col, val;
+    int64_t lo_bw = 0, hi_bw = 0;  // max (row - col), max (col - row)
+    bool set = false;
+    void release() { rowptr.release(); col.release(); val.release(); d = CsrDev(); set = false; }
+};
+
+struct EventPair { cudaEvent_t a, b; };
+
+}  // namespace
+
+struct rsvdt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // LNS_vars (Variables.h:59-62)
+    int64_t N = 0;
+    CsrOwned A, AH;
+    bool real_operator = false;
+
+    // Weight_matrices (Variables.h:69-80): 0=W_f_sqrt_inv 1=B 2=W_q_sqrt_inv 3=W_q_sqrt 4=C, and their conj-transposes
+    CsrOwned W[5], WH[5];
+    int64_t Nb = 0, Nc = 0;
+
+    // RSVD_vars + TS_vars
+    rsvdt_grid g{};
+    bool grid_set = false;
+
+    // RSVD_matrices / Resolvent_matrices (device stacks [iw][row][ik])
+    DevBuf Yhat, Uhat, Vhat, Shat;
+    int64_t yhat_rows = 0, uhat_rows = 0, vhat_rows = 0;
+
+    // TS_matrices: work block vectors, forcing slices, snapshots
+    DevBuf y, xa, xb, acc, slices[2], coef, snaps, small, smallM, status, gram_partial, scalars;
+    bool keep_snapshots = false;
+    int64_t snaps_nstore = 0;
+
+    // options
+    int64_t chunk_steps = 16;
+    int64_t stage_variant = 0;
+    int64_t idft_variant = 0;
+    int64_t use_banded = 1;
+
+    // instrumentation
+    int64_t launches = 0;
+    bool profile = false;
+    std::vector<EventPair> ev_stage, ev_idft, ev_dft;
+    std::vector<EventPair> ev_pool;
+    float last_ms_stage = 0, last_ms_idft = 0, last_ms_dft = 0, last_ms_all = 0;
+    int64_t last_n_stage = 0, last_n_idft = 0, last_n_dft = 0;
+};
+
+namespace {
+
+int fail(rsvdt_handle h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? RSVDT_ERR_MEM : RSVDT_ERR_CUDA,            \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);    \
+    } while (0)
+
+#define RS(call)                     \
+    do {                             \
+        int r__ = (call);            \
+        if (r__ != RSVDT_OK) return r__; \
+    } while (0)
+
+int bind(rsvdt_handle h)
+{
+    if (!h) return RSVDT_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    return RSVDT_OK;
+}
+
+// event bracketing of one kernel family while profiling
+struct Bracket {
+    rsvdt_handle h;
+    std::vector<EventPair> *list;
+    EventPair ep{};
+    bool on = false;
+    Bracket(rsvdt_handle h_, std::vector<EventPair> *l) : h(h_), list(l)
+    {
+        if (h->profile && list->size() < 8192) {
+            on = cudaEventCreate(&ep.a) == cudaSuccess && cudaEventCreate(&ep.b) == cudaSuccess;
+            if (on) cudaEventRecord(ep.a, h->stream);
+        }
+    }
+    ~Bracket()
+    {
+        if (on) {
+            cudaEventRecord(ep.b, h->stream);
+            list->push_back(ep);
+        }
+    }
+};
+
+float drain(std::vector<EventPair> &v, int64_t *n)
+{
+    float tot = 0;
+    *n = (int64_t)v.size();
+    for (auto &e : v) {
+        float ms = 0;
+        cudaEventSynchronize(e.b);
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        tot += ms;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    v.clear();
+    return tot;
+}
+
+// ---- CSR upload: 64-bit host CSR -> device CSR with 32-bit columns; optionally conj-transposed -------------
+int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, const int64_t *rowptr, const int64_t *col,
+               const cplx *val, bool hermitian_transpose, double shift)
+{
+    dst.release();
+    const int64_t nnz = rowptr[nrows];
+    if (ncols > (int64_t)INT32_MAX) return fail(h, RSVDT_ERR_ARG, "more than 2^31-1 columns not supported");
+    std::vector<int64_t> rp;
+    std::vector<int32_t> ci((size_t)std::max<int64_t>(nnz, 1));
+    std::vector<cplx> va((size_t)std::max<int64_t>(nnz, 1));
+    int64_t out_rows = nrows, out_cols = ncols;
+    int64_t lo = 0, hi = 0, maxnnz = 0;
+    if (!hermitian_transpose) {
+        rp.assign(rowptr, rowptr + nrows + 1);
+        for (int64_t r = 0; r < nrows; r++) {
+            bool shifted = (shift == 0.0);
+            for (int64_t p = rowptr[r]; p < rowptr[r + 1]; p++) {
+                if (col[p] < 0 || col[p] >= ncols) return fail(h, RSVDT_ERR_ARG, "column index out of range in row %lld", (long long)r);
+                ci[p] = (int32_t)col[p];
+                va[p] = val[p];
+                if (!shifted && col[p] == r) { va[p].x -= shift; shifted = true; }  // MatShift, LNSStructure.c:54
+                lo = std::max(lo, r - col[p]);
+                hi = std::max(hi, col[p] - r);
+            }
+            if (!shifted) return fail(h, RSVDT_ERR_ARG, "discounting needs a stored diagonal entry (row %lld)", (long long)r);
+            maxnnz = std::max(maxnnz, rowptr[r + 1] - rowptr[r]);
+        }
+    } else {
+        out_rows = ncols;
+        out_cols = nrows;
+        if (nrows > (int64_t)INT32_MAX) return fail(h, RSVDT_ERR_ARG, "more than 2^31-1 rows not supported");
+        rp.assign((size_t)ncols + 1, 0);
+        for (int64_t p = 0; p < nnz; p++) {
+            if (col[p] < 0 || col[p] >= ncols) return fail(h, RSVDT_ERR_ARG, "column index out of range");
+            rp[col[p] + 1]++;
+        }
+        for (int64_t c = 0; c < ncols; c++) rp[c + 1] += rp[c];
+        std::vector<int64_t> next(rp.begin(), rp.end() - 1);
+        for (int64_t r = 0; r < nrows; r++)
+            for (int64_t p = rowptr[r]; p < rowptr[r + 1]; p++) {
+                const int64_t q = next[col[p]]++;
+                ci[q] = (int32_t)r;
+                va[q] = make_double2(val[p].x, -val[p].y);
+                if (shift != 0.0 && col[p] == r) va[q].x -= shift;
+                lo = std::max(lo, col[p] - r);
+                hi = std::max(hi, r - col[p]);
+            }
+        for (int64_t c = 0; c < ncols; c++) maxnnz = std::max(maxnnz, rp[c + 1] - rp[c]);
+    }
+    CU(dst.rowptr.alloc((size_t)(out_rows + 1) * sizeof(int64_t)));
+    CU(dst.col.alloc((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    CU(dst.val.alloc((size_t)std::max<int64_t>(nnz, 1) * sizeof(cplx)));
+    CU(cudaMemcpyAsync(dst.rowptr.p, rp.data(), (size_t)(out_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (nnz > 0) {
+        CU(cudaMemcpyAsync(dst.col.p, ci.data(), (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(dst.val.p, va.data(), (size_t)nnz * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    dst.d.nrows = out_rows;
+    dst.d.ncols = out_cols;
+    dst.d.nnz = nnz;
+    dst.d.rowptr = dst.rowptr.as<int64_t>();
+    dst.d.col = dst.col.as<int32_t>();
+    dst.d.val = dst.val.as<cplx>();
+    dst.d.max_row_nnz = maxnnz;
+    dst.lo_bw = lo;
+    dst.hi_bw = hi;
+    dst.set = true;
+    return RSVDT_OK;
+}
+
+int ensure(rsvdt_handle h, DevBuf &b, size_t bytes)
+{
+    if (b.bytes >= bytes && b.p) return RSVDT_OK;
+    CU(b.alloc(bytes));
+    return RSVDT_OK;
+}
+
+size_t stack_bytes(int64_t na, int64_t rows, int64_t nb) { return (size_t)na * (size_t)rows * (size_t)nb * sizeof(cplx); }
+
+// host (pageable or pinned) column-major <-> device stack, through a device staging buffer
+int upload_stack(rsvdt_handle h, DevBuf &dst, const double *host, int64_t rows, int na, int nb, int64_t ca, int64_t cb)
+{
+    const size_t bytes = stack_bytes(na, rows, nb);
+    RS(ensure(h, dst, bytes));
+    DevBuf stage;
+    CU(stage.alloc(bytes));
+    cudaError_t e = cudaMemcpyAsync(stage.p, host, bytes, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = launch_host_to_stack(dst.as<cplx>(), stage.as<cplx>(), rows, na, nb, ca, cb, h->stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    stage.release();
+    CU(e);
+    return RSVDT_OK;
+}
+
+int download_stack(rsvdt_handle h, const DevBuf &src, double *host, int64_t rows, int na, int nb, int64_t ca, int64_t cb)
+{
+    const size_t bytes = stack_bytes(na, rows, nb);
+    if (src.bytes < bytes) return fail(h, RSVDT_ERR_STATE, "device matrix not available");
+    DevBuf stage;
+    CU(stage.alloc(bytes));
+    cudaError_t e = launch_stack_to_host(stage.as<cplx>(), src.as<cplx>(), rows, na, nb, ca, cb, h->stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host, stage.p, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    stage.release();
+    CU(e);
+    return RSVDT_OK;
+}
+
+// ---- one RK4 step on a block of nv vectors (TSRK4.c:18-47 / TSTransRK4.c:15-36) ---------------------------
+// y: state (in/out), xa/xb/acc: work, f_prev/f_half/f_next: forcing slices or nullptr, snap: optional copy of y_{n+1}
+int rk4_step(rsvdt_handle h, const CsrOwned &Op, int nv, cplx *y, cplx *xa, cplx *xb, cplx *acc, const cplx *f_prev,
+             const cplx *f_half, const cplx *f_next, cplx *snap)
+{
+    const double dt = h->g.dt;
+    StageArgs a;
+    {   // k1 = Op y + F3(prev) ; x2 = y + dt/2 k1 ; acc = y + dt/6 k1            TSRK4.c:18,30,44
+        Bracket br(h, &h->ev_stage);
+        a = StageArgs();
+        a.xin = y; a.ybase = y; a.f = f_prev; a.xout = xa; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6;
+        CU(launch_rk4_stage(Op.d, nv, 0, a, (int)h->stage_variant, h->stream));
+    }
+    {   // k2 = Op x2 + F2 ; x3 = y + dt/2 k2 ; acc += dt/6*2 k2                   TSRK4.c:31-32,45
+        Bracket br(h, &h->ev_stage);
+        a = StageArgs();
+        a.xin = xa; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xb; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6 * 2;
+        CU(launch_rk4_stage(Op.d, nv, 1, a, (int)h->stage_variant, h->stream));
+    }
+    {   // k3 = Op x3 + F2 ; x4 = y + dt k3 ; acc += dt/6*2 k3                     TSRK4.c:33-34,46
+        Bracket br(h, &h->ev_stage);
+        a = StageArgs();
+        a.xin = xb; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xa; a.acc_out = acc; a.cx = dt; a.ca = dt / 6 * 2;
+        CU(launch_rk4_stage(Op.d, nv, 1, a, (int)h->stage_variant, h->stream));
+    }
+    {   // k4 = Op x4 + F3 ; y = acc + dt/6 k4 ; snapshot                         TSRK4.c:35,47 ; SaveSnapshots.c:26-28
+        Bracket br(h, &h->ev_stage);
+        a = StageArgs();
+        a.xin = xa; a.f = f_next; a.acc_in = acc; a.acc_out = y; a.snap = snap; a.ca = dt / 6;
+        CU(launch_rk4_stage(Op.d, nv, 2, a, (int)h->stage_variant, h->stream));
+    }
+    h->launches += 4;
+    return RSVDT_OK;
+}
+
+int64_t pos_mod(int64_t a, int64_t m)
+{
+    int64_t r = a % m;
+    return r < 0 ? r + m : r;
+}
+
+// SaveSnapshots.c:19-28 : slot of step i in Y_all, or -1
+int64_t snapshot_slot(const rsvdt_grid &g, bool direct, int64_t Nstore, int64_t i)
+{
+    if (i <= g.Nt) return -1;
+    int64_t pos = i - g.Nt;
+    if (pos % g.ResRatio != 0) return -1;
+    pos = pos / g.ResRatio - 1;
+    pos = pos_mod(pos, Nstore);
+    pos = direct ? pos : Nstore - 1 - pos;
+    return pos_mod(pos, Nstore);
+}
+
+// ---- the forced stepping loop of TSActionRK4.c:89-122 with all k test vectors batched -------------------------
+// Fhat: stack [Nw_eff][N][k]; y must be zeroed by the caller for a fresh action.  Steps i = i_begin..i_end (1-based).
+int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *snaps, int64_t Nstore, int64_t i_begin,
+                 int64_t i_end)
+{
+    const rsvdt_grid &g = h->g;
+    const CsrOwned &Op = direct ? h->A : h->AH;
+    const int nv = (int)g.k;
+    const int64_t U = h->N * g.k;
+    const int64_t Tc = std::max<int64_t>(1, h->chunk_steps);
+    const int S = (int)(2 * Tc);
+    for (int b = 0; b < 2; b++) RS(ensure(h, h->slices[b], (size_t)S * U * sizeof(cplx)));
+    RS(ensure(h, h->coef, (size_t)S * g.Nw_eff * sizeof(cplx)));
+    RS(ensure(h, h->xa, (size_t)U * sizeof(cplx)));
+    RS(ensure(h, h->xb, (size_t)U * sizeof(cplx)));
+    RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
+
+    int cur = 0;
+    const cplx *f_carry = nullptr;  // forcing at t_n of the first step of the chunk (F3 carried over, TSRK4.c:18)
+    {
+        // initial forcing, TSActionRK4.c:103 (i_begin == 1 -> column 0) or the slice preceding i_begin
+        const int64_t j0 = direct ? 2 * (i_begin - 1) : -2 * (i_begin - 1);
+        Bracket br(h, &h->ev_idft);
+        CU(launch_idft_coef(h->coef.as<cplx>(), 1, (int)g.Nw_eff, j0, 1, g.Ns, g.RealOperator, h->stream));
+        cplx *dst = h->slices[1].as<cplx>() + (int64_t)(S - 1) * U;
+        CU(launch_small_cgemm(dst, U, h->coef.as<cplx>(), Fhat, h->N * g.k, 1, (int)g.Nw_eff, U, 3, h->stream));
+        h->launches += 2;
+        f_carry = dst;
+    }
+    for (int64_t i0 = i_begin; i0 <= i_end; i0 += Tc) {
+        const int64_t nsteps = std::min(Tc, i_end - i0 + 1);
+        const int Sc = (int)(2 * nsteps);
+        cplx *sl = h->slices[cur].as<cplx>();
+        {   // forcing synthesis for the chunk: slices s = 0..Sc-1 at half-step indices j_start + dir*s   (TSRK4.c:21-27)
+            const int64_t j_start = direct ? 2 * (i0 - 1) + 1 : -1 - 2 * (i0 - 1);
+            Bracket br(h, &h->ev_idft);
+            CU(launch_idft_coef(h->coef.as<cplx>(), Sc, (int)g.Nw_eff, j_start, direct ? 1 : -1, g.Ns, g.RealOperator, h->stream));
+            CU(launch_small_cgemm(sl, U, h->coef.as<cplx>(), Fhat, h->N * g.k, Sc, (int)g.Nw_eff, U, (int)h->idft_variant, h->stream));
+            h->launches += 2;
+        }
+        for (int64_t c = 0; c < nsteps; c++) {
+            const int64_t i = i0 + c;
+            const cplx *f_prev = (c == 0) ? f_carry : sl + (2 * c - 1) * U;
+            const cplx *f_half = sl + (2 * c) * U;
+            const cplx *f_next = sl + (2 * c + 1) * U;
+            cplx *snap = nullptr;
+            if (snaps) {
+                const int64_t slot = snapshot_slot(g, direct, Nstore, i);
+                if (slot >= 0) snap = snaps + slot * U;
+            }
+            RS(rk4_step(h, Op, nv, y, h->xa.as<cplx>(), h->xb.as<cplx>(), h->acc.as<cplx>(), f_prev, f_half, f_next, snap));
+        }
+        f_carry = sl + (int64_t)(Sc - 1) * U;
+        cur ^= 1;
+    }
+    return RSVDT_OK;
+}
+
+// unforced steps on a block of nv vectors (TSTransRK4.c:15-36)
+int unforced_steps(rsvdt_handle h, bool direct, int nv, cplx *y, int64_t nsteps)
+{
+    const CsrOwned &Op = direct ? h->A : h->AH;
+    const int64_t U = h->N * nv;
+    RS(ensure(h, h->xa, (size_t)U * sizeof(cplx)));
+    RS(ensure(h, h->xb, (size_t)U * sizeof(cplx)));
+    RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
+    for (int64_t i = 0; i < nsteps; i++)
+        RS(rk4_step(h, Op, nv, y, h->xa.as<cplx>(), h->xb.as<cplx>(), h->acc.as<cplx>(), nullptr, nullptr, nullptr, nullptr));
+    return RSVDT_OK;
+}
+
+// DFT.c:26-39 : Y_hat[w'][u] = ResRatio * sum_j dft[j][w'] * Y_all[j][u]
+int dft_snapshots(rsvdt_handle h, const cplx *snaps, cplx *Yhat_out)
+{
+    const rsvdt_grid &g = h->g;
+    const int64_t U = h->N * g.k;
+    RS(ensure(h, h->coef, (size_t)std::max<int64_t>(g.Nw_eff * g.Nw, 2 * h->chunk_steps * g.Nw_eff) * sizeof(cplx)));
+    Bracket br(h, &h->ev_dft);
+    CU(launch_dft_coef(h->coef.as<cplx>(), (int)g.Nw_eff, (int)g.Nw, g.ResRatio, h->stream));
+    CU(launch_small_cgemm(Yhat_out, U, h->coef.as<cplx>(), snaps, U, (int)g.Nw_eff, (int)g.Nw, U, 0, h->stream));
+    h->launches += 2;
+    return RSVDT_OK;
+}
+
+int check_ready(rsvdt_handle h)
+{
+    if (!h) return RSVDT_ERR_ARG;
+    if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "operator not set (rsvdt_set_operator_csr)");
+    if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "grid not set (rsvdt_set_grid)");
+    return RSVDT_OK;
+}
+
+// TSActionRK4.c:15-164 on the resident Y_hat (rows must equal N here; weights are applied by the callers)
+int ts_action(rsvdt_handle h, bool direct)
+{
+    RS(check_ready(h));
+    const rsvdt_grid &g = h->g;
+    if (h->yhat_rows != h->N || !h->Yhat.p) return fail(h, RSVDT_ERR_STATE, "Y_hat not set or wrong row count");
+    if (g.TransientRemoval) return fail(h, RSVDT_ERR_USER, "TransientRemoval is not implemented yet in this build");
+    const int64_t U = h->N * g.k;
+    int64_t rend = g.Nt + g.Ns;                                   // TSActionRK4.c:41
+    rend += g.TransientRemoval ? g.ResRatio : 0;                  // :42
+    const int64_t Nstore = g.TransientRemoval ? g.Nw + 1 : g.Nw;  // :43
+
+    DevBuf Fhat;
+    Fhat.swap(h->Yhat);                                           // :49-50 ownership hand-off
+    h->yhat_rows = 0;
+    int rc = RSVDT_OK;
+    do {
+        if ((rc = ensure(h, h->y, (size_t)U * sizeof(cplx))) != RSVDT_OK) break;
+        if ((rc = ensure(h, h->snaps, (size_t)Nstore * U * sizeof(cplx))) != RSVDT_OK) break;
+        h->snaps_nstore = Nstore;
+        cudaError_t e = launch_fill_zero(h->y.as<cplx>(), U, h->stream);  // :91
+        if (e == cudaSuccess) e = launch_fill_zero(h->snaps.as<cplx>(), Nstore * U, h->stream);
+        if (e != cudaSuccess) { rc = fail(h, RSVDT_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e)); break; }
+        if ((rc = forced_steps(h, direct, Fhat.as<cplx>(), h->y.as<cplx>(), h->snaps.as<cplx>(), Nstore, 1, rend)) != RSVDT_OK) break;
+        // the forcing is no longer needed (:139); its storage becomes the new Y_hat
+        if ((rc = dft_snapshots(h, h->snaps.as<cplx>(), Fhat.as<cplx>())) != RSVDT_OK) break;   // :148
+        cudaError_t es = cudaStreamSynchronize(h->stream);
+        if (es != cudaSuccess) { rc = fail(h, RSVDT_ERR_CUDA, "action failed: %s", cudaGetErrorString(es)); break; }
+    } while (0);
+    if (rc == RSVDT_OK) {
+        h->Yhat.swap(Fhat);
+        h->yhat_rows = h->N;
+        if (!h->keep_snapshots) h->snaps.release();
+    }
+    Fhat.release();
+    return rc;
+}
+
+// ApplyWeightMats.c:16-80 : Y_hat <- M * Y_hat for sparse M (rows may change)
+int apply_sparse(rsvdt_handle h, const CsrOwned &M)
+{
+    const rsvdt_grid &g = h->g;
+    if (h->yhat_rows != M.d.ncols) return fail(h, RSVDT_ERR_ARG, "weight matrix has %lld columns, Y_hat has %lld rows", (long long)M.d.ncols, (long long)h->yhat_rows);
+    DevBuf out;
+    CU(out.alloc(stack_bytes(g.Nw_eff, M.d.nrows, g.k)));
+    CU(launch_spmm_stack(M.d, h->Yhat.as<cplx>(), out.as<cplx>(), (int)g.Nw_eff, (int)g.k, h->stream));
+    h->launches++;
+    CU(cudaStreamSynchronize(h->stream));
+    h->Yhat.swap(out);
+    h->yhat_rows = M.d.nrows;
+    out.release();
+    return RSVDT_OK;
+}
+
+int action_with_weights(rsvdt_handle h, bool direct)
+{
+    RS(check_ready(h));
+    if (direct) {  // ApplyWeightMats.c:18-28 then :29-41
+        if (h->W[0].set) RS(apply_sparse(h, h->W[0]));   // W_f_sqrt_inv
+        if (h->W[1].set) RS(apply_sparse(h, h->W[1]));   // B
+        RS(ts_action(h, true));
+        if (h->W[4].set) RS(apply_sparse(h, h->W[4]));   // C
+        if (h->W[3].set) RS(apply_sparse(h, h->W[3]));   // W_q_sqrt
+    } else {       // ApplyWeightMats.c:43-60 then :61-78
+        if (h->W[3].set) RS(apply_sparse(h, h->WH[3]));  // W_q_sqrt^H
+        if (h->W[4].set) RS(apply_sparse(h, h->WH[4]));  // C^H
+        RS(ts_action(h, false));
+        if (h->W[1].set) RS(apply_sparse(h, h->WH[1]));  // B^H
+        if (h->W[0].set) RS(apply_sparse(h, h->WH[0]));  // W_f_sqrt_inv^H
+    }
+    return RSVDT_OK;
+}
+
+int gram_all(rsvdt_handle h, const cplx *Y, int64_t rows)
+{
+    const rsvdt_grid &g = h->g;
+    const int nblk = gram_num_blocks(rows);
+    RS(ensure(h, h->gram_partial, (size_t)nblk * g.Nw_eff * g.k * g.k * sizeof(cplx)));
+    RS(ensure(h, h->small, (size_t)g.Nw_eff * g.k * g.k * sizeof(cplx)));
+    RS(ensure(h, h->smallM, (size_t)g.Nw_eff * g.k * g.k * sizeof(cplx)));
+    RS(ensure(h, h->status, (size_t)g.Nw_eff * sizeof(int)));
+    CU(launch_gram(Y, rows, (int)g.k, (int)g.Nw_eff, h->gram_partial.as<cplx>(), h->small.as<cplx>(), h->stream));
+    h->launches += 2;
+    return RSVDT_OK;
+}
+
+// per-frequency cross-product SVD: Y_w <- left singular vectors; sigma -> dst_sigma (device, k x Nw_eff) if not null
+int svd_all(rsvdt_handle h, DevBuf &Y, int64_t rows, double *dst_sigma)
+{
+    const rsvdt_grid &g = h->g;
+    RS(gram_all(h, Y.as<cplx>(), rows));
+    DevBuf sig;
+    CU(sig.alloc((size_t)g.Nw_eff * g.k * sizeof(double)));
+    CU(launch_cross_svd_small(h->small.as<cplx>(), (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), sig.as<double>(), h->stream));
+    CU(launch_apply_right(Y.as<cplx>(), rows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
+    h->launches += 2;
+    if (dst_sigma) CU(cudaMemcpyAsync(dst_sigma, sig.p, (size_t)g.Nw_eff * g.k * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    sig.release();
+    return RSVDT_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char *rsvdt_version(void) { return "rsvdt-b200 0.1 (sm_100a)"; }
+
+int rsvdt_create(int device, rsvdt_handle *hout)
+{
+    if (!hout) return RSVDT_ERR_ARG;
+    *hout = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return RSVDT_ERR_CUDA;  // no CPU fallback: fail loudly
+    if (device < 0 || device >= ndev) return RSVDT_ERR_ARG;
+    rsvdt_handle h = new (std::nothrow) rsvdt_context();
+    if (!h) return RSVDT_ERR_MEM;
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return RSVDT_ERR_CUDA;
+    }
+    *hout = h;
+    return RSVDT_OK;
+}
+
+int rsvdt_destroy(rsvdt_handle h)
+{
+    if (!h) return RSVDT_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    int64_t n;
+    drain(h->ev_stage, &n); drain(h->ev_idft, &n); drain(h->ev_dft, &n);
+    h->A.release(); h->AH.release();
+    for (int i = 0; i < 5; i++) { h->W[i].release(); h->WH[i].release(); }
+    DevBuf *bufs[] = {&h->Yhat, &h->Uhat, &h->Vhat, &h->Shat, &h->y, &h->xa, &h->xb, &h->acc, &h->slices[0], &h->slices[1],
+                      &h->coef, &h->snaps, &h->small, &h->smallM, &h->status, &h->gram_partial, &h->scalars};
+    for (DevBuf *b : bufs) b->release();
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return RSVDT_OK;
+}
+
+const char *rsvdt_last_error(rsvdt_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int rsvdt_setup_time_freq_grid(double w, int64_t Nw, double dt_in, double TransientLength, double *dt, int64_t *Ns,
+                               int64_t *Nt, int64_t *ResRatio)
+{
+    if (!dt || !Ns || !Nt || !ResRatio || Nw <= 0 || !(w > 0) || !(dt_in > 0)) return RSVDT_ERR_ARG;
+    const double PI = 3.14159265358979323846264338327950288;  // PETSC_PI
+    const double T_ss = 2 * PI / w;                           // SetupTimeFreqGrid.c:16
+    const double dt_w = T_ss / (double)Nw;                    // :17
+    *dt = dt_w / std::ceil(dt_w / dt_in);                     // :18
+    *Ns = (int64_t)std::round(T_ss / *dt);                    // :19
+    *Nt = (int64_t)std::round(TransientLength / *dt);         // :20
+    *ResRatio = *Ns / Nw;                                     // :21
+    return RSVDT_OK;
+}
+
+int rsvdt_set_operator_csr(rsvdt_handle h, int64_t N, const int64_t *rowptr, const int64_t *col, const double *val,
+                           int disc_flg, double beta, int *real_operator)
+{
+    RS(bind(h));
+    if (N <= 0 || !rowptr || !col || !val) return fail(h, RSVDT_ERR_ARG, "bad operator arguments");
+    if (disc_flg && beta < 0) return fail(h, RSVDT_ERR_USER, "'beta' must be positive, current value: %g", beta);  // ReadUserInput.c:133
+    const cplx *v = reinterpret_cast<const cplx *>(val);
+    const int64_t nnz = rowptr[N];
+    double im2 = 0.0;                                         // LNSStructure.c:37-40
+    for (int64_t p = 0; p < nnz; p++) im2 += v[p].y * v[p].y;
+    h->real_operator = std::sqrt(im2) < 1e-12;
+    if (real_operator) *real_operator = h->real_operator ? 1 : 0;
+    const double shift = disc_flg ? beta : 0.0;               // LNSStructure.c:53-56
+    h->N = N;
+    RS(upload_csr(h, h->A, N, N, rowptr, col, v, false, shift));
+    RS(upload_csr(h, h->AH, N, N, rowptr, col, v, true, shift));
+    return RSVDT_OK;
+}
+
+int rsvdt_set_grid(rsvdt_handle h, const rsvdt_grid *g)
+{
+    RS(bind(h));
+    if (!g) return fail(h, RSVDT_ERR_ARG, "null grid");
+    if (g->k <= 0 || g->Nw <= 0 || g->Nw_eff <= 0 || g->Ns <= 0 || g->Nt < 0 || g->ResRatio <= 0 || !(g->dt > 0))
+        return fail(h, RSVDT_ERR_ARG, "grid parameters out of range");
+    if (g->k > 32) return fail(h, RSVDT_ERR_ARG, "k > 32 is not supported by the per-frequency QR/SVD kernels");
+    if (g->Nw_eff != (g->RealOperator ? g->Nw / 2 : g->Nw)) return fail(h, RSVDT_ERR_ARG, "Nw_eff inconsistent with RealOperator (LNSStructure.c:44)");
+    h->g = *g;
+    h->grid_set = true;
+    return RSVDT_OK;
+}
+
+int rsvdt_set_weight_csr(rsvdt_handle h, int which, int64_t nrows, int64_t ncols, const int64_t *rowptr,
+                         const int64_t *col, const double *val)
+{
+    RS(bind(h));
+    if (which < 0 || which > 4 || !rowptr || !col || !val) return fail(h, RSVDT_ERR_ARG, "bad weight arguments");
+    if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "set the operator before the weights");
+    static const char *names[5] = {"W_f_sqrt_inv", "B", "W_q_sqrt_inv", "W_q_sqrt", "C"};
+    if ((which == 0 || which == 2 || which == 3) && nrows != ncols)   // ReadWeightMats.c:34,64,75
+        return fail(h, RSVDT_ERR_USER, "weight matrix (%s) must be square, current size = %lld x %lld", names[which], (long long)nrows, (long long)ncols);
+    if (which == 1 && nrows != h->N) return fail(h, RSVDT_ERR_USER, "Input matrix (B) must have %lld rows", (long long)h->N);        // :49
+    if (which == 4 && ncols != h->N) return fail(h, RSVDT_ERR_USER, "Output matrix (C) must have %lld columns", (long long)h->N);   // :89
+    const cplx *v = reinterpret_cast<const cplx *>(val);
+    RS(upload_csr(h, h->W[which], nrows, ncols, rowptr, col, v, false, 0.0));
+    RS(upload_csr(h, h->WH[which], nrows, ncols, rowptr, col, v, true, 0.0));
+    return RSVDT_OK;
+}
+
+int64_t rsvdt_yhat_rows(rsvdt_handle h) { return h ? h->yhat_rows : -1; }
+
+int rsvdt_set_yhat(rsvdt_handle h, const double *Y_host, int64_t nrows)
+{
+    RS(bind(h));
+    if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "grid not set");
+    if (!Y_host || nrows <= 0) return fail(h, RSVDT_ERR_ARG, "bad Y_hat arguments");
+    RS(upload_stack(h, h->Yhat, Y_host, nrows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1));
+    h->yhat_rows = nrows;
+    return RSVDT_OK;
+}
+
+int rsvdt_get_yhat(rsvdt_handle h, double *Y_host, int64_t nrows)
+{
+    RS(bind(h));
+    if (!Y_host || nrows != h->yhat_rows || !h->Yhat.p) return fail(h, RSVDT_ERR_STATE, "Y_hat not available with %lld rows", (long long)nrows);
+    return download_stack(h, h->Yhat, Y_host, nrows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1);
+}
+
+int rsvdt_direct_action_rk4(rsvdt_handle h) { RS(bind(h)); return action_with_weights(h, true); }
+int rsvdt_adjoint_action_rk4(rsvdt_handle h) { RS(bind(h)); return action_with_weights(h, false); }
+
+int rsvdt_ts_action_rk4(rsvdt_handle h, int direct, const double *F_hat_host, double *Y_hat_host)
+{
+    RS(bind(h));
+    RS(check_ready(h));
+    if (!F_hat_host || !Y_hat_host) return fail(h, RSVDT_ERR_ARG, "null host buffer");
+    RS(rsvdt_set_yhat(h, F_hat_host, h->N));
+    RS(ts_action(h, direct != 0));
+    return rsvdt_get_yhat(h, Y_hat_host, h->N);
+}
+
+int rsvdt_qr_all_freqs(rsvdt_handle h)
+{
+    RS(bind(h));
+    RS(check_ready(h));
+    if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
+    const rsvdt_grid &g = h->g;
+    std::vector<int> st((size_t)g.Nw_eff);
+    for (int pass = 0; pass < 2; pass++) {  // CholeskyQR2 (QRAllFreqs.c:22-32 semantics: Q with diag(R) > 0)
+        RS(gram_all(h, h->Yhat.as<cplx>(), h->yhat_rows));
+        CU(launch_chol_inverse(h->small.as<cplx>(), (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->status.as<int>(), h->stream));
+        CU(launch_apply_right(h->Yhat.as<cplx>(), h->yhat_rows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
+        h->launches += 2;
+        CU(cudaMemcpyAsync(st.data(), h->status.p, st.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int64_t w = 0; w < g.Nw_eff; w++)
+            if (st[(size_t)w] != 0) return fail(h, RSVDT_ERR_NUMERIC, "QR breakdown at frequency %lld (column %d, pass %d)", (long long)w, st[(size_t)w] - 1, pass);
+    }
+    return RSVDT_OK;
+}
+
+int rsvdt_power_iteration_rk4(rsvdt_handle h, int64_t q)
+{
+    RS(bind(h));
+    for (int64_t iq = 0; iq < q; iq++) {  // PowerIterationRK4.c:20-29
+        RS(rsvdt_qr_all_freqs(h));
+        RS(action_with_weights(h, false));
+        RS(rsvdt_qr_all_freqs(h));
+        RS(action_with_weights(h, true));
+    }
+    return RSVDT_OK;
+}
+
+int rsvdt_svd_all_freqs_before_adjoint(rsvdt_handle h)
+{
+    RS(bind(h));
+    RS(check_ready(h));
+    if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
+    return svd_all(h, h->Yhat, h->yhat_rows, nullptr);
+}
+
+int rsvdt_store_u(rsvdt_handle h)
+{
+    RS(bind(h));
+    if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
+    const size_t bytes = stack_bytes(h->g.Nw_eff, h->yhat_rows, h->g.k);
+    RS(ensure(h, h->Uhat, bytes));
+    CU(cudaMemcpyAsync(h->Uhat.p, h->Yhat.p, bytes, cudaMemcpyDeviceToDevice, h->stream));  // StoreU.c:15
+    CU(cudaStreamSynchronize(h->stream));
+    h->uhat_rows = h->yhat_rows;
+    return RSVDT_OK;
+}
+
+int rsvdt_svd_all_freqs(rsvdt_handle h)
+{
+    RS(bind(h));
+    RS(check_ready(h));
+    if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
+    const rsvdt_grid &g = h->g;
+    RS(ensure(h, h->Shat, (size_t)g.Nw_eff * g.k * sizeof(double)));
+    RS(svd_all(h, h->Yhat, h->yhat_rows, h->Shat.as<double>()));
+    h->Vhat.release();
+    h->Vhat.swap(h->Yhat);                                    // SVDAllFreqs.c:58 MatDestroy(Y_hat)
+    h->vhat_rows = h->yhat_rows;
+    h->yhat_rows = 0;
+    // SVDAllFreqs.c:63-64 optional W^{-1/2} scalings
+    if (h->W[2].set && h->Uhat.p) {
+        DevBuf out;
+        if (h->uhat_rows != h->W[2].d.ncols) return fail(h, RSVDT_ERR_ARG, "W_q_sqrt_inv size mismatch");
+        CU(out.alloc(stack_bytes(g.Nw_eff, h->W[2].d.nrows, g.k)));
+        CU(launch_spmm_stack(h->W[2].d, h->Uhat.as<cplx>(), out.as<cplx>(), (int)g.Nw_eff, (int)g.k, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->Uhat.swap(out);
+        out.release();
+    }
+    if (h->W[0].set) {
+        DevBuf out;
+        if (h->vhat_rows != h->W[0].d.ncols) return fail(h, RSVDT_ERR_ARG, "W_f_sqrt_inv size mismatch");
+        CU(out.alloc(stack_bytes(g.Nw_eff, h->W[0].d.nrows, g.k)));
+        CU(launch_spmm_stack(h->W[0].d, h->Vhat.as<cplx>(), out.as<cplx>(), (int)g.Nw_eff, (int)g.k, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->Vhat.swap(out);
+        out.release();
+    }
+    return RSVDT_OK;
+}
+
+int rsvdt_get_u_hat(rsvdt_handle h, double *U_host)
+{
+    RS(bind(h));
+    if (!U_host || !h->Uhat.p) return fail(h, RSVDT_ERR_STATE, "U_hat not available");
+    return download_stack(h, h->Uhat, U_host, h->uhat_rows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1);
+}
+
+int rsvdt_get_v_hat(rsvdt_handle h, double *V_host)
+{
+    RS(bind(h));
+    if (!V_host || !h->Vhat.p) return fail(h, RSVDT_ERR_STATE, "V_hat not available");
+    return download_stack(h, h->Vhat, V_host, h->vhat_rows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1);
+}
+
+int rsvdt_get_s_hat(rsvdt_handle h, double *S_host)
+{
+    RS(bind(h));
+    if (!S_host || !h->Shat.p) return fail(h, RSVDT_ERR_STATE, "S_hat not available");
+    // device layout [iw][m] == column-major k x Nw_eff
+    CU(cudaMemcpyAsync(S_host, h->Shat.p, (size_t)h->g.Nw_eff * h->g.k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return RSVDT_OK;
+}
+
+int rsvdt_ts_exp_a_deltat(rsvdt_handle h, int direct, double *U_host, int64_t ncols)
+{
+    RS(bind(h));
+    RS(check_ready(h));
+    if (!U_host || ncols <= 0) return fail(h, RSVDT_ERR_ARG, "bad arguments");
+    // columns batched: block vector [row][col] ; host column-major N x ncols = stack with na=1, nb=ncols, cb=1
+    DevBuf blk;
+    RS(upload_stack(h, blk, U_host, h->N, 1, (int)ncols, 0, 1));
+    int rc = unforced_steps(h, direct != 0, (int)ncols, blk.as<cplx>(), h->g.ResRatio);   // TSExpADeltaT.c:25-34
+    if (rc == RSVDT_OK) rc = download_stack(h, blk, U_host, h->N, 1, (int)ncols, 0, 1);
+    blk.release();
+    return rc;
+}
+
+int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t rend, int64_t TransSaveMod,
+                            double TransDivVal, double TransConVal, double *norms_out, int64_t *steps_done, int *reason,
+                            rsvdt_snapshot_cb cb, void *user)
+{
+    RS(bind(h));
+    if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "operator not set");
+    if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "grid not set (dt)");
+    if (!q0_host || rend < 0 || TransSaveMod <= 0 || !norms_out) return fail(h, RSVDT_ERR_ARG, "bad arguments");
+    const int64_t N = h->N;
+    DevBuf q;
+    CU(q.alloc((size_t)N * sizeof(cplx)));
+    RS(ensure(h, h->scalars, 512 * sizeof(double)));
+    double *partial = h->scalars.as<double>();
+    double *d_norm = partial + 400;
+    CU(cudaMemcpyAsync(q.p, q0_host, (size_t)N * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    double n2 = 0;
+    CU(launch_norm2(q.as<cplx>(), N, partial, d_norm, h->stream));
+    CU(cudaMemcpyAsync(&n2, d_norm, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    norms_out[0] = std::sqrt(n2);                              // TransientRunRK4.c:106-108
+    int why = 0;
+    int64_t i = 1;
+    std::vector<double> snap_host;
+    for (; i <= rend;) {
+        const int64_t next_stop = std::min(rend, ((i - 1) / TransSaveMod + 1) * TransSaveMod);
+        int rc = unforced_steps(h, direct != 0, 1, q.as<cplx>(), next_stop - i + 1);   // :128-130
+        if (rc != RSVDT_OK) { q.release(); return rc; }
+        i = next_stop + 1;
+        if (next_stop % TransSaveMod == 0) {                   // :137
+            const int64_t pos = next_stop / TransSaveMod;
+            CU(launch_norm2(q.as<cplx>(), N, partial, d_norm, h->stream));
+            h->launches += 2;
+            CU(cudaMemcpyAsync(&n2, d_norm, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            const double norm = std::sqrt(n2);
+            if (std::isnan(norm)) { why = 1; i = next_stop; break; }         // :143-146
+            if (norm > TransDivVal) { why = 2; i = next_stop; break; }       // :147-151
+            if (norm < TransConVal) { why = 3; i = next_stop; break; }       // :152-156
+            if (cb) {                                                        // :160-164
+                snap_host.resize((size_t)2 * N);
+                CU(cudaMemcpyAsync(snap_host.data(), q.p, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                int crc = cb(pos, snap_host.data(), N, user);
+                if (crc != 0) { q.release(); return fail(h, RSVDT_ERR_USER, "snapshot callback failed (%d)", crc); }
+            }
+            norms_out[pos] = norm;                                           // :166
+        }
+    }
+    if (steps_done) *steps_done = why ? i : rend;
+    if (reason) *reason = why;
+    CU(cudaMemcpyAsync(q0_host, q.p, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    q.release();
+    return RSVDT_OK;
+}
+
+int rsvdt_keep_snapshots(rsvdt_handle h, int keep)
+{
+    if (!h) return RSVDT_ERR_ARG;
+    h->keep_snapshots = keep != 0;
+    return RSVDT_OK;
+}
+
+int rsvdt_get_snapshots(rsvdt_handle h, double *Yall_host)
+{
+    RS(bind(h));
+    if (!Yall_host || !h->snaps.p || h->snaps_nstore <= 0) return fail(h, RSVDT_ERR_STATE, "snapshots not kept (rsvdt_keep_snapshots)");
+    // device [pos][row][ik] -> reference test-vector-major column ik*Nstore + pos  (TSActionRK4.c:126-130)
+    return download_stack(h, h->snaps, Yall_host, h->N, (int)h->snaps_nstore, (int)h->g.k, 1, h->snaps_nstore);
+}
+
+int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *ms_total)
+{
+    RS(bind(h));
+    RS(check_ready(h));
+    if (nsteps <= 0 || !ms_total) return fail(h, RSVDT_ERR_ARG, "bad arguments");
+    if (!h->Yhat.p || h->yhat_rows != h->N) return fail(h, RSVDT_ERR_STATE, "Y_hat (forcing) not set");
+    const int64_t U = h->N * h->g.k;
+    RS(ensure(h, h->y, (size_t)U * sizeof(cplx)));
+    CU(launch_fill_zero(h->y.as<cplx>(), U, h->stream));
+    // allocate work buffers outside the timed region
+    RS(forced_steps(h, direct != 0, h->Yhat.as<cplx>(), h->y.as<cplx>(), nullptr, h->g.Nw, 1, std::min<int64_t>(nsteps, h->chunk_steps)));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(launch_fill_zero(h->y.as<cplx>(), U, h->stream));
+    int64_t n;
+    drain(h->ev_stage, &n); drain(h->ev_idft, &n); drain(h->ev_dft, &n);
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    h->profile = true;
+    CU(cudaEventRecord(e0, h->stream));
+    int rc = forced_steps(h, direct != 0, h->Yhat.as<cplx>(), h->y.as<cplx>(), nullptr, h->g.Nw, 1, nsteps);
+    cudaEventRecord(e1, h->stream);
+    h->profile = false;
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->last_ms_stage = drain(h->ev_stage, &h->last_n_stage);
+    h->last_ms_idft = drain(h->ev_idft, &h->last_n_idft);
+    h->last_ms_dft = drain(h->ev_dft, &h->last_n_dft);
+    h->last_ms_all = ms;
+    if (rc != RSVDT_OK) return rc;
+    CU(e);
+    *ms_total = ms;
+    return RSVDT_OK;
+}
+
+int64_t rsvdt_kernel_launches(rsvdt_handle h, int reset)
+{
+    if (!h) return -1;
+    const int64_t n = h->launches;
+    if (reset) h->launches = 0;
+    return n;
+}
+
+int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
+{
+    if (!h || !name) return RSVDT_ERR_ARG;
+    if (!strcmp(name, "chunk_steps")) { if (value < 1 || value > 64) return fail(h, RSVDT_ERR_ARG, "chunk_steps out of range"); h->chunk_steps = value; }
+    else if (!strcmp(name, "stage_variant")) h->stage_variant = value;
+    else if (!strcmp(name, "idft_variant")) h->idft_variant = value;
+    else if (!strcmp(name, "use_banded")) h->use_banded = value;
+    else return fail(h, RSVDT_ERR_ARG, "unknown option '%s'", name);
+    return RSVDT_OK;
+}
+
+int rsvdt_last_kernel_ms(rsvdt_handle h, const char *which, float *ms, int64_t *launches)
+{
+    if (!h || !which || !ms) return RSVDT_ERR_ARG;
+    int64_t n = 0;
+    if (!strcmp(which, "stage")) { *ms = h->last_ms_stage; n = h->last_n_stage; }
+    else if (!strcmp(which, "idft")) { *ms = h->last_ms_idft; n = h->last_n_idft; }
+    else if (!strcmp(which, "dft")) { *ms = h->last_ms_dft; n = h->last_n_dft; }
+    else if (!strcmp(which, "all")) { *ms = h->last_ms_all; n = h->last_n_stage + h->last_n_idft + h->last_n_dft; }
+    else return fail(h, RSVDT_ERR_ARG, "unknown kernel family '%s'", which);
+    if (launches) *launches = n;
+    return RSVDT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// kernels.cuh -- launchers of the sm_100a kernels behind the C ABI (include/rsvdt.h).
+//
+// Device data layout.  All values are complex double (double2, 16-B aligned).
+//   block vector      X[row][iv]                 iv = 0..nv-1 fastest: one RK4 state for nv test vectors
+//   frequency stack   T[a][row][iv]              a = frequency slot iw (Y_hat, F_hat) or snapshot slot pos (Y_all)
+// so that (i) a gather of row `c` of a block vector is nv*16 contiguous bytes, (ii) every frequency block
+// Y_hat_w is a contiguous row-major N x k matrix (QR / SVD operate on it in place) and (iii) the iDFT / DFT
+// contractions read and write unit-stride along (row, iv).  The reference's column permutations
+// (PermuteMat.c / ReversePermuteMat.c) are therefore index arithmetic, not data movement.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef double2 cplx;
+
+struct CsrDev {
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int64_t *rowptr = nullptr;  // nrows+1
+    int32_t *col = nullptr;     // nnz
+    cplx *val = nullptr;        // nnz
+    int64_t max_row_nnz = 0;
+};
+
+// One RK4 stage  (TSRK4.c:18-47, TSTransRK4.c:15-36)
+//   ksum = Op * xin + f
+//   mode 0 (stage 1)  : xout = ybase + cx*ksum ; acc_out = ybase  + ca*ksum
+//   mode 1 (stage 2,3): xout = ybase + cx*ksum ; acc_out = acc_in + ca*ksum
+//   mode 2 (stage 4)  : acc_out = acc_in + ca*ksum (this is y_{n+1}; acc_out may alias ybase) ; snap = same (optional)
+struct StageArgs {
+    const cplx *xin = nullptr;
+    const cplx *ybase = nullptr;
+    const cplx *f = nullptr;
+    const cplx *acc_in = nullptr;
+    cplx *xout = nullptr;
+    cplx *acc_out = nullptr;
+    cplx *snap = nullptr;
+    double cx = 0, ca = 0;
+};
+
+cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s);
+
+// Whole RK4 step in one kernel for narrow-band operators (all 4 stages, halo recomputation in shared memory).
+//   f_prev / f_half / f_next : forcing slices at t_n, t_n + dt/2, t_n + dt (nullptr -> unforced)
+struct BandedStepArgs {
+    const cplx *y_in = nullptr;
+    cplx *y_out = nullptr;
+    const cplx *f_prev = nullptr, *f_half = nullptr, *f_next = nullptr;
+    cplx *snap = nullptr;
+    double dt = 0;
+};
+bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv);
+cudaError_t launch_rk4_banded_step(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, const BandedStepArgs &a,
+                                   cudaStream_t s);
+
+// Twiddle coefficient tables (CreateDFTiDFTMats.c:42-58,76-84), generated on the device with exactly reduced phases.
+//   idft: coef[s][w] = (1/Ns) * exp(+2*pi*i * m(w) * j_s / (2Ns)),  j_s = (j_start + dir*s) mod 2Ns,  s < S, w < Nw_eff
+//   dft : coef[w'][j] = ResRatio * exp(-2*pi*i * w' * j / Nw),       w' < Nw_eff, j < Nw
+cudaError_t launch_idft_coef(cplx *coef, int S, int Nw_eff, int64_t j_start, int dir, int64_t Ns, int real_op,
+                             cudaStream_t s);
+cudaError_t launch_dft_coef(cplx *coef, int Nw_eff, int Nw, int64_t ResRatio, cudaStream_t s);
+
+// out[s][u] = sum_{w<K} coef[s*K + w] * in[w*in_stride + u],  s < S, u < U   (complex double contraction)
+//   forcing synthesis (CreateForcingOnFly.c:17-19 batched over a chunk of half steps) and DFT (DFT.c:26-39).
+cudaError_t launch_small_cgemm(cplx *out, int64_t out_stride, const cplx *coef, const cplx *in, int64_t in_stride,
+                               int S, int K, int64_t U, int variant, cudaStream_t s);
+
+// reference (column-major, column c = a*ca + b*cb) <-> device stack T[a][row][b]
+cudaError_t launch_host_to_stack(cplx *dst, const cplx *src_colmajor, int64_t nrows, int na, int nb, int64_t ca,
+                                 int64_t cb, cudaStream_t s);
+cudaError_t launch_stack_to_host(cplx *dst_colmajor, const cplx *src, int64_t nrows, int na, int nb, int64_t ca,
+                                 int64_t cb, cudaStream_t s);
+
+// ---- per-frequency small dense work (QRAllFreqs.c, SVDAllFreqs*.c) -----------------------------------
+// G[w] = Y_w^H Y_w for all w (k x k each, row-major), deterministic two-stage reduction. partial: nblk*nw*k*k
+int gram_num_blocks(int64_t nrows);
+cudaError_t launch_gram(const cplx *Y, int64_t nrows, int k, int nw, cplx *partial, cplx *G, cudaStream_t s);
+// M[w] = R_w^{-1} with G_w = R_w^H R_w (Cholesky, upper R, positive diagonal); status[w] != 0 on breakdown
+cudaError_t launch_chol_inverse(const cplx *G, int k, int nw, cplx *M, int *status, cudaStream_t s);
+// eigen-decomposition of G_w (Hermitian Jacobi): sigma[w][m] = sqrt(lambda_m) descending, M[w] = V * diag(1/sigma)
+cudaError_t launch_cross_svd_small(const cplx *G, int k, int nw, cplx *M, double *sigma, cudaStream_t s);
+// Y_w <- Y_w * M_w in place (row tiles staged through shared memory)
+cudaError_t launch_apply_right(cplx *Y, int64_t nrows, int k, int nw, const cplx *M, cudaStream_t s);
+
+// ||q||_2^2 partial sums -> out (deterministic two-stage)
+cudaError_t launch_norm2(const cplx *q, int64_t n, double *partial, double *out, cudaStream_t s);
+
+// y <- 0 etc.
+cudaError_t launch_fill_zero(cplx *p, int64_t n, cudaStream_t s);
+
+// sparse (CSR, nrows x ncols) times stack: out[a][r][b] = sum_c M[r][c] in[a][c][b]  (ApplyWeightMats.c:18-76)
+cudaError_t launch_spmm_stack(const CsrDev &M, const cplx *in, cplx *out, int na, int nb, cudaStream_t s);
