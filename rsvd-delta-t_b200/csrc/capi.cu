@@ -78,7 +78,7 @@ struct rsvdt_context {
     int64_t snaps_nstore = 0;
 
     // options
-    int64_t chunk_steps = 16;
+    int64_t chunk_steps = 32;
     int64_t stage_variant = 0;
     int64_t idft_variant = 0;
     int64_t use_banded = 1;
@@ -328,6 +328,63 @@ int64_t snapshot_slot(const rsvdt_grid &g, bool direct, int64_t Nstore, int64_t 
     return pos_mod(pos, Nstore);
 }
 
+bool use_banded_path(rsvdt_handle h, const CsrOwned &Op, int nv)
+{
+    return h->use_banded && banded_step_supported(Op.d, Op.lo_bw, Op.hi_bw, nv, (int)h->stage_variant);
+}
+
+// one whole RK4 step, dispatching between the fused banded kernel (y ping-pongs between *ycur and *ynext) and the
+// stage-by-stage kernels (in place on *ycur)
+int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, bool banded, cplx **ycur, cplx **ynext, const cplx *f_prev,
+                 const cplx *f_half, const cplx *f_next, cplx *snap)
+{
+    if (!banded)
+        return rk4_step(h, Op, nv, *ycur, h->xa.as<cplx>(), h->xb.as<cplx>(), h->acc.as<cplx>(), f_prev, f_half, f_next, snap);
+    Bracket br(h, &h->ev_stage);
+    BandedStepArgs a;
+    a.y_in = *ycur; a.y_out = *ynext; a.f_prev = f_prev; a.f_half = f_half; a.f_next = f_next; a.snap = snap; a.dt = h->g.dt;
+    CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, h->stream));
+    h->launches += 1;
+    std::swap(*ycur, *ynext);
+    return RSVDT_OK;
+}
+
+// largest |harmonic| of the frequency slots (CreateDFTiDFTMats.c:44-50)
+int64_t max_harmonic(const rsvdt_grid &g)
+{
+    if (g.RealOperator) return g.Nw_eff - 1;
+    return (g.Nw_eff % 2 == 0) ? g.Nw_eff / 2 : (g.Nw_eff - 1) / 2;
+}
+
+// forcing slices s = 0..Sc-1 at half-step indices j_start + dir*s  (TSRK4.c:21-27, CreateForcingOnFly.c:17-19)
+int synth_forcing(rsvdt_handle h, const cplx *Fhat, cplx *slices, int Sc, int64_t j_start, int dir)
+{
+    const rsvdt_grid &g = h->g;
+    const int64_t U = h->N * g.k;
+    Bracket br(h, &h->ev_idft);
+    const double PI = 3.14159265358979323846;
+    const double hh = 0.5 * (double)Sc;
+    const double x = (double)max_harmonic(g) * (PI / (double)g.Ns) * hh;
+    const int P = (h->idft_variant >= 10 || Sc < 4) ? -1 : idft_taylor_terms(x);
+    if (P > 0 && P < Sc) {
+        const int64_t J2 = 2 * j_start + (int64_t)dir * (Sc - 1);
+        CU(launch_idft_taylor_coef(h->coef.as<cplx>(), P, (int)g.Nw_eff, J2, dir, g.Ns, hh, g.RealOperator, h->stream));
+        CU(launch_idft_taylor(slices, U, h->coef.as<cplx>(), Fhat, U, Sc, P, (int)g.Nw_eff, U, h->stream));
+    } else {
+        // direct contraction in tiles of at most 32 slices
+        for (int s0 = 0; s0 < Sc; s0 += 32) {
+            const int Sb = std::min(32, Sc - s0);
+            CU(launch_idft_coef(h->coef.as<cplx>() + (int64_t)s0 * g.Nw_eff, Sb, (int)g.Nw_eff, j_start + (int64_t)dir * s0, dir, g.Ns, g.RealOperator, h->stream));
+            CU(launch_small_cgemm(slices + (int64_t)s0 * U, U, h->coef.as<cplx>() + (int64_t)s0 * g.Nw_eff, Fhat, U, Sb, (int)g.Nw_eff, U,
+                                  (int)(h->idft_variant % 10), h->stream));
+            h->launches += 2;
+        }
+        h->launches -= 2;
+    }
+    h->launches += 2;
+    return RSVDT_OK;
+}
+
 // ---- the forced stepping loop of TSActionRK4.c:89-122 with all k test vectors batched -------------------------
 // Fhat: stack [Nw_eff][N][k]; y must be zeroed by the caller for a fresh action.  Steps i = i_begin..i_end (1-based).
 int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *snaps, int64_t Nstore, int64_t i_begin,
@@ -339,11 +396,15 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
     const int64_t U = h->N * g.k;
     const int64_t Tc = std::max<int64_t>(1, h->chunk_steps);
     const int S = (int)(2 * Tc);
+    const bool banded = use_banded_path(h, Op, nv);
     for (int b = 0; b < 2; b++) RS(ensure(h, h->slices[b], (size_t)S * U * sizeof(cplx)));
-    RS(ensure(h, h->coef, (size_t)S * g.Nw_eff * sizeof(cplx)));
+    RS(ensure(h, h->coef, (size_t)std::max<int64_t>((int64_t)S * g.Nw_eff, g.Nw_eff * g.Nw) * sizeof(cplx)));
     RS(ensure(h, h->xa, (size_t)U * sizeof(cplx)));
-    RS(ensure(h, h->xb, (size_t)U * sizeof(cplx)));
-    RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
+    if (!banded) {
+        RS(ensure(h, h->xb, (size_t)U * sizeof(cplx)));
+        RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
+    }
+    cplx *ycur = y, *ynext = h->xa.as<cplx>();
 
     int cur = 0;
     const cplx *f_carry = nullptr;  // forcing at t_n of the first step of the chunk (F3 carried over, TSRK4.c:18)
@@ -353,7 +414,7 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
         Bracket br(h, &h->ev_idft);
         CU(launch_idft_coef(h->coef.as<cplx>(), 1, (int)g.Nw_eff, j0, 1, g.Ns, g.RealOperator, h->stream));
         cplx *dst = h->slices[1].as<cplx>() + (int64_t)(S - 1) * U;
-        CU(launch_small_cgemm(dst, U, h->coef.as<cplx>(), Fhat, h->N * g.k, 1, (int)g.Nw_eff, U, 3, h->stream));
+        CU(launch_small_cgemm(dst, U, h->coef.as<cplx>(), Fhat, U, 1, (int)g.Nw_eff, U, 3, h->stream));
         h->launches += 2;
         f_carry = dst;
     }
@@ -361,13 +422,8 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
         const int64_t nsteps = std::min(Tc, i_end - i0 + 1);
         const int Sc = (int)(2 * nsteps);
         cplx *sl = h->slices[cur].as<cplx>();
-        {   // forcing synthesis for the chunk: slices s = 0..Sc-1 at half-step indices j_start + dir*s   (TSRK4.c:21-27)
-            const int64_t j_start = direct ? 2 * (i0 - 1) + 1 : -1 - 2 * (i0 - 1);
-            Bracket br(h, &h->ev_idft);
-            CU(launch_idft_coef(h->coef.as<cplx>(), Sc, (int)g.Nw_eff, j_start, direct ? 1 : -1, g.Ns, g.RealOperator, h->stream));
-            CU(launch_small_cgemm(sl, U, h->coef.as<cplx>(), Fhat, h->N * g.k, Sc, (int)g.Nw_eff, U, (int)h->idft_variant, h->stream));
-            h->launches += 2;
-        }
+        const int64_t j_start = direct ? 2 * (i0 - 1) + 1 : -1 - 2 * (i0 - 1);
+        RS(synth_forcing(h, Fhat, sl, Sc, j_start, direct ? 1 : -1));
         for (int64_t c = 0; c < nsteps; c++) {
             const int64_t i = i0 + c;
             const cplx *f_prev = (c == 0) ? f_carry : sl + (2 * c - 1) * U;
@@ -378,11 +434,12 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
                 const int64_t slot = snapshot_slot(g, direct, Nstore, i);
                 if (slot >= 0) snap = snaps + slot * U;
             }
-            RS(rk4_step(h, Op, nv, y, h->xa.as<cplx>(), h->xb.as<cplx>(), h->acc.as<cplx>(), f_prev, f_half, f_next, snap));
+            RS(rk4_step_any(h, Op, nv, banded, &ycur, &ynext, f_prev, f_half, f_next, snap));
         }
         f_carry = sl + (int64_t)(Sc - 1) * U;
         cur ^= 1;
     }
+    if (ycur != y) CU(cudaMemcpyAsync(y, ycur, (size_t)U * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
     return RSVDT_OK;
 }
 
@@ -391,11 +448,15 @@ int unforced_steps(rsvdt_handle h, bool direct, int nv, cplx *y, int64_t nsteps)
 {
     const CsrOwned &Op = direct ? h->A : h->AH;
     const int64_t U = h->N * nv;
+    const bool banded = use_banded_path(h, Op, nv);
     RS(ensure(h, h->xa, (size_t)U * sizeof(cplx)));
-    RS(ensure(h, h->xb, (size_t)U * sizeof(cplx)));
-    RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
-    for (int64_t i = 0; i < nsteps; i++)
-        RS(rk4_step(h, Op, nv, y, h->xa.as<cplx>(), h->xb.as<cplx>(), h->acc.as<cplx>(), nullptr, nullptr, nullptr, nullptr));
+    if (!banded) {
+        RS(ensure(h, h->xb, (size_t)U * sizeof(cplx)));
+        RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
+    }
+    cplx *ycur = y, *ynext = h->xa.as<cplx>();
+    for (int64_t i = 0; i < nsteps; i++) RS(rk4_step_any(h, Op, nv, banded, &ycur, &ynext, nullptr, nullptr, nullptr, nullptr));
+    if (ycur != y) CU(cudaMemcpyAsync(y, ycur, (size_t)U * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
     return RSVDT_OK;
 }
 

@@ -94,10 +94,170 @@ cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs
     return cudaGetLastError();
 }
 
-bool banded_step_supported(const CsrDev &, int64_t, int64_t, int) { return false; }
-cudaError_t launch_rk4_banded_step(const CsrDev &, int64_t, int64_t, int, const BandedStepArgs &, cudaStream_t)
+// =====================================================================================================
+// K1b: a whole RK4 step in ONE kernel for narrow-band operators (temporal fusion of the four stages).
+//   A CTA owns TR consecutive rows and recomputes a halo of 4*b rows on each side (b = matrix half bandwidth), so the
+//   three intermediate stage vectors never leave shared memory.  Per unit and step the HBM traffic drops from the
+//   20 block-vector passes of the stage-by-stage scheme (320 B) to: read y, f(t_n), f(t_n+dt/2), f(t_n+dt), write y
+//   (80 B) times the halo factor (TR+8b)/TR.  Arithmetic and summation order per row are identical to K1.
+// =====================================================================================================
+template <int BT, int UPT, int MINB, bool FORCED>
+__global__ void __launch_bounds__(BT, MINB)
+rk4_banded_step_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const cplx *__restrict__ val,
+                       int64_t N, int nv, int b, int TR, int E0, BandedStepArgs a)
 {
-    return cudaErrorNotSupported;
+    extern __shared__ cplx sm[];
+    const int n_e = E0 * nv;
+    cplx *Y = sm, *B1 = sm + n_e, *B2 = sm + 2 * n_e;
+    const int64_t base = (int64_t)blockIdx.x * TR - 4 * b;  // global row of local row 0 (may be negative)
+    const double dt = a.dt;
+    const double c_half = dt / 2, c_full = dt, w1 = dt / 6, w2 = dt / 6 * 2;  // TSRK4.c:30-34,44-47
+
+    cplx acc[UPT];
+    int lrow[UPT], liv[UPT];
+    bool valid[UPT];
+#pragma unroll
+    for (int i = 0; i < UPT; i++) {
+        const int e = threadIdx.x + i * BT;
+        const int lr = e / nv;
+        lrow[i] = lr;
+        liv[i] = e - lr * nv;
+        const int64_t gr = base + lr;
+        valid[i] = (e < n_e) && gr >= 0 && gr < N;
+        cplx y = make_double2(0.0, 0.0);
+        if (valid[i]) y = ldg(a.y_in + gr * nv + liv[i]);
+        if (e < n_e) Y[e] = y;
+        acc[i] = y;
+    }
+    __syncthreads();
+
+    // ---- stage 1: k1 = Op y + F3(t_n) on local rows [b, E0-b) ; x2 = y + dt/2 k1 ; acc = y + dt/6 k1
+#pragma unroll
+    for (int i = 0; i < UPT; i++) {
+        const int lr = lrow[i];
+        if (valid[i] && lr >= b && lr < E0 - b) {
+            const int64_t gr = base + lr;
+            const int64_t gu = gr * nv + liv[i];
+            cplx s = make_double2(0.0, 0.0);
+            if (FORCED) s = ldg(a.f_prev + gu);
+            const int64_t p1 = __ldg(rowptr + gr + 1);
+            for (int64_t p = __ldg(rowptr + gr); p < p1; ++p)
+                cfma(s, ldg(val + p), Y[(int)(__ldg(col + p) - base) * nv + liv[i]]);
+            const cplx y = acc[i];
+            B1[threadIdx.x + i * BT] = make_double2(fma(c_half, s.x, y.x), fma(c_half, s.y, y.y));
+            acc[i] = make_double2(fma(w1, s.x, y.x), fma(w1, s.y, y.y));
+        }
+    }
+    __syncthreads();
+    // ---- stage 2: k2 = Op x2 + F2 on [2b, E0-2b) ; x3 = y + dt/2 k2 ; acc += dt/3 k2
+#pragma unroll
+    for (int i = 0; i < UPT; i++) {
+        const int lr = lrow[i];
+        if (valid[i] && lr >= 2 * b && lr < E0 - 2 * b) {
+            const int64_t gr = base + lr;
+            cplx s = make_double2(0.0, 0.0);
+            if (FORCED) s = ldg(a.f_half + gr * nv + liv[i]);
+            const int64_t p1 = __ldg(rowptr + gr + 1);
+            for (int64_t p = __ldg(rowptr + gr); p < p1; ++p)
+                cfma(s, ldg(val + p), B1[(int)(__ldg(col + p) - base) * nv + liv[i]]);
+            const cplx y = Y[threadIdx.x + i * BT];
+            B2[threadIdx.x + i * BT] = make_double2(fma(c_half, s.x, y.x), fma(c_half, s.y, y.y));
+            acc[i] = make_double2(fma(w2, s.x, acc[i].x), fma(w2, s.y, acc[i].y));
+        }
+    }
+    __syncthreads();
+    // ---- stage 3: k3 = Op x3 + F2 on [3b, E0-3b) ; x4 = y + dt k3 ; acc += dt/3 k3
+#pragma unroll
+    for (int i = 0; i < UPT; i++) {
+        const int lr = lrow[i];
+        if (valid[i] && lr >= 3 * b && lr < E0 - 3 * b) {
+            const int64_t gr = base + lr;
+            cplx s = make_double2(0.0, 0.0);
+            if (FORCED) s = ldg(a.f_half + gr * nv + liv[i]);   // second read of the slice: L2 hit
+            const int64_t p1 = __ldg(rowptr + gr + 1);
+            for (int64_t p = __ldg(rowptr + gr); p < p1; ++p)
+                cfma(s, ldg(val + p), B2[(int)(__ldg(col + p) - base) * nv + liv[i]]);
+            const cplx y = Y[threadIdx.x + i * BT];
+            B1[threadIdx.x + i * BT] = make_double2(fma(c_full, s.x, y.x), fma(c_full, s.y, y.y));
+            acc[i] = make_double2(fma(w2, s.x, acc[i].x), fma(w2, s.y, acc[i].y));
+        }
+    }
+    __syncthreads();
+    // ---- stage 4: k4 = Op x4 + F3(t_n+dt) on the owned rows [4b, E0-4b) ; y_{n+1} = acc + dt/6 k4
+#pragma unroll
+    for (int i = 0; i < UPT; i++) {
+        const int lr = lrow[i];
+        if (valid[i] && lr >= 4 * b && lr < E0 - 4 * b) {
+            const int64_t gr = base + lr;
+            const int64_t gu = gr * nv + liv[i];
+            cplx s = make_double2(0.0, 0.0);
+            if (FORCED) s = ldg(a.f_next + gu);
+            const int64_t p1 = __ldg(rowptr + gr + 1);
+            for (int64_t p = __ldg(rowptr + gr); p < p1; ++p)
+                cfma(s, ldg(val + p), B1[(int)(__ldg(col + p) - base) * nv + liv[i]]);
+            const cplx yn = make_double2(fma(w1, s.x, acc[i].x), fma(w1, s.y, acc[i].y));
+            a.y_out[gu] = yn;
+            if (a.snap) a.snap[gu] = yn;
+        }
+    }
+}
+
+namespace {
+struct BandedCfg { int bt, upt; };
+inline BandedCfg banded_cfg(int variant)
+{
+    switch (variant) {
+        case 1: return {512, 4};   // 1 CTA/SM, no spills
+        case 2: return {512, 3};   // smaller tile, 2 CTAs/SM
+        case 3: return {256, 6};   // 3 CTAs/SM
+        default: return {512, 4};  // 2 CTAs/SM (64 registers)
+    }
+}
+inline int banded_E0(int variant, int nv) { const BandedCfg c = banded_cfg(variant); return (c.bt * c.upt) / nv; }
+
+template <int BT, int UPT, int MINB>
+cudaError_t banded_launch(const CsrDev &Op, int b, int nv, int E0, const BandedStepArgs &a, cudaStream_t s)
+{
+    const int TR = E0 - 8 * b;
+    const size_t smem = (size_t)3 * E0 * nv * sizeof(cplx);
+    const unsigned grid = (unsigned)((Op.nrows + TR - 1) / TR);
+    cudaError_t e;
+    if (a.f_prev) {
+        auto kfn = rk4_banded_step_kernel<BT, UPT, MINB, true>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<grid, BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, a);
+    } else {
+        auto kfn = rk4_banded_step_kernel<BT, UPT, MINB, false>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<grid, BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, a);
+    }
+    return cudaGetLastError();
+}
+}  // namespace
+
+bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, int variant)
+{
+    const int64_t b = lo_bw > hi_bw ? lo_bw : hi_bw;
+    if (nv <= 0 || Op.nrows <= 0) return false;
+    const int E0 = banded_E0(variant, nv);
+    // the halo (8b rows) must stay a modest fraction of the tile
+    return b >= 1 && 8 * b * 4 <= E0;
+}
+
+cudaError_t launch_rk4_banded_step(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, const BandedStepArgs &a,
+                                   int variant, cudaStream_t s)
+{
+    const int b = (int)(lo_bw > hi_bw ? lo_bw : hi_bw);
+    const int E0 = banded_E0(variant, nv);
+    if (E0 - 8 * b <= 0) return cudaErrorInvalidValue;
+    switch (variant) {
+        case 1: return banded_launch<512, 4, 1>(Op, b, nv, E0, a, s);
+        case 2: return banded_launch<512, 3, 2>(Op, b, nv, E0, a, s);
+        case 3: return banded_launch<256, 6, 3>(Op, b, nv, E0, a, s);
+        default: return banded_launch<512, 4, 2>(Op, b, nv, E0, a, s);
+    }
 }
 
 // =====================================================================================================
@@ -230,6 +390,130 @@ cudaError_t launch_small_cgemm(cplx *out, int64_t out_stride, const cplx *coef, 
         case 3: return small_cgemm_launch<16, 1>(out, out_stride, coef, in, in_stride, S, K, U, s);
         default: return small_cgemm_launch<32, 1>(out, out_stride, coef, in, in_stride, S, K, U, s);
     }
+}
+
+// =====================================================================================================
+// K2b: forcing synthesis through Taylor moments.  Within a chunk of S consecutive half steps centred at j_c,
+//   f_s = sum_w Fhat_w g_w exp(i m_w phi (j_s - j_c)),  phi = pi/Ns,  g_w = exp(i m_w phi j_c)/Ns,
+// and |m_w phi (j_s - j_c)| <= x = m_max*phi*S/2 is tiny (0.08 for the bench grid), so with tau = (j_s-j_c)/(S/2)
+//   f_s = sum_{p<P} C_p tau^p,   C_p = sum_w Fhat_w g_w (i m_w phi dir S/2)^p / p!
+// to a truncation error x^P/P! chosen below 2^-60 relative to sum_w |Fhat_w|/Ns, i.e. below the rounding error of the
+// direct sum.  The contraction over frequencies shrinks from S to P outputs (P ~ 11 for S = 64) and the S slices are
+// produced by a Horner evaluation from registers: the kernel turns from FP64-bound into HBM-bound
+// (reads Fhat once per chunk, writes the S slices).
+// =====================================================================================================
+int idft_taylor_terms(double x)
+{
+    // smallest P with sum_{p>=P} x^p/p! < 2^-60; -1 if more than 16 terms would be needed
+    double term = 1.0;
+    for (int p = 1; p <= 16; p++) {
+        term *= x / p;
+        const double tail = term / (1.0 - x / (p + 1));
+        if (x < p + 1 && tail < 8.7e-19) return p;
+    }
+    return -1;
+}
+
+__global__ void idft_taylor_coef_kernel(cplx *coef, int P, int K, int64_t J2, int dir, int64_t Ns, double h, int real_op)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= K) return;
+    const int64_t m = freq_harmonic(w, K, real_op);
+    const int64_t P4 = 4 * Ns;
+    int64_t r = (m * (J2 % P4)) % P4;      // phase of the chunk centre j_c = J2/2 :  m*j_c*pi/Ns = pi*r/(2Ns)
+    if (r < 0) r += P4;
+    double sn, cs;
+    sincospi((double)r / (double)(2 * Ns), &sn, &cs);
+    const double sc = 1.0 / (double)Ns;    // CreateDFTiDFTMats.c:55 (2/Nt, Nt = 2Ns)
+    cplx term = make_double2(cs * sc, sn * sc);
+    const double q = (double)m * (3.14159265358979323846 / (double)Ns) * (double)dir * h;  // z = i*q
+    coef[w] = term;
+    for (int p = 1; p < P; p++) {
+        const double f = q / (double)p;
+        term = make_double2(-term.y * f, term.x * f);   // term *= i*q/p
+        coef[(int64_t)p * K + w] = term;
+    }
+}
+
+cudaError_t launch_idft_taylor_coef(cplx *coef, int P, int K, int64_t J2, int dir, int64_t Ns, double h, int real_op,
+                                    cudaStream_t s)
+{
+    idft_taylor_coef_kernel<<<(K + 63) / 64, 64, 0, s>>>(coef, P, K, J2, dir, Ns, h, real_op);
+    return cudaGetLastError();
+}
+
+template <int PT, int UT>
+__global__ void __launch_bounds__(128)
+idft_taylor_kernel(cplx *__restrict__ out, int64_t out_stride, const cplx *__restrict__ coef,
+                   const cplx *__restrict__ in, int64_t in_stride, int S, int P, int K, int64_t U)
+{
+    extern __shared__ cplx sm_coef[];  // [K][PT]
+    for (int t = threadIdx.x; t < K * PT; t += blockDim.x) {
+        const int w = t / PT, p = t - w * PT;
+        sm_coef[t] = (p < P) ? coef[(int64_t)p * K + w] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const int64_t ub = ((int64_t)blockIdx.x * blockDim.x) * UT + threadIdx.x;
+    cplx acc[UT][PT];
+#pragma unroll
+    for (int i = 0; i < UT; i++)
+#pragma unroll
+        for (int j = 0; j < PT; j++) acc[i][j] = make_double2(0.0, 0.0);
+    bool ok[UT];
+#pragma unroll
+    for (int i = 0; i < UT; i++) ok[i] = (ub + (int64_t)i * blockDim.x) < U;
+
+#pragma unroll 2
+    for (int w = 0; w < K; w++) {
+        cplx v[UT];
+#pragma unroll
+        for (int i = 0; i < UT; i++)
+            v[i] = ok[i] ? ldg(in + (int64_t)w * in_stride + ub + (int64_t)i * blockDim.x) : make_double2(0.0, 0.0);
+        const cplx *cw = sm_coef + w * PT;
+#pragma unroll
+        for (int j = 0; j < PT; j++) {
+            const cplx c = cw[j];
+#pragma unroll
+            for (int i = 0; i < UT; i++) cfma(acc[i][j], c, v[i]);
+        }
+    }
+    const double inv_h = 2.0 / (double)S;
+    for (int sidx = 0; sidx < S; sidx++) {
+        const double tau = ((double)(2 * sidx - S + 1) * 0.5) * inv_h;   // (j_s - j_c) / (S/2)
+#pragma unroll
+        for (int i = 0; i < UT; i++) {
+            cplx f = acc[i][PT - 1];
+#pragma unroll
+            for (int j = PT - 2; j >= 0; j--) {
+                f.x = fma(f.x, tau, acc[i][j].x);
+                f.y = fma(f.y, tau, acc[i][j].y);
+            }
+            if (ok[i]) out[(int64_t)sidx * out_stride + ub + (int64_t)i * blockDim.x] = f;
+        }
+    }
+}
+
+template <int PT, int UT>
+static cudaError_t idft_taylor_launch(cplx *out, int64_t out_stride, const cplx *coef, const cplx *in, int64_t in_stride,
+                                      int S, int P, int K, int64_t U, cudaStream_t s)
+{
+    const int threads = 128;
+    const size_t smem = (size_t)K * PT * sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(idft_taylor_kernel<PT, UT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((U + (int64_t)threads * UT - 1) / ((int64_t)threads * UT));
+    idft_taylor_kernel<PT, UT><<<grid, threads, smem, s>>>(out, out_stride, coef, in, in_stride, S, P, K, U);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_idft_taylor(cplx *out, int64_t out_stride, const cplx *coef, const cplx *in, int64_t in_stride, int S,
+                               int P, int K, int64_t U, cudaStream_t s)
+{
+    if (U == 0 || S == 0) return cudaSuccess;
+    if (P <= 8) return idft_taylor_launch<8, 2>(out, out_stride, coef, in, in_stride, S, P, K, U, s);
+    if (P <= 12) return idft_taylor_launch<12, 2>(out, out_stride, coef, in, in_stride, S, P, K, U, s);
+    if (P <= 16) return idft_taylor_launch<16, 2>(out, out_stride, coef, in, in_stride, S, P, K, U, s);
+    return cudaErrorInvalidValue;
 }
 
 // =====================================================================================================

@@ -49,9 +49,9 @@ struct BandedStepArgs {
     cplx *snap = nullptr;
     double dt = 0;
 };
-bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv);
+bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, int variant);
 cudaError_t launch_rk4_banded_step(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, const BandedStepArgs &a,
-                                   cudaStream_t s);
+                                   int variant, cudaStream_t s);
 
 // Twiddle coefficient tables (CreateDFTiDFTMats.c:42-58,76-84), generated on the device with exactly reduced phases.
 //   idft: coef[s][w] = (1/Ns) * exp(+2*pi*i * m(w) * j_s / (2Ns)),  j_s = (j_start + dir*s) mod 2Ns,  s < S, w < Nw_eff
@@ -64,6 +64,14 @@ cudaError_t launch_dft_coef(cplx *coef, int Nw_eff, int Nw, int64_t ResRatio, cu
 //   forcing synthesis (CreateForcingOnFly.c:17-19 batched over a chunk of half steps) and DFT (DFT.c:26-39).
 cudaError_t launch_small_cgemm(cplx *out, int64_t out_stride, const cplx *coef, const cplx *in, int64_t in_stride,
                                int S, int K, int64_t U, int variant, cudaStream_t s);
+
+// Forcing synthesis through Taylor moments about the chunk centre (see kernels.cu, K2b).  J2 = 2*j_centre (integer),
+// h = S/2.  coef: [P][K].  idft_taylor_terms(x) returns the number of terms for |m*phi*(j-j_c)| <= x, or -1.
+int idft_taylor_terms(double x);
+cudaError_t launch_idft_taylor_coef(cplx *coef, int P, int K, int64_t J2, int dir, int64_t Ns, double h, int real_op,
+                                    cudaStream_t s);
+cudaError_t launch_idft_taylor(cplx *out, int64_t out_stride, const cplx *coef, const cplx *in, int64_t in_stride, int S,
+                               int P, int K, int64_t U, cudaStream_t s);
 
 // reference (column-major, column c = a*ca + b*cb) <-> device stack T[a][row][b]
 cudaError_t launch_host_to_stack(cplx *dst, const cplx *src_colmajor, int64_t nrows, int na, int nb, int64_t ca,

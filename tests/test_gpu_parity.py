@@ -240,3 +240,27 @@ def test_full_size_properties(pkg, O):
         P = Q[:, blk] @ (Q[:, blk].conj().T @ Y1[:, blk])
         assert rel_err(P, Y1[:, blk]) < 1e-10
     r.close()
+
+
+@pytest.mark.parametrize("opts", [dict(use_banded=0, idft_variant=10), dict(use_banded=0, idft_variant=0),
+                                  dict(use_banded=1, idft_variant=10), dict(use_banded=1, stage_variant=1),
+                                  dict(use_banded=1, stage_variant=2), dict(use_banded=1, stage_variant=3),
+                                  dict(use_banded=1, chunk_steps=64), dict(use_banded=0, idft_variant=11, chunk_steps=5)])
+def test_kernel_variants_agree_with_oracle(pkg, O, A_GL, opts):
+    # every code path (stage-by-stage vs fused banded step; direct vs Taylor-moment forcing synthesis) gives the
+    # oracle's answer; Ns is large enough here (w = 0.05) for the Taylor path to be selected
+    k, Nw = 4, 6
+    dt, Ns, Nt, RR = O.setup_time_freq_grid(0.05, Nw, 0.02, 3.0)
+    v = O.Vars(N=500, k=k, Nw=Nw, Nw_eff=Nw, Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=0.05)
+    F = _forcing(500, k * Nw, 11)
+    A = A_GL.shifted(2.0)
+    r = _handle(pkg, A, v)
+    for name, val in opts.items():
+        r.set_option(name, val)
+    for direct in (True, False):
+        ref, snaps_ref = _oracle_action(O, A, v, F, direct, snaps=True)
+        r.keep_snapshots(True)
+        got = r.TSActionRK4(F, direct=direct)
+        assert rel_err(r.get_snapshots(), snaps_ref) < ACTION_TOL
+        assert rel_err(got, ref) < ACTION_TOL
+    r.close()
