@@ -43,7 +43,18 @@ struct CsrOwned {
     DevBuf rowptr, col, val;
     int64_t lo_bw = 0, hi_bw = 0;  // max (row - col), max (col - row)
     bool set = false;
-    void release() { rowptr.release(); col.release(); val.release(); d = CsrDev(); set = false; }
+    // diagonal (DIA) form for the fused sliding-window step kernel: dia[row][dia_lo+dia_hi+1]
+    DevBuf dia, tile_ok, slow_ranges;
+    int dia_lo = 0, dia_hi = 0;
+    bool dia_valid = false;
+    std::vector<unsigned char> row_regular;
+    int plan_nv = -1, plan_variant = -1, plan_mode = -1, ntiles = 0, nslow = 0;
+    bool plan_ok = false;
+    void release()
+    {
+        rowptr.release(); col.release(); val.release(); dia.release(); tile_ok.release(); slow_ranges.release();
+        d = CsrDev(); set = false; dia_valid = false; plan_nv = -1; plan_ok = false; row_regular.clear();
+    }
 };
 
 struct EventPair { cudaEvent_t a, b; };
@@ -81,7 +92,8 @@ struct rsvdt_context {
     int64_t chunk_steps = 32;
     int64_t stage_variant = 0;
     int64_t idft_variant = 0;
-    int64_t use_banded = 1;
+    int64_t use_banded = 3;   // 0: stage kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged DIA step
+    int64_t tma_variant = 0;  // 0: tiles sized for 3 CTAs/SM, 1: for 2 CTAs/SM
 
     // instrumentation
     int64_t launches = 0;
@@ -232,6 +244,86 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
     dst.lo_bw = lo;
     dst.hi_bw = hi;
     dst.set = true;
+    // ---- diagonal pattern analysis (square, narrow-band operators only) ------------------------------------------
+    if (out_rows == out_cols && lo <= 8 && hi <= 8 && out_rows >= 64) {
+        std::vector<int64_t> cnt(17, 0);
+        for (int64_t r = 0; r < out_rows; r++)
+            for (int64_t p = rp[r]; p < rp[r + 1]; p++) cnt[(size_t)(ci[p] - r + 8)]++;
+        int omin = 99, omax = -99;
+        for (int o = -8; o <= 8; o++)
+            if (2 * cnt[(size_t)(o + 8)] >= out_rows) { omin = std::min(omin, o); omax = std::max(omax, o); }
+        if (omin <= omax) {
+            const int LO = std::max(0, -omin), HI = std::max(0, omax), ND = LO + HI + 1;
+            std::vector<cplx> dia((size_t)out_rows * ND, make_double2(0.0, 0.0));
+            dst.row_regular.assign((size_t)out_rows, 1);
+            int64_t nirr = 0;
+            for (int64_t r = 0; r < out_rows; r++) {
+                bool reg = true;
+                int64_t prev = -1;
+                for (int64_t p = rp[r]; p < rp[r + 1]; p++) {
+                    const int64_t o = ci[p] - r;
+                    if (o < -LO || o > HI || ci[p] <= prev) { reg = false; break; }   // outside the window / not ascending
+                    prev = ci[p];
+                    dia[(size_t)r * ND + (size_t)(o + LO)] = va[p];
+                }
+                if (!reg) {
+                    dst.row_regular[(size_t)r] = 0;
+                    nirr++;
+                    for (int d = 0; d < ND; d++) dia[(size_t)r * ND + d] = make_double2(0.0, 0.0);
+                }
+            }
+            if (nirr * 100 <= out_rows) {
+                CU(dst.dia.alloc(dia.size() * sizeof(cplx)));
+                CU(cudaMemcpy(dst.dia.p, dia.data(), dia.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+                dst.dia_lo = LO;
+                dst.dia_hi = HI;
+                dst.dia_valid = true;
+            }
+        }
+    }
+    return RSVDT_OK;
+}
+
+// tile plan of the DIA step kernel for nv vectors: which tiles are regular, and the row ranges left to the CSR kernel
+int plan_dia(rsvdt_handle h, CsrOwned &Op, int nv, int mode)
+{
+    const int variant = (int)h->stage_variant + 16 * (int)h->tma_variant;
+    if (Op.plan_nv == nv && Op.plan_variant == variant && Op.plan_mode == mode) return RSVDT_OK;
+    Op.plan_nv = nv;
+    Op.plan_variant = variant;
+    Op.plan_mode = mode;
+    Op.plan_ok = false;
+    if (!Op.dia_valid) return RSVDT_OK;
+    if (mode == 3 ? !dia_tma_supported(Op.dia_lo, Op.dia_hi, nv, (int)h->tma_variant) : !dia_step_supported(Op.dia_lo, Op.dia_hi, nv))
+        return RSVDT_OK;
+    const int64_t N = Op.d.nrows;
+    const int TR = mode == 3 ? dia_tma_tile_rows(Op.dia_lo, Op.dia_hi, nv, (int)h->tma_variant) : dia_tile_rows(Op.dia_lo, Op.dia_hi, nv);
+    const int64_t ntiles = (N + TR - 1) / TR;
+    std::vector<int64_t> irr_prefix((size_t)N + 1, 0);
+    for (int64_t r = 0; r < N; r++) irr_prefix[(size_t)r + 1] = irr_prefix[(size_t)r] + (Op.row_regular[(size_t)r] ? 0 : 1);
+    std::vector<unsigned char> ok((size_t)ntiles, 1);
+    std::vector<int64_t> ranges;
+    const bool slow_ok = banded_step_supported(Op.d, Op.lo_bw, Op.hi_bw, nv, (int)h->stage_variant);
+    const int TRs = slow_ok ? banded_tile_rows(Op.lo_bw, Op.hi_bw, nv, (int)h->stage_variant) : 0;
+    for (int64_t t = 0; t < ntiles; t++) {
+        const int64_t r0 = t * TR, r1 = std::min(N, r0 + TR);
+        const int64_t e0 = std::max<int64_t>(0, r0 - 3 * Op.dia_lo), e1 = std::min(N, r1 + 3 * Op.dia_hi);
+        if (irr_prefix[(size_t)e1] - irr_prefix[(size_t)e0] > 0) {
+            ok[(size_t)t] = 0;
+            if (!slow_ok) return RSVDT_OK;   // no way to finish the irregular tiles: stay on the other paths
+            for (int64_t a = r0; a < r1; a += TRs) { ranges.push_back(a); ranges.push_back(std::min(r1, a + TRs)); }
+        }
+    }
+    if ((int64_t)ranges.size() / 2 > std::max<int64_t>(8, ntiles / 10)) return RSVDT_OK;   // too irregular to pay off
+    CU(Op.tile_ok.alloc((size_t)ntiles));
+    CU(cudaMemcpy(Op.tile_ok.p, ok.data(), (size_t)ntiles, cudaMemcpyHostToDevice));
+    if (!ranges.empty()) {
+        CU(Op.slow_ranges.alloc(ranges.size() * sizeof(int64_t)));
+        CU(cudaMemcpy(Op.slow_ranges.p, ranges.data(), ranges.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    Op.ntiles = (int)ntiles;
+    Op.nslow = (int)(ranges.size() / 2);
+    Op.plan_ok = true;
     return RSVDT_OK;
 }
 
@@ -328,23 +420,48 @@ int64_t snapshot_slot(const rsvdt_grid &g, bool direct, int64_t Nstore, int64_t 
     return pos_mod(pos, Nstore);
 }
 
-bool use_banded_path(rsvdt_handle h, const CsrOwned &Op, int nv)
+// 0: stage-by-stage CSR kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged fused DIA step
+// (2 and 3 leave the tiles with irregular rows to the CSR banded kernel)
+int step_path(rsvdt_handle h, CsrOwned &Op, int nv, int *path)
 {
-    return h->use_banded && banded_step_supported(Op.d, Op.lo_bw, Op.hi_bw, nv, (int)h->stage_variant);
+    *path = 0;
+    if (!h->use_banded) return RSVDT_OK;
+    if (h->use_banded >= 3) {
+        RS(plan_dia(h, Op, nv, 3));
+        if (Op.plan_ok) { *path = 3; return RSVDT_OK; }
+    }
+    if (h->use_banded >= 2) {
+        RS(plan_dia(h, Op, nv, 2));
+        if (Op.plan_ok) { *path = 2; return RSVDT_OK; }
+    }
+    if (banded_step_supported(Op.d, Op.lo_bw, Op.hi_bw, nv, (int)h->stage_variant)) *path = 1;
+    return RSVDT_OK;
 }
 
-// one whole RK4 step, dispatching between the fused banded kernel (y ping-pongs between *ycur and *ynext) and the
+// one whole RK4 step, dispatching between the fused kernels (y ping-pongs between *ycur and *ynext) and the
 // stage-by-stage kernels (in place on *ycur)
-int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, bool banded, cplx **ycur, cplx **ynext, const cplx *f_prev,
+int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **ycur, cplx **ynext, const cplx *f_prev,
                  const cplx *f_half, const cplx *f_next, cplx *snap)
 {
-    if (!banded)
+    if (path == 0)
         return rk4_step(h, Op, nv, *ycur, h->xa.as<cplx>(), h->xb.as<cplx>(), h->acc.as<cplx>(), f_prev, f_half, f_next, snap);
     Bracket br(h, &h->ev_stage);
     BandedStepArgs a;
     a.y_in = *ycur; a.y_out = *ynext; a.f_prev = f_prev; a.f_half = f_half; a.f_next = f_next; a.snap = snap; a.dt = h->g.dt;
-    CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, h->stream));
-    h->launches += 1;
+    if (path >= 2) {
+        if (path == 3)
+            CU(launch_rk4_dia_tma_step(Op.dia.as<cplx>(), Op.dia_lo, Op.dia_hi, Op.tile_ok.as<unsigned char>(), Op.ntiles, Op.d.nrows, nv, (int)h->tma_variant, a, h->stream));
+        else
+            CU(launch_rk4_dia_step(Op.dia.as<cplx>(), Op.dia_lo, Op.dia_hi, Op.tile_ok.as<unsigned char>(), Op.ntiles, Op.d.nrows, nv, a, h->stream));
+        h->launches += 1;
+        if (Op.nslow > 0) {
+            CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, Op.slow_ranges.as<int64_t>(), Op.nslow, h->stream));
+            h->launches += 1;
+        }
+    } else {
+        CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, nullptr, 0, h->stream));
+        h->launches += 1;
+    }
     std::swap(*ycur, *ynext);
     return RSVDT_OK;
 }
@@ -357,20 +474,27 @@ int64_t max_harmonic(const rsvdt_grid &g)
 }
 
 // forcing slices s = 0..Sc-1 at half-step indices j_start + dir*s  (TSRK4.c:21-27, CreateForcingOnFly.c:17-19)
-int synth_forcing(rsvdt_handle h, const cplx *Fhat, cplx *slices, int Sc, int64_t j_start, int dir)
+// prev (optional): also produce the slice at j_start - dir (the forcing at t_n of the chunk's first step, i.e. the F3
+// carried over from the previous step, TSRK4.c:18 / TSActionRK4.c:103) into *prev
+int synth_forcing(rsvdt_handle h, const cplx *Fhat, cplx *slices, int Sc, int64_t j_start, int dir, cplx *prev)
 {
     const rsvdt_grid &g = h->g;
     const int64_t U = h->N * g.k;
     Bracket br(h, &h->ev_idft);
     const double PI = 3.14159265358979323846;
     const double hh = 0.5 * (double)Sc;
-    const double x = (double)max_harmonic(g) * (PI / (double)g.Ns) * hh;
+    const double x = (double)max_harmonic(g) * (PI / (double)g.Ns) * (hh + 1.0);   // |tau| <= 1 + 1/hh with the extra slice
     const int P = (h->idft_variant >= 10 || Sc < 4) ? -1 : idft_taylor_terms(x);
     if (P > 0 && P < Sc) {
         const int64_t J2 = 2 * j_start + (int64_t)dir * (Sc - 1);
         CU(launch_idft_taylor_coef(h->coef.as<cplx>(), P, (int)g.Nw_eff, J2, dir, g.Ns, hh, g.RealOperator, h->stream));
-        CU(launch_idft_taylor(slices, U, h->coef.as<cplx>(), Fhat, U, Sc, P, (int)g.Nw_eff, U, h->stream));
+        CU(launch_idft_taylor(slices, U, h->coef.as<cplx>(), Fhat, U, Sc, P, (int)g.Nw_eff, U, prev, h->stream));
     } else {
+        if (prev) {
+            CU(launch_idft_coef(h->coef.as<cplx>(), 1, (int)g.Nw_eff, j_start - dir, 1, g.Ns, g.RealOperator, h->stream));
+            CU(launch_small_cgemm(prev, U, h->coef.as<cplx>(), Fhat, U, 1, (int)g.Nw_eff, U, 2, h->stream));
+            h->launches += 2;
+        }
         // direct contraction in tiles of at most 32 slices
         for (int s0 = 0; s0 < Sc; s0 += 32) {
             const int Sb = std::min(32, Sc - s0);
@@ -391,12 +515,14 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
                  int64_t i_end)
 {
     const rsvdt_grid &g = h->g;
-    const CsrOwned &Op = direct ? h->A : h->AH;
+    CsrOwned &Op = direct ? h->A : h->AH;
     const int nv = (int)g.k;
     const int64_t U = h->N * g.k;
     const int64_t Tc = std::max<int64_t>(1, h->chunk_steps);
     const int S = (int)(2 * Tc);
-    const bool banded = use_banded_path(h, Op, nv);
+    int path = 0;
+    RS(step_path(h, Op, nv, &path));
+    const bool banded = path != 0;
     for (int b = 0; b < 2; b++) RS(ensure(h, h->slices[b], (size_t)S * U * sizeof(cplx)));
     RS(ensure(h, h->coef, (size_t)std::max<int64_t>((int64_t)S * g.Nw_eff, g.Nw_eff * g.Nw) * sizeof(cplx)));
     RS(ensure(h, h->xa, (size_t)U * sizeof(cplx)));
@@ -407,23 +533,20 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
     cplx *ycur = y, *ynext = h->xa.as<cplx>();
 
     int cur = 0;
-    const cplx *f_carry = nullptr;  // forcing at t_n of the first step of the chunk (F3 carried over, TSRK4.c:18)
-    {
-        // initial forcing, TSActionRK4.c:103 (i_begin == 1 -> column 0) or the slice preceding i_begin
-        const int64_t j0 = direct ? 2 * (i_begin - 1) : -2 * (i_begin - 1);
-        Bracket br(h, &h->ev_idft);
-        CU(launch_idft_coef(h->coef.as<cplx>(), 1, (int)g.Nw_eff, j0, 1, g.Ns, g.RealOperator, h->stream));
-        cplx *dst = h->slices[1].as<cplx>() + (int64_t)(S - 1) * U;
-        CU(launch_small_cgemm(dst, U, h->coef.as<cplx>(), Fhat, U, 1, (int)g.Nw_eff, U, 3, h->stream));
-        h->launches += 2;
-        f_carry = dst;
-    }
+    // forcing at t_n of the first step of the chunk (F3 carried over, TSRK4.c:18); for the very first chunk it is the
+    // initial forcing of TSActionRK4.c:103, produced together with the chunk's slices
+    const cplx *f_carry = nullptr;
     for (int64_t i0 = i_begin; i0 <= i_end; i0 += Tc) {
         const int64_t nsteps = std::min(Tc, i_end - i0 + 1);
         const int Sc = (int)(2 * nsteps);
         cplx *sl = h->slices[cur].as<cplx>();
         const int64_t j_start = direct ? 2 * (i0 - 1) + 1 : -1 - 2 * (i0 - 1);
-        RS(synth_forcing(h, Fhat, sl, Sc, j_start, direct ? 1 : -1));
+        cplx *first_prev = nullptr;
+        if (!f_carry) {
+            first_prev = h->slices[1].as<cplx>() + (int64_t)(S - 1) * U;   // a slot of the other buffer, free until chunk 2
+            f_carry = first_prev;
+        }
+        RS(synth_forcing(h, Fhat, sl, Sc, j_start, direct ? 1 : -1, first_prev));
         for (int64_t c = 0; c < nsteps; c++) {
             const int64_t i = i0 + c;
             const cplx *f_prev = (c == 0) ? f_carry : sl + (2 * c - 1) * U;
@@ -434,7 +557,7 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
                 const int64_t slot = snapshot_slot(g, direct, Nstore, i);
                 if (slot >= 0) snap = snaps + slot * U;
             }
-            RS(rk4_step_any(h, Op, nv, banded, &ycur, &ynext, f_prev, f_half, f_next, snap));
+            RS(rk4_step_any(h, Op, nv, path, &ycur, &ynext, f_prev, f_half, f_next, snap));
         }
         f_carry = sl + (int64_t)(Sc - 1) * U;
         cur ^= 1;
@@ -446,16 +569,18 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
 // unforced steps on a block of nv vectors (TSTransRK4.c:15-36)
 int unforced_steps(rsvdt_handle h, bool direct, int nv, cplx *y, int64_t nsteps)
 {
-    const CsrOwned &Op = direct ? h->A : h->AH;
+    CsrOwned &Op = direct ? h->A : h->AH;
     const int64_t U = h->N * nv;
-    const bool banded = use_banded_path(h, Op, nv);
+    int path = 0;
+    RS(step_path(h, Op, nv, &path));
+    const bool banded = path != 0;
     RS(ensure(h, h->xa, (size_t)U * sizeof(cplx)));
     if (!banded) {
         RS(ensure(h, h->xb, (size_t)U * sizeof(cplx)));
         RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
     }
     cplx *ycur = y, *ynext = h->xa.as<cplx>();
-    for (int64_t i = 0; i < nsteps; i++) RS(rk4_step_any(h, Op, nv, banded, &ycur, &ynext, nullptr, nullptr, nullptr, nullptr));
+    for (int64_t i = 0; i < nsteps; i++) RS(rk4_step_any(h, Op, nv, path, &ycur, &ynext, nullptr, nullptr, nullptr, nullptr));
     if (ycur != y) CU(cudaMemcpyAsync(y, ycur, (size_t)U * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
     return RSVDT_OK;
 }
@@ -971,6 +1096,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "stage_variant")) h->stage_variant = value;
     else if (!strcmp(name, "idft_variant")) h->idft_variant = value;
     else if (!strcmp(name, "use_banded")) h->use_banded = value;
+    else if (!strcmp(name, "tma_variant")) h->tma_variant = value;
     else return fail(h, RSVDT_ERR_ARG, "unknown option '%s'", name);
     return RSVDT_OK;
 }

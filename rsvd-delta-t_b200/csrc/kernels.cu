@@ -104,12 +104,15 @@ cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs
 template <int BT, int UPT, int MINB, bool FORCED>
 __global__ void __launch_bounds__(BT, MINB)
 rk4_banded_step_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const cplx *__restrict__ val,
-                       int64_t N, int nv, int b, int TR, int E0, BandedStepArgs a)
+                       int64_t N, int nv, int b, int TR, int E0, const int64_t *__restrict__ ranges, BandedStepArgs a)
 {
     extern __shared__ cplx sm[];
     const int n_e = E0 * nv;
     cplx *Y = sm, *B1 = sm + n_e, *B2 = sm + 2 * n_e;
-    const int64_t base = (int64_t)blockIdx.x * TR - 4 * b;  // global row of local row 0 (may be negative)
+    // owned rows: [row0, row0 + nown) -- either the regular tiling or an explicit list of row ranges
+    const int64_t row0 = ranges ? ranges[2 * blockIdx.x] : (int64_t)blockIdx.x * TR;
+    const int nown = ranges ? (int)(ranges[2 * blockIdx.x + 1] - row0) : TR;
+    const int64_t base = row0 - 4 * b;  // global row of local row 0 (may be negative)
     const double dt = a.dt;
     const double c_half = dt / 2, c_full = dt, w1 = dt / 6, w2 = dt / 6 * 2;  // TSRK4.c:30-34,44-47
 
@@ -187,7 +190,7 @@ rk4_banded_step_kernel(const int64_t *__restrict__ rowptr, const int32_t *__rest
 #pragma unroll
     for (int i = 0; i < UPT; i++) {
         const int lr = lrow[i];
-        if (valid[i] && lr >= 4 * b && lr < E0 - 4 * b) {
+        if (valid[i] && lr >= 4 * b && lr < 4 * b + nown) {
             const int64_t gr = base + lr;
             const int64_t gu = gr * nv + liv[i];
             cplx s = make_double2(0.0, 0.0);
@@ -216,22 +219,24 @@ inline BandedCfg banded_cfg(int variant)
 inline int banded_E0(int variant, int nv) { const BandedCfg c = banded_cfg(variant); return (c.bt * c.upt) / nv; }
 
 template <int BT, int UPT, int MINB>
-cudaError_t banded_launch(const CsrDev &Op, int b, int nv, int E0, const BandedStepArgs &a, cudaStream_t s)
+cudaError_t banded_launch(const CsrDev &Op, int b, int nv, int E0, const BandedStepArgs &a, const int64_t *ranges,
+                          int nranges, cudaStream_t s)
 {
     const int TR = E0 - 8 * b;
     const size_t smem = (size_t)3 * E0 * nv * sizeof(cplx);
-    const unsigned grid = (unsigned)((Op.nrows + TR - 1) / TR);
+    const unsigned grid = ranges ? (unsigned)nranges : (unsigned)((Op.nrows + TR - 1) / TR);
+    if (grid == 0) return cudaSuccess;
     cudaError_t e;
     if (a.f_prev) {
         auto kfn = rk4_banded_step_kernel<BT, UPT, MINB, true>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kfn<<<grid, BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, a);
+        kfn<<<grid, BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, ranges, a);
     } else {
         auto kfn = rk4_banded_step_kernel<BT, UPT, MINB, false>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kfn<<<grid, BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, a);
+        kfn<<<grid, BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, ranges, a);
     }
     return cudaGetLastError();
 }
@@ -246,18 +251,462 @@ bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int n
     return b >= 1 && 8 * b * 4 <= E0;
 }
 
+int banded_tile_rows(int64_t lo_bw, int64_t hi_bw, int nv, int variant)
+{
+    const int b = (int)(lo_bw > hi_bw ? lo_bw : hi_bw);
+    return banded_E0(variant, nv) - 8 * b;
+}
+
 cudaError_t launch_rk4_banded_step(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, const BandedStepArgs &a,
-                                   int variant, cudaStream_t s)
+                                   int variant, const int64_t *ranges, int nranges, cudaStream_t s)
 {
     const int b = (int)(lo_bw > hi_bw ? lo_bw : hi_bw);
     const int E0 = banded_E0(variant, nv);
     if (E0 - 8 * b <= 0) return cudaErrorInvalidValue;
     switch (variant) {
-        case 1: return banded_launch<512, 4, 1>(Op, b, nv, E0, a, s);
-        case 2: return banded_launch<512, 3, 2>(Op, b, nv, E0, a, s);
-        case 3: return banded_launch<256, 6, 3>(Op, b, nv, E0, a, s);
-        default: return banded_launch<512, 4, 2>(Op, b, nv, E0, a, s);
+        case 1: return banded_launch<512, 4, 1>(Op, b, nv, E0, a, ranges, nranges, s);
+        case 2: return banded_launch<512, 3, 2>(Op, b, nv, E0, a, ranges, nranges, s);
+        case 3: return banded_launch<256, 6, 3>(Op, b, nv, E0, a, ranges, nranges, s);
+        default: return banded_launch<512, 4, 2>(Op, b, nv, E0, a, ranges, nranges, s);
     }
+}
+
+// =====================================================================================================
+// K1c: the fused RK4 step for operators whose rows (almost all) follow one diagonal pattern (offsets -LO..+HI):
+//   the operator is stored by diagonals (DIA: dia[row][LO+HI+1], no column indices), a thread owns R consecutive rows of
+//   one test vector and keeps the R+LO+HI gathered entries of the stage vector in registers (sliding window), so the
+//   shared-memory traffic per row drops from (LO+HI+1) to (R+LO+HI)/R loads and the A entries come from a shared tile.
+//   Tiles that contain a row outside the pattern (e.g. the boundary rows of the Ginzburg-Landau operator) are skipped
+//   here (tile_ok == 0) and handled by the CSR kernel above on an explicit row-range list.
+//   Halo: 4*LO rows on the left, 4*HI on the right.
+// =====================================================================================================
+template <int LO, int HI, int R, bool FORCED>
+__global__ void __launch_bounds__(448, 2)
+rk4_dia_step_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict__ tile_ok, int64_t N, int nv, int nq,
+                    int TR, BandedStepArgs a)
+{
+    constexpr int ND = LO + HI + 1, WN = R + LO + HI;
+    if (!tile_ok[blockIdx.x]) return;
+    extern __shared__ cplx sm[];
+    // Shared layout, bank-conflict free for every access of the stage loops: a tile row lr = q*R + rr of a block vector
+    // lives at slot  rr*TP + q*nv + iv  ("rr-major"): the threads (q, iv) of a warp are consecutive in q*nv + iv, so both
+    // their own rows and the neighbouring row blocks (q-1, q+1) are contiguous runs of 16-byte slots.  The operator tile
+    // is stored as [rr][d][q] for the same reason (lanes of one row block broadcast, different blocks hit different banks).
+    const int T = nq * nv;
+    const int TP = T + ((nv - T) & 7);          // TP == nv (mod 8): consecutive rows continue the bank sequence
+    const int E0 = nq * R, n_e = E0 * nv;
+    cplx *BA = sm, *BB = sm + R * TP, *Asm = sm + 2 * R * TP;   // BA: y then x3 ; BB: x2 then x4
+    const int64_t base = (int64_t)blockIdx.x * TR - 4 * LO;
+    const double dt = a.dt;
+    const double c_half = dt / 2, c_full = dt, w1 = dt / 6, w2 = dt / 6 * 2;
+
+    {   // cooperative, coalesced tile loads: the tile of a block vector / of dia is contiguous in global memory
+        const int64_t g0 = base * nv, gN = N * nv;
+        for (int e = threadIdx.x; e < n_e; e += blockDim.x) {
+            const int64_t g = g0 + e;
+            const int lr = e / nv, iv = e - lr * nv;
+            const int qq = lr / R, rr = lr - qq * R;
+            BA[rr * TP + qq * nv + iv] = (g >= 0 && g < gN) ? ldg(a.y_in + g) : make_double2(0.0, 0.0);
+        }
+        const int64_t d0 = base * ND, dN = N * ND;
+        for (int e = threadIdx.x; e < E0 * ND; e += blockDim.x) {
+            const int64_t g = d0 + e;
+            const int lr = e / ND, d = e - lr * ND;
+            const int qq = lr / R, rr = lr - qq * R;
+            Asm[(rr * ND + d) * nq + qq] = (g >= 0 && g < dN) ? ldg(dia + g) : make_double2(0.0, 0.0);
+        }
+    }
+    __syncthreads();
+    const bool active = threadIdx.x < T;
+    const int q = active ? threadIdx.x / nv : 0;
+    const int iv = active ? threadIdx.x - q * nv : 0;
+    const int r_first = q * R;
+    const int t = q * nv + iv;   // == threadIdx.x for active threads
+    cplx yo[R], acc[R];
+#pragma unroll
+    for (int rr = 0; rr < R; rr++) {
+        yo[rr] = BA[rr * TP + t];
+        acc[rr] = yo[rr];
+    }
+
+    // window slot of tile row (r_first - LO + j): previous / own / next row block
+    // stages 1..3 (k_s on every tile row; rows of the outer halo hold don't-care values that never reach owned rows)
+#pragma unroll
+    for (int st = 1; st <= 3; st++) {
+        const cplx *Xin = (st == 2) ? BB : BA;
+        cplx *Xout = (st == 2) ? BA : BB;
+        const cplx *fsl = (st == 1) ? a.f_prev : a.f_half;
+        const double cx = (st == 3) ? c_full : c_half;
+        const double ca = (st == 1) ? w1 : w2;
+        if (active) {
+            cplx xw[WN];
+#pragma unroll
+            for (int j = 0; j < WN; j++) {
+                // j - LO in [-LO, R+HI): row block offset and row-in-block are compile-time
+                const int off = j - LO;
+                const int dq = (off < 0) ? -1 : (off >= R ? 1 : 0);
+                const int rr2 = off - dq * R;
+                const int q2 = q + dq;
+                xw[j] = (q2 >= 0 && q2 < nq) ? Xin[rr2 * TP + t + dq * nv] : make_double2(0.0, 0.0);
+            }
+            cplx xo[R];
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) {
+                const int lr = r_first + rr;
+                const int64_t gr = base + lr;
+                cplx s = make_double2(0.0, 0.0);
+                if (FORCED && lr >= st * LO && lr < E0 - st * HI && gr >= 0 && gr < N) s = ldg(fsl + gr * nv + iv);
+#pragma unroll
+                for (int d = 0; d < ND; d++) cfma(s, Asm[(rr * ND + d) * nq + q], xw[rr + d]);
+                xo[rr] = make_double2(fma(cx, s.x, yo[rr].x), fma(cx, s.y, yo[rr].y));
+                acc[rr] = make_double2(fma(ca, s.x, acc[rr].x), fma(ca, s.y, acc[rr].y));
+            }
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) Xout[rr * TP + t] = xo[rr];
+        }
+        __syncthreads();
+    }
+    // stage 4 on the owned rows
+    if (active) {
+        cplx xw[WN];
+#pragma unroll
+        for (int j = 0; j < WN; j++) {
+            const int off = j - LO;
+            const int dq = (off < 0) ? -1 : (off >= R ? 1 : 0);
+            const int rr2 = off - dq * R;
+            const int q2 = q + dq;
+            xw[j] = (q2 >= 0 && q2 < nq) ? BB[rr2 * TP + t + dq * nv] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; rr++) {
+            const int lr = r_first + rr;
+            const int64_t gr = base + lr;
+            if (lr >= 4 * LO && lr < 4 * LO + TR && gr < N) {
+                const int64_t gu = gr * nv + iv;
+                cplx s = make_double2(0.0, 0.0);
+                if (FORCED) s = ldg(a.f_next + gu);
+#pragma unroll
+                for (int d = 0; d < ND; d++) cfma(s, Asm[(rr * ND + d) * nq + q], xw[rr + d]);
+                const cplx yn = make_double2(fma(w1, s.x, acc[rr].x), fma(w1, s.y, acc[rr].y));
+                a.y_out[gu] = yn;
+                if (a.snap) a.snap[gu] = yn;
+            }
+        }
+    }
+}
+
+// ---- TMA (cp.async.bulk) + mbarrier helpers -------------------------------------------------------------------
+DEVFN unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+DEVFN void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DEVFN void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVFN void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+DEVFN void tma_load_1d(void *sdst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+DEVFN void tma_store_1d(void *gdst, const void *ssrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+DEVFN void tma_store_commit_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+DEVFN void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// =====================================================================================================
+// K1d: the DIA fused step with TMA-staged tiles.  All inputs of a tile -- y, the operator diagonals and the three
+//   forcing slices -- are contiguous ranges of global memory, so one elected thread brings them into shared memory with
+//   five bulk copies (cp.async.bulk -> mbarrier) issued up front; with 2-3 CTAs resident per SM the whole input of the
+//   next tile is in flight while the current one computes, which is what it takes to keep HBM busy (the CTA would
+//   otherwise expose one DRAM round trip per stage).  y_{n+1} (and the snapshot) leave through bulk stores.
+//   Natural [row][iv] tile layout; R is chosen so that (R-1)*nv is a multiple of 8, which makes the row-block stride
+//   R*nv congruent to nv modulo the 8 16-byte slots of a shared-memory wavefront: conflict-free sliding-window accesses.
+// =====================================================================================================
+template <int LO, int HI, int R, int MINB, bool FORCED>
+__global__ void __launch_bounds__(MINB >= 3 ? 192 : 320, MINB)
+rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict__ tile_ok, int64_t N, int nv, int nq,
+                   int TR, BandedStepArgs a)
+{
+    constexpr int ND = LO + HI + 1, WN = R + LO + HI;
+    if (!tile_ok[blockIdx.x]) return;
+    extern __shared__ __align__(128) cplx sm[];
+    const int T = nq * nv, E0 = nq * R, n_e = E0 * nv;
+    cplx *BA = sm;                      // y, later x3, finally y_{n+1}
+    cplx *BB = BA + n_e;                // x2, later x4
+    cplx *At = BB + n_e;                // operator diagonals [row][d]
+    cplx *Fp = At + E0 * ND, *Fh = Fp + n_e, *Fn = Fh + n_e;   // forcing tiles (FORCED only)
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(FORCED ? (Fn + n_e) : Fp);
+    const int64_t base = (int64_t)blockIdx.x * TR - 4 * LO;
+    const int lr_lo = (int)max((int64_t)0, -base), lr_hi = (int)min((int64_t)E0, N - base);   // tile rows inside [0, N)
+    const double dt = a.dt;
+    const double c_half = dt / 2, c_full = dt, w1 = dt / 6, w2 = dt / 6 * 2;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_proxy_async();
+    }
+    // rows of the tile outside the matrix: zero (disjoint from the bulk-copy destinations)
+    if (lr_lo > 0 || lr_hi < E0) {
+        for (int e = threadIdx.x; e < n_e; e += blockDim.x) {
+            const int lr = e / nv;
+            if (lr < lr_lo || lr >= lr_hi) {
+                BA[e] = make_double2(0.0, 0.0);
+                if (FORCED) { Fp[e] = BA[e]; Fh[e] = BA[e]; Fn[e] = BA[e]; }
+            }
+        }
+        for (int e = threadIdx.x; e < E0 * ND; e += blockDim.x) {
+            const int lr = e / ND;
+            if (lr < lr_lo || lr >= lr_hi) At[e] = make_double2(0.0, 0.0);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned vb = (unsigned)(lr_hi - lr_lo) * nv * sizeof(cplx), ab = (unsigned)(lr_hi - lr_lo) * ND * sizeof(cplx);
+        const int64_t g = (base + lr_lo) * nv;
+        mbar_expect_tx(bar, vb * (FORCED ? 4u : 1u) + ab);
+        tma_load_1d(BA + lr_lo * nv, a.y_in + g, vb, bar);
+        tma_load_1d(At + lr_lo * ND, dia + (base + lr_lo) * ND, ab, bar);
+        if (FORCED) {
+            tma_load_1d(Fp + lr_lo * nv, a.f_prev + g, vb, bar);
+            tma_load_1d(Fh + lr_lo * nv, a.f_half + g, vb, bar);
+            tma_load_1d(Fn + lr_lo * nv, a.f_next + g, vb, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+
+    const bool active = threadIdx.x < T;
+    const int q = active ? threadIdx.x / nv : 0;
+    const int iv = active ? threadIdx.x - q * nv : 0;
+    const int r_first = q * R;
+    const int own = r_first * nv + iv;   // slot of the thread's first row; consecutive rows are nv slots apart
+    cplx yo[R], acc[R];
+#pragma unroll
+    for (int rr = 0; rr < R; rr++) {
+        yo[rr] = BA[own + rr * nv];
+        acc[rr] = yo[rr];
+    }
+#pragma unroll
+    for (int st = 1; st <= 3; st++) {
+        const cplx *Xin = (st == 2) ? BB : BA;
+        cplx *Xout = (st == 2) ? BA : BB;
+        const cplx *fsl = (st == 1) ? Fp : Fh;
+        const double cx = (st == 3) ? c_full : c_half;
+        const double ca = (st == 1) ? w1 : w2;
+        cplx xo[R];
+        if (active) {
+            cplx xw[WN];
+#pragma unroll
+            for (int j = 0; j < WN; j++) {
+                const int lr = r_first - LO + j;
+                xw[j] = (lr >= 0 && lr < E0) ? Xin[own + (j - LO) * nv] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) {
+                cplx s = make_double2(0.0, 0.0);
+                if (FORCED) s = fsl[own + rr * nv];
+                const cplx *ar = At + (r_first + rr) * ND;
+#pragma unroll
+                for (int d = 0; d < ND; d++) cfma(s, ar[d], xw[rr + d]);
+                xo[rr] = make_double2(fma(cx, s.x, yo[rr].x), fma(cx, s.y, yo[rr].y));
+                acc[rr] = make_double2(fma(ca, s.x, acc[rr].x), fma(ca, s.y, acc[rr].y));
+            }
+        }
+        if (st == 1) __syncthreads();   // every thread has read its y window before BA... (BA is written in stage 2 only)
+        if (active) {
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) Xout[own + rr * nv] = xo[rr];
+        }
+        __syncthreads();
+    }
+    // stage 4 on the owned rows; y_{n+1} goes to BA (x3 is dead) and leaves through a bulk store
+    if (active) {
+        cplx xw[WN];
+#pragma unroll
+        for (int j = 0; j < WN; j++) {
+            const int lr = r_first - LO + j;
+            xw[j] = (lr >= 0 && lr < E0) ? BB[own + (j - LO) * nv] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; rr++) {
+            const int lr = r_first + rr;
+            if (lr >= 4 * LO && lr < 4 * LO + TR) {
+                cplx s = make_double2(0.0, 0.0);
+                if (FORCED) s = Fn[own + rr * nv];
+                const cplx *ar = At + lr * ND;
+#pragma unroll
+                for (int d = 0; d < ND; d++) cfma(s, ar[d], xw[rr + d]);
+                BA[own + rr * nv] = make_double2(fma(w1, s.x, acc[rr].x), fma(w1, s.y, acc[rr].y));
+            }
+        }
+    }
+    fence_proxy_async();   // make the generic-proxy writes to BA visible to the bulk-copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int o_lo = 4 * LO, o_hi = min(4 * LO + TR, lr_hi);
+        if (o_hi > o_lo) {
+            const unsigned ob = (unsigned)(o_hi - o_lo) * nv * sizeof(cplx);
+            const int64_t g = (base + o_lo) * nv;
+            tma_store_1d(a.y_out + g, BA + o_lo * nv, ob);
+            if (a.snap) tma_store_1d(a.snap + g, BA + o_lo * nv, ob);
+            tma_store_commit_wait();
+        }
+    }
+}
+
+namespace {
+// R with (R-1)*nv a multiple of 8 (see above); 0 if none of the instantiated values fits
+inline int tma_R(int nv)
+{
+    const int cand[3] = {4, 5, 3};
+    for (int r : cand)
+        if (((r - 1) * nv) % 8 == 0) return r;
+    return 0;
+}
+inline int tma_nq(int nv, int R, int nd, bool forced, int minb)
+{
+    // shared memory per CTA = ((nbuf*nv + nd) * E0) * 16 + 16, E0 = R*nq; threads = nq*nv <= 192 (3 CTAs/SM) or 320 (2)
+    const int budget = (minb >= 3 ? 74 : 112) * 1024;
+    const int per_row = ((forced ? 5 : 2) * nv + nd) * 16;
+    int nq = (budget - 64) / (per_row * R);
+    const int tmax = (minb >= 3 ? 192 : 320) / nv;
+    return nq < tmax ? nq : tmax;
+}
+
+template <int LO, int HI, int R, int MINB>
+cudaError_t dia_tma_launch(const cplx *dia, const unsigned char *tile_ok, int ntiles, int64_t N, int nv, int nq,
+                           const BandedStepArgs &a, cudaStream_t s)
+{
+    const int E0 = nq * R;
+    const int TR = E0 - 4 * (LO + HI);
+    const bool forced = a.f_prev != nullptr;
+    const size_t smem = ((size_t)(forced ? 5 : 2) * E0 * nv + (size_t)E0 * (LO + HI + 1)) * sizeof(cplx) + 16;
+    const int threads = ((nq * nv + 31) / 32) * 32;
+    cudaError_t e;
+    if (forced) {
+        auto kfn = rk4_dia_tma_kernel<LO, HI, R, MINB, true>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<(unsigned)ntiles, threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
+    } else {
+        auto kfn = rk4_dia_tma_kernel<LO, HI, R, MINB, false>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<(unsigned)ntiles, threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
+    }
+    return cudaGetLastError();
+}
+
+template <int LO, int HI, int MINB>
+cudaError_t dia_tma_dispatch_R(int R, const cplx *dia, const unsigned char *tile_ok, int ntiles, int64_t N, int nv, int nq,
+                               const BandedStepArgs &a, cudaStream_t s)
+{
+    if (R == 3) return dia_tma_launch<LO, HI, 3, MINB>(dia, tile_ok, ntiles, N, nv, nq, a, s);
+    if (R == 4) return dia_tma_launch<LO, HI, 4, MINB>(dia, tile_ok, ntiles, N, nv, nq, a, s);
+    if (R == 5) return dia_tma_launch<LO, HI, 5, MINB>(dia, tile_ok, ntiles, N, nv, nq, a, s);
+    return cudaErrorInvalidValue;
+}
+}  // namespace
+
+// variant: 0 -> 3 CTAs/SM tiles, 1 -> 2 CTAs/SM tiles.  The tile height must not depend on `forced` (the plan is shared),
+// so it is always sized for the forced case.
+bool dia_tma_supported(int lo, int hi, int nv, int variant)
+{
+    const bool combo = (lo == 1 && hi == 1) || (lo == 2 && hi == 1) || (lo == 1 && hi == 2) || (lo == 2 && hi == 2);
+    const int R = tma_R(nv);
+    if (!combo || R == 0 || nv > 64) return false;
+    const int nq = tma_nq(nv, R, lo + hi + 1, true, variant == 1 ? 2 : 3);
+    return nq >= 2 && 4 * (lo + hi) * 4 <= nq * R;
+}
+
+int dia_tma_tile_rows(int lo, int hi, int nv, int variant)
+{
+    const int R = tma_R(nv);
+    return tma_nq(nv, R, lo + hi + 1, true, variant == 1 ? 2 : 3) * R - 4 * (lo + hi);
+}
+
+cudaError_t launch_rk4_dia_tma_step(const cplx *dia, int lo, int hi, const unsigned char *tile_ok, int ntiles, int64_t N,
+                                    int nv, int variant, const BandedStepArgs &a, cudaStream_t s)
+{
+    const int R = tma_R(nv);
+    const int minb = variant == 1 ? 2 : 3;
+    const int nq = tma_nq(nv, R, lo + hi + 1, true, minb);
+#define DISPATCH(L, H)                                                                                    \
+    if (lo == L && hi == H)                                                                               \
+        return minb == 2 ? dia_tma_dispatch_R<L, H, 2>(R, dia, tile_ok, ntiles, N, nv, nq, a, s)          \
+                         : dia_tma_dispatch_R<L, H, 3>(R, dia, tile_ok, ntiles, N, nv, nq, a, s);
+    DISPATCH(1, 1)
+    DISPATCH(2, 1)
+    DISPATCH(1, 2)
+    DISPATCH(2, 2)
+#undef DISPATCH
+    return cudaErrorInvalidValue;
+}
+
+namespace {
+constexpr int DIA_R = 4;
+inline int dia_nq(int nv) { return 448 / nv; }
+
+template <int LO, int HI>
+cudaError_t dia_launch(const cplx *dia, const unsigned char *tile_ok, int ntiles, int64_t N, int nv,
+                       const BandedStepArgs &a, cudaStream_t s)
+{
+    const int nq = dia_nq(nv);
+    const int E0 = nq * DIA_R;
+    const int TR = E0 - 4 * (LO + HI);
+    const int T = nq * nv, TP = T + ((nv - T) & 7);
+    const size_t smem = ((size_t)2 * DIA_R * TP + (size_t)E0 * (LO + HI + 1)) * sizeof(cplx);
+    const int threads = ((T + 31) / 32) * 32;
+    cudaError_t e;
+    if (a.f_prev) {
+        auto kfn = rk4_dia_step_kernel<LO, HI, DIA_R, true>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<(unsigned)ntiles, threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
+    } else {
+        auto kfn = rk4_dia_step_kernel<LO, HI, DIA_R, false>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<(unsigned)ntiles, threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
+    }
+    return cudaGetLastError();
+}
+}  // namespace
+
+bool dia_step_supported(int lo, int hi, int nv)
+{
+    if (nv <= 0 || nv > 60) return false;
+    const bool combo = (lo == 1 && hi == 1) || (lo == 2 && hi == 1) || (lo == 1 && hi == 2) || (lo == 2 && hi == 2);
+    if (!combo) return false;
+    const int E0 = dia_nq(nv) * DIA_R;
+    return 4 * (lo + hi) * 4 <= E0;   // halo at most a quarter of the tile
+}
+
+int dia_tile_rows(int lo, int hi, int nv) { return dia_nq(nv) * DIA_R - 4 * (lo + hi); }
+
+cudaError_t launch_rk4_dia_step(const cplx *dia, int lo, int hi, const unsigned char *tile_ok, int ntiles, int64_t N, int nv,
+                                const BandedStepArgs &a, cudaStream_t s)
+{
+    if (lo == 1 && hi == 1) return dia_launch<1, 1>(dia, tile_ok, ntiles, N, nv, a, s);
+    if (lo == 2 && hi == 1) return dia_launch<2, 1>(dia, tile_ok, ntiles, N, nv, a, s);
+    if (lo == 1 && hi == 2) return dia_launch<1, 2>(dia, tile_ok, ntiles, N, nv, a, s);
+    if (lo == 2 && hi == 2) return dia_launch<2, 2>(dia, tile_ok, ntiles, N, nv, a, s);
+    return cudaErrorInvalidValue;
 }
 
 // =====================================================================================================
@@ -442,33 +891,69 @@ cudaError_t launch_idft_taylor_coef(cplx *coef, int P, int K, int64_t J2, int di
     return cudaGetLastError();
 }
 
-template <int PT, int UT>
+// cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass L1 and the register file
+DEVFN void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+DEVFN void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NPEND> DEVFN void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory"); }
+
+// Each thread streams its own UT units of Fhat through a private STAGES-deep shared-memory ring (no block-level
+// synchronisation in the loop): enough bytes in flight to cover HBM latency at 3-4 resident CTAs per SM.
+template <int PT, int UT, int STAGES>
 __global__ void __launch_bounds__(128)
 idft_taylor_kernel(cplx *__restrict__ out, int64_t out_stride, const cplx *__restrict__ coef,
-                   const cplx *__restrict__ in, int64_t in_stride, int S, int P, int K, int64_t U)
+                   const cplx *__restrict__ in, int64_t in_stride, int S, int P, int K, int64_t U, cplx *__restrict__ out_prev)
 {
-    extern __shared__ cplx sm_coef[];  // [K][PT]
+    extern __shared__ cplx sm_dyn[];
+    cplx *sm_coef = sm_dyn;                 // [K][PT]
+    cplx *ring = sm_dyn + (size_t)K * PT;   // [STAGES][UT][128]
     for (int t = threadIdx.x; t < K * PT; t += blockDim.x) {
         const int w = t / PT, p = t - w * PT;
         sm_coef[t] = (p < P) ? coef[(int64_t)p * K + w] : make_double2(0.0, 0.0);
     }
-    __syncthreads();
     const int64_t ub = ((int64_t)blockIdx.x * blockDim.x) * UT + threadIdx.x;
+    bool ok[UT];
+#pragma unroll
+    for (int i = 0; i < UT; i++) ok[i] = (ub + (int64_t)i * blockDim.x) < U;
+    // out-of-range lanes read zeros from their (never written) ring slots
+#pragma unroll
+    for (int i = 0; i < UT; i++)
+        if (!ok[i])
+            for (int st = 0; st < STAGES; st++) ring[(st * UT + i) * 128 + threadIdx.x] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; st++) {
+        if (st < K) {
+#pragma unroll
+            for (int i = 0; i < UT; i++)
+                if (ok[i]) cp_async16(ring + (st * UT + i) * 128 + threadIdx.x, in + (int64_t)st * in_stride + ub + (int64_t)i * blockDim.x);
+        }
+        cp_async_commit();
+    }
+    __syncthreads();   // coefficient table ready
+
     cplx acc[UT][PT];
 #pragma unroll
     for (int i = 0; i < UT; i++)
 #pragma unroll
         for (int j = 0; j < PT; j++) acc[i][j] = make_double2(0.0, 0.0);
-    bool ok[UT];
-#pragma unroll
-    for (int i = 0; i < UT; i++) ok[i] = (ub + (int64_t)i * blockDim.x) < U;
 
-#pragma unroll 2
     for (int w = 0; w < K; w++) {
+        const int wn = w + STAGES - 1;
+        if (wn < K) {
+            const int st = wn % STAGES;
+#pragma unroll
+            for (int i = 0; i < UT; i++)
+                if (ok[i]) cp_async16(ring + (st * UT + i) * 128 + threadIdx.x, in + (int64_t)wn * in_stride + ub + (int64_t)i * blockDim.x);
+        }
+        cp_async_commit();
+        cp_async_wait<STAGES - 1>();   // the group that carried slice w has landed (own data: no barrier needed)
+        const int sc = w % STAGES;
         cplx v[UT];
 #pragma unroll
-        for (int i = 0; i < UT; i++)
-            v[i] = ok[i] ? ldg(in + (int64_t)w * in_stride + ub + (int64_t)i * blockDim.x) : make_double2(0.0, 0.0);
+        for (int i = 0; i < UT; i++) v[i] = ring[(sc * UT + i) * 128 + threadIdx.x];
         const cplx *cw = sm_coef + w * PT;
 #pragma unroll
         for (int j = 0; j < PT; j++) {
@@ -478,7 +963,7 @@ idft_taylor_kernel(cplx *__restrict__ out, int64_t out_stride, const cplx *__res
         }
     }
     const double inv_h = 2.0 / (double)S;
-    for (int sidx = 0; sidx < S; sidx++) {
+    for (int sidx = out_prev ? -1 : 0; sidx < S; sidx++) {
         const double tau = ((double)(2 * sidx - S + 1) * 0.5) * inv_h;   // (j_s - j_c) / (S/2)
 #pragma unroll
         for (int i = 0; i < UT; i++) {
@@ -488,31 +973,34 @@ idft_taylor_kernel(cplx *__restrict__ out, int64_t out_stride, const cplx *__res
                 f.x = fma(f.x, tau, acc[i][j].x);
                 f.y = fma(f.y, tau, acc[i][j].y);
             }
-            if (ok[i]) out[(int64_t)sidx * out_stride + ub + (int64_t)i * blockDim.x] = f;
+            if (ok[i]) {
+                if (sidx < 0) out_prev[ub + (int64_t)i * blockDim.x] = f;
+                else out[(int64_t)sidx * out_stride + ub + (int64_t)i * blockDim.x] = f;
+            }
         }
     }
 }
 
-template <int PT, int UT>
+template <int PT, int UT, int STAGES>
 static cudaError_t idft_taylor_launch(cplx *out, int64_t out_stride, const cplx *coef, const cplx *in, int64_t in_stride,
-                                      int S, int P, int K, int64_t U, cudaStream_t s)
+                                      int S, int P, int K, int64_t U, cplx *out_prev, cudaStream_t s)
 {
     const int threads = 128;
-    const size_t smem = (size_t)K * PT * sizeof(cplx);
-    cudaError_t e = cudaFuncSetAttribute(idft_taylor_kernel<PT, UT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = ((size_t)K * PT + (size_t)STAGES * UT * 128) * sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(idft_taylor_kernel<PT, UT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((U + (int64_t)threads * UT - 1) / ((int64_t)threads * UT));
-    idft_taylor_kernel<PT, UT><<<grid, threads, smem, s>>>(out, out_stride, coef, in, in_stride, S, P, K, U);
+    idft_taylor_kernel<PT, UT, STAGES><<<grid, threads, smem, s>>>(out, out_stride, coef, in, in_stride, S, P, K, U, out_prev);
     return cudaGetLastError();
 }
 
 cudaError_t launch_idft_taylor(cplx *out, int64_t out_stride, const cplx *coef, const cplx *in, int64_t in_stride, int S,
-                               int P, int K, int64_t U, cudaStream_t s)
+                               int P, int K, int64_t U, cplx *out_prev, cudaStream_t s)
 {
     if (U == 0 || S == 0) return cudaSuccess;
-    if (P <= 8) return idft_taylor_launch<8, 2>(out, out_stride, coef, in, in_stride, S, P, K, U, s);
-    if (P <= 12) return idft_taylor_launch<12, 2>(out, out_stride, coef, in, in_stride, S, P, K, U, s);
-    if (P <= 16) return idft_taylor_launch<16, 2>(out, out_stride, coef, in, in_stride, S, P, K, U, s);
+    if (P <= 8) return idft_taylor_launch<8, 2, 8>(out, out_stride, coef, in, in_stride, S, P, K, U, out_prev, s);
+    if (P <= 12) return idft_taylor_launch<12, 2, 8>(out, out_stride, coef, in, in_stride, S, P, K, U, out_prev, s);
+    if (P <= 16) return idft_taylor_launch<16, 2, 8>(out, out_stride, coef, in, in_stride, S, P, K, U, out_prev, s);
     return cudaErrorInvalidValue;
 }
 

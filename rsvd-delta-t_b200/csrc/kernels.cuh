@@ -50,8 +50,23 @@ struct BandedStepArgs {
     double dt = 0;
 };
 bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, int variant);
+int banded_tile_rows(int64_t lo_bw, int64_t hi_bw, int nv, int variant);
+// ranges (device, optional): explicit list of nranges owned row ranges [r0, r1), each at most banded_tile_rows long
 cudaError_t launch_rk4_banded_step(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, const BandedStepArgs &a,
-                                   int variant, cudaStream_t s);
+                                   int variant, const int64_t *ranges, int nranges, cudaStream_t s);
+
+// Same fused step on the diagonal (DIA) form of the operator: dia[row][lo+hi+1], offsets -lo..+hi; tile_ok[t] == 0
+// marks tiles (of dia_tile_rows rows) containing rows that do not follow the pattern -- they are left untouched.
+bool dia_step_supported(int lo, int hi, int nv);
+int dia_tile_rows(int lo, int hi, int nv);
+cudaError_t launch_rk4_dia_step(const cplx *dia, int lo, int hi, const unsigned char *tile_ok, int ntiles, int64_t N, int nv,
+                                const BandedStepArgs &a, cudaStream_t s);
+
+// TMA-staged form of the DIA step (bulk copies of whole tiles, 2-3 CTAs per SM); variant 0: 3 CTAs/SM, 1: 2 CTAs/SM
+bool dia_tma_supported(int lo, int hi, int nv, int variant);
+int dia_tma_tile_rows(int lo, int hi, int nv, int variant);
+cudaError_t launch_rk4_dia_tma_step(const cplx *dia, int lo, int hi, const unsigned char *tile_ok, int ntiles, int64_t N,
+                                    int nv, int variant, const BandedStepArgs &a, cudaStream_t s);
 
 // Twiddle coefficient tables (CreateDFTiDFTMats.c:42-58,76-84), generated on the device with exactly reduced phases.
 //   idft: coef[s][w] = (1/Ns) * exp(+2*pi*i * m(w) * j_s / (2Ns)),  j_s = (j_start + dir*s) mod 2Ns,  s < S, w < Nw_eff
@@ -70,8 +85,9 @@ cudaError_t launch_small_cgemm(cplx *out, int64_t out_stride, const cplx *coef, 
 int idft_taylor_terms(double x);
 cudaError_t launch_idft_taylor_coef(cplx *coef, int P, int K, int64_t J2, int dir, int64_t Ns, double h, int real_op,
                                     cudaStream_t s);
+// out_prev (optional): additionally receives the slice one half step before slice 0 (s = -1)
 cudaError_t launch_idft_taylor(cplx *out, int64_t out_stride, const cplx *coef, const cplx *in, int64_t in_stride, int S,
-                               int P, int K, int64_t U, cudaStream_t s);
+                               int P, int K, int64_t U, cplx *out_prev, cudaStream_t s);
 
 // reference (column-major, column c = a*ca + b*cb) <-> device stack T[a][row][b]
 cudaError_t launch_host_to_stack(cplx *dst, const cplx *src_colmajor, int64_t nrows, int na, int nb, int64_t ca,

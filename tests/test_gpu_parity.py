@@ -245,7 +245,9 @@ def test_full_size_properties(pkg, O):
 @pytest.mark.parametrize("opts", [dict(use_banded=0, idft_variant=10), dict(use_banded=0, idft_variant=0),
                                   dict(use_banded=1, idft_variant=10), dict(use_banded=1, stage_variant=1),
                                   dict(use_banded=1, stage_variant=2), dict(use_banded=1, stage_variant=3),
-                                  dict(use_banded=1, chunk_steps=64), dict(use_banded=0, idft_variant=11, chunk_steps=5)])
+                                  dict(use_banded=1, chunk_steps=64), dict(use_banded=0, idft_variant=11, chunk_steps=5),
+                                  dict(use_banded=2), dict(use_banded=2, chunk_steps=7, stage_variant=2),
+                                  dict(use_banded=3), dict(use_banded=3, tma_variant=1)])
 def test_kernel_variants_agree_with_oracle(pkg, O, A_GL, opts):
     # every code path (stage-by-stage vs fused banded step; direct vs Taylor-moment forcing synthesis) gives the
     # oracle's answer; Ns is large enough here (w = 0.05) for the Taylor path to be selected
