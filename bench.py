@@ -205,6 +205,8 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         r.time_forced_steps(STEPS_PER_PASS)
+    path_name = {0: "rk4_stage_csr (4 launches/step)", 1: "rk4_banded_step (CSR, fused 4 stages)",
+                 2: "rk4_dia_step (fused 4 stages)", 3: "rk4_dia_tma (fused 4 stages, TMA tiles)"}
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -241,8 +243,20 @@ def main():
     bytes_per_launch = bytes_per_unit_step * N * k / max(launches_per_step, 1e-9)
     avg_launch_ms = stage_ms / max(stage_n, 1)
     achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
-    roofline = {"bound": "hbm", "kernel": "rk4_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+    ncu_traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        try:
+            ncu_traffic = json.load(open(tp)).get("rk4_step_kernel_bytes_per_launch")
+        except Exception:
+            ncu_traffic = None
+    roofline = {"bound": "hbm", "kernel": "rk4 step kernel(s), %.0f launch(es) per RK4 step" % launches_per_step,
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic,
+                "note": "achieved uses the ALGORITHMIC bytes of SURVEY.md 8(d) (stage-by-stage model, 353.6 B per unit and "
+                        "step); the fused-step kernel moves fewer bytes than the model (temporal fusion of the 4 stages), "
+                        "so frac > 1 is a traffic reduction, not a bandwidth above peak; `traffic` is the ncu-measured DRAM "
+                        "bytes per launch",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_ms,
                 "launches_per_rk4_step": launches_per_step, "peak_source": peak_src,
                 "share_of_step": stage_ms / dev_ms if dev_ms else None,
