@@ -124,6 +124,41 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
                             double TransDivVal, double TransConVal, double *norms_out, int64_t *steps_done,
                             int *reason, rsvdt_snapshot_cb snapshot_cb, void *user);
 
+/* ---- row partition across GPUs (one process per GPU) ----------------------------------------------------
+ * Replaces PETSc's MPIAIJ distribution (LNSStructure.c:24-26: MatSetType MATMPIAIJ; CreateTSMats.c:15-17: VECMPI with
+ * PETSC_DECIDE): rank r owns floor(N/P) + (r < N mod P) consecutive rows.  The planning (which rows are ghosts, who
+ * sends what) is host arithmetic done by the caller (rsvd-delta-t_b200/dist.py); the library receives the LOCAL matrix
+ * -- rows it stores, column indices already in local numbering -- and the halo message lists, exchanges CUDA IPC
+ * handles through the caller, and from then on moves halo rows itself with peer stores over NVLink.
+ *   layout 0: local rows = owned rows; ghost columns appended after them (general sparsity, one exchange per RK4 stage)
+ *   layout 1: local rows = owned rows plus `halo` neighbour rows on each side (narrow-band operators advanced by the
+ *             fused step kernel, one exchange per RK4 step). */
+int rsvdt_plan_partition(int64_t N, int nranks, int rank, int64_t *row_begin, int64_t *row_end);   /* PETSC_DECIDE split */
+int rsvdt_dist_init(rsvdt_handle h, int rank, int nranks, int layout);
+/* LNSStructure.c:23-56 for one rank: n_rows stored rows with column indices in [0, n_ext); the owned rows are the local
+ * rows [own0, own0 + n_own).  A and A^H are both given (the caller partitions A^H the same way, like the pre-transposed
+ * operator of SURVEY.md 8e).  real_operator is the GLOBAL decision (||Im A||_F < 1e-12 over all ranks). */
+int rsvdt_set_operator_csr_local(rsvdt_handle h, int64_t N_global, int64_t n_own, int64_t own0, int64_t n_ext,
+                                 int64_t n_rows, const int64_t *rowptr, const int64_t *col, const double *val_re_im,
+                                 const int64_t *rowptr_H, const int64_t *col_H, const double *val_H_re_im,
+                                 int disc_flg, double beta, int real_operator);
+/* halo messages: nout outgoing (peer, count, rows to send = local row indices, first ghost row they fill on the peer),
+ * nin incoming (peer, count, first local ghost row).  Call after rsvdt_set_grid (the mailbox is sized for k). */
+int rsvdt_dist_set_messages(rsvdt_handle h, int nout, const int *out_peer, const int *out_count, const int64_t *out_rows,
+                            const int64_t *out_dest_row0, int nin, const int *in_peer, const int *in_count,
+                            const int64_t *in_dest_row0);
+/* CUDA IPC bootstrap: export 2 handles (mailbox, flags) = 128 bytes; import the nranks*128 bytes gathered from all ranks
+ * plus, for every outgoing message i, the row offset of my region inside that peer's mailbox slot. */
+int rsvdt_dist_ipc_export(rsvdt_handle h, unsigned char *bytes128);
+int rsvdt_dist_ipc_import(rsvdt_handle h, const unsigned char *all_bytes, const int64_t *out_mailbox_row_offset);
+/* offsets (in rows) of each incoming message inside my mailbox slot, to be sent to the corresponding senders */
+int rsvdt_dist_get_in_offsets(rsvdt_handle h, int64_t *in_mailbox_row_offset);
+/* sum-reduction across ranks of n doubles resident on the device (Gram matrices of QRAllFreqs / SVDAllFreqs, norms):
+ * the caller supplies it (torch.distributed all_reduce over NCCL in the Python host); stream-ordered on `stream`. */
+typedef int (*rsvdt_allreduce_fn)(void *device_ptr, int64_t n_doubles, void *cuda_stream, void *user);
+int rsvdt_set_allreduce(rsvdt_handle h, rsvdt_allreduce_fn fn, void *user);
+void *rsvdt_cuda_stream(rsvdt_handle h);
+
 /* ---- test / measurement hooks (no reference counterpart) ------------------------------------------ */
 /* snapshots Y_all of the last action: N x (Nstore*k), test-vector-major columns (TSActionRK4.c:62-70,126-130);
  * only kept when rsvdt_keep_snapshots(h, 1) was called before the action. */

@@ -36,6 +36,7 @@ class Grid(C.Structure):
 
 
 SNAPSHOT_CB = C.CFUNCTYPE(C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int64, _vp)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -68,6 +69,15 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(_vp)
+
+
+def plan_partition(N, nranks, rank):
+    """PETSC_DECIDE row split through the C ABI -> (row_begin, row_end)"""
+    b, e = C.c_int64(), C.c_int64()
+    rc = lib().rsvdt_plan_partition(C.c_int64(N), C.c_int(nranks), C.c_int(rank), C.byref(b), C.byref(e))
+    if rc:
+        raise RsvdtError(rc, "rsvdt_plan_partition: bad arguments")
+    return b.value, e.value
 
 
 def setup_time_freq_grid(w, Nw, dt_in, TransientLength):
@@ -124,6 +134,23 @@ class RSVDt:
         self.N = int(N)
         self.real_operator = bool(ro.value)
         return self.real_operator
+
+    def dist_init(self, rank, nranks, layout):
+        """row partition over GPUs (MATMPIAIJ / VECMPI of the reference); see dist.py"""
+        self._ck(lib().rsvdt_dist_init(self._h, C.c_int(rank), C.c_int(nranks), C.c_int(layout)))
+
+    def LNSStructure_local(self, N_global, n_own, own0, n_ext, A, AH, real_operator, DiscFlg=False, beta=0.0):
+        """LNSStructure.c:23-56 for one rank.  A, AH: (rowptr, col_local, val) of the stored local rows"""
+        arrs = []
+        for rp, ci, va in (A, AH):
+            arrs += [np.ascontiguousarray(rp, np.int64), np.ascontiguousarray(ci, np.int64), np.ascontiguousarray(va, c128)]
+        n_rows = arrs[0].size - 1
+        self._ck(lib().rsvdt_set_operator_csr_local(self._h, C.c_int64(N_global), C.c_int64(n_own), C.c_int64(own0),
+                                                    C.c_int64(n_ext), C.c_int64(n_rows), _p(arrs[0]), _p(arrs[1]), _p(arrs[2]),
+                                                    _p(arrs[3]), _p(arrs[4]), _p(arrs[5]), C.c_int(int(DiscFlg)),
+                                                    C.c_double(beta), C.c_int(int(real_operator))))
+        self.N = int(n_own)
+        self.real_operator = bool(real_operator)
 
     def set_grid(self, k, Nw, Ns, Nt, ResRatio, dt, w, TransientRemoval=False, RealOperator=None):
         ro = self.real_operator if RealOperator is None else RealOperator

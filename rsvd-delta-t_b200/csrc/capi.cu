@@ -66,10 +66,30 @@ struct rsvdt_context {
     cudaStream_t stream = nullptr;
     std::string err;
 
-    // LNS_vars (Variables.h:59-62)
-    int64_t N = 0;
+    // LNS_vars (Variables.h:59-62).  N = rows owned by this rank (all rows on one GPU); the local arrays hold n_ext rows:
+    // the owned ones at [own0, own0 + N) plus halo/ghost copies of the neighbours' rows (row-partitioned runs).
+    int64_t N = 0, n_ext = 0, own0 = 0, N_global = 0;
     CsrOwned A, AH;
     bool real_operator = false;
+
+    // row partition over GPUs (PETSc's MPIAIJ layout; one process per GPU): halo messages, peer mailboxes, flags
+    struct DistMsg { int peer; int count; int64_t dest_row0; int64_t mb_off_rows; DevBuf rows; };
+    struct DistIn { int peer; int count; int64_t dest_row0; int64_t mb_off_rows; };
+    struct Dist {
+        bool on = false, connected = false;
+        int rank = 0, nranks = 1;
+        int layout = 0;                       // 0: ghosts appended after the owned rows, 1: halo rows around the owned range
+        std::vector<DistMsg> out;             // what I send
+        std::vector<DistIn> in;               // what I receive
+        int64_t in_rows_total = 0;            // rows per mailbox slot
+        int nvec_max = 0;
+        DevBuf mailbox, flags, msgs_dev, ins_dev, peer_flags_dev;
+        std::vector<void *> peer_mailbox, peer_flags;   // IPC-mapped peer pointers (index = rank)
+        unsigned long long epoch = 0;
+        int max_out = 0, max_in = 0;
+        rsvdt_allreduce_fn allreduce = nullptr;
+        void *allreduce_user = nullptr;
+    } dist;
 
     // Weight_matrices (Variables.h:69-80): 0=W_f_sqrt_inv 1=B 2=W_q_sqrt_inv 3=W_q_sqrt 4=C, and their conj-transposes
     CsrOwned W[5], WH[5];
@@ -296,9 +316,11 @@ int plan_dia(rsvdt_handle h, CsrOwned &Op, int nv, int mode)
     if (!Op.dia_valid) return RSVDT_OK;
     if (mode == 3 ? !dia_tma_supported(Op.dia_lo, Op.dia_hi, nv, (int)h->tma_variant) : !dia_step_supported(Op.dia_lo, Op.dia_hi, nv))
         return RSVDT_OK;
-    const int64_t N = Op.d.nrows;
+    const int64_t N = Op.d.nrows;                       // rows of the local arrays (owned + halo)
+    const int64_t ob = h->own0, oe = h->own0 + h->N;    // owned rows: the tiles cover exactly these
+    if (ob != 0 && mode != 3) return RSVDT_OK;
     const int TR = mode == 3 ? dia_tma_tile_rows(Op.dia_lo, Op.dia_hi, nv, (int)h->tma_variant) : dia_tile_rows(Op.dia_lo, Op.dia_hi, nv);
-    const int64_t ntiles = (N + TR - 1) / TR;
+    const int64_t ntiles = (oe - ob + TR - 1) / TR;
     std::vector<int64_t> irr_prefix((size_t)N + 1, 0);
     for (int64_t r = 0; r < N; r++) irr_prefix[(size_t)r + 1] = irr_prefix[(size_t)r] + (Op.row_regular[(size_t)r] ? 0 : 1);
     std::vector<unsigned char> ok((size_t)ntiles, 1);
@@ -306,7 +328,7 @@ int plan_dia(rsvdt_handle h, CsrOwned &Op, int nv, int mode)
     const bool slow_ok = banded_step_supported(Op.d, Op.lo_bw, Op.hi_bw, nv, (int)h->stage_variant);
     const int TRs = slow_ok ? banded_tile_rows(Op.lo_bw, Op.hi_bw, nv, (int)h->stage_variant) : 0;
     for (int64_t t = 0; t < ntiles; t++) {
-        const int64_t r0 = t * TR, r1 = std::min(N, r0 + TR);
+        const int64_t r0 = ob + t * TR, r1 = std::min(oe, r0 + TR);
         const int64_t e0 = std::max<int64_t>(0, r0 - 3 * Op.dia_lo), e1 = std::min(N, r1 + 3 * Op.dia_hi);
         if (irr_prefix[(size_t)e1] - irr_prefix[(size_t)e0] > 0) {
             ok[(size_t)t] = 0;
@@ -337,14 +359,19 @@ int ensure(rsvdt_handle h, DevBuf &b, size_t bytes)
 size_t stack_bytes(int64_t na, int64_t rows, int64_t nb) { return (size_t)na * (size_t)rows * (size_t)nb * sizeof(cplx); }
 
 // host (pageable or pinned) column-major <-> device stack, through a device staging buffer
-int upload_stack(rsvdt_handle h, DevBuf &dst, const double *host, int64_t rows, int na, int nb, int64_t ca, int64_t cb)
+// srows: rows per slot of the device stack; the `rows` host rows are its rows [roff, roff + rows)
+int upload_stack(rsvdt_handle h, DevBuf &dst, const double *host, int64_t rows, int na, int nb, int64_t ca, int64_t cb,
+                 int64_t srows = -1, int64_t roff = 0)
 {
+    if (srows < 0) srows = rows;
     const size_t bytes = stack_bytes(na, rows, nb);
-    RS(ensure(h, dst, bytes));
+    const bool fresh = dst.bytes < stack_bytes(na, srows, nb) || !dst.p;
+    RS(ensure(h, dst, stack_bytes(na, srows, nb)));
+    if (fresh && srows != rows) CU(cudaMemsetAsync(dst.p, 0, stack_bytes(na, srows, nb), h->stream));
     DevBuf stage;
     CU(stage.alloc(bytes));
     cudaError_t e = cudaMemcpyAsync(stage.p, host, bytes, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = launch_host_to_stack(dst.as<cplx>(), stage.as<cplx>(), rows, na, nb, ca, cb, h->stream);
+    if (e == cudaSuccess) e = launch_host_to_stack(dst.as<cplx>(), stage.as<cplx>(), rows, na, nb, ca, cb, srows, roff, h->stream);
     h->launches++;
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     stage.release();
@@ -352,18 +379,36 @@ int upload_stack(rsvdt_handle h, DevBuf &dst, const double *host, int64_t rows, 
     return RSVDT_OK;
 }
 
-int download_stack(rsvdt_handle h, const DevBuf &src, double *host, int64_t rows, int na, int nb, int64_t ca, int64_t cb)
+int download_stack(rsvdt_handle h, const DevBuf &src, double *host, int64_t rows, int na, int nb, int64_t ca, int64_t cb,
+                   int64_t srows = -1, int64_t roff = 0)
 {
+    if (srows < 0) srows = rows;
     const size_t bytes = stack_bytes(na, rows, nb);
-    if (src.bytes < bytes) return fail(h, RSVDT_ERR_STATE, "device matrix not available");
+    if (src.bytes < stack_bytes(na, srows, nb)) return fail(h, RSVDT_ERR_STATE, "device matrix not available");
     DevBuf stage;
     CU(stage.alloc(bytes));
-    cudaError_t e = launch_stack_to_host(stage.as<cplx>(), src.as<cplx>(), rows, na, nb, ca, cb, h->stream);
+    cudaError_t e = launch_stack_to_host(stage.as<cplx>(), src.as<cplx>(), rows, na, nb, ca, cb, srows, roff, h->stream);
     h->launches++;
     if (e == cudaSuccess) e = cudaMemcpyAsync(host, stage.p, bytes, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     stage.release();
     CU(e);
+    return RSVDT_OK;
+}
+
+// ---- halo exchange of a block vector [row][nvec] (the VecScatter of PETSc's MPIAIJ mat-vec) ----------------------------
+int dist_exchange(rsvdt_handle h, cplx *buf, int nvec)
+{
+    auto &D = h->dist;
+    if (!D.on) return RSVDT_OK;
+    if (!D.connected) return fail(h, RSVDT_ERR_STATE, "row-partitioned run: peers not connected (rsvdt_dist_ipc_import)");
+    if (nvec > D.nvec_max) return fail(h, RSVDT_ERR_ARG, "halo exchange of %d vectors exceeds the mailbox (%d)", nvec, D.nvec_max);
+    D.epoch++;
+    const int parity = (int)(D.epoch & 1ull);
+    CU(launch_halo_push(buf, nvec, D.msgs_dev.p, (int)D.out.size(), D.max_out, parity, D.nvec_max, h->stream));
+    CU(launch_halo_signal(D.peer_flags_dev.p, (int)D.out.size(), D.epoch, h->stream));
+    CU(launch_halo_wait_unpack(buf, nvec, D.ins_dev.p, (int)D.in.size(), D.max_in, parity, D.nvec_max, D.epoch, h->stream));
+    h->launches += (D.out.empty() ? 0 : 2) + (D.in.empty() ? 0 : 1);
     return RSVDT_OK;
 }
 
@@ -380,24 +425,28 @@ int rk4_step(rsvdt_handle h, const CsrOwned &Op, int nv, cplx *y, cplx *xa, cplx
         a.xin = y; a.ybase = y; a.f = f_prev; a.xout = xa; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6;
         CU(launch_rk4_stage(Op.d, nv, 0, a, (int)h->stage_variant, h->stream));
     }
+    RS(dist_exchange(h, xa, nv));
     {   // k2 = Op x2 + F2 ; x3 = y + dt/2 k2 ; acc += dt/6*2 k2                   TSRK4.c:31-32,45
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xa; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xb; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6 * 2;
         CU(launch_rk4_stage(Op.d, nv, 1, a, (int)h->stage_variant, h->stream));
     }
+    RS(dist_exchange(h, xb, nv));
     {   // k3 = Op x3 + F2 ; x4 = y + dt k3 ; acc += dt/6*2 k3                     TSRK4.c:33-34,46
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xb; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xa; a.acc_out = acc; a.cx = dt; a.ca = dt / 6 * 2;
         CU(launch_rk4_stage(Op.d, nv, 1, a, (int)h->stage_variant, h->stream));
     }
+    RS(dist_exchange(h, xa, nv));
     {   // k4 = Op x4 + F3 ; y = acc + dt/6 k4 ; snapshot                         TSRK4.c:35,47 ; SaveSnapshots.c:26-28
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xa; a.f = f_next; a.acc_in = acc; a.acc_out = y; a.snap = snap; a.ca = dt / 6;
         CU(launch_rk4_stage(Op.d, nv, 2, a, (int)h->stage_variant, h->stream));
     }
+    RS(dist_exchange(h, y, nv));
     h->launches += 4;
     return RSVDT_OK;
 }
@@ -425,6 +474,14 @@ int64_t snapshot_slot(const rsvdt_grid &g, bool direct, int64_t Nstore, int64_t 
 int step_path(rsvdt_handle h, CsrOwned &Op, int nv, int *path)
 {
     *path = 0;
+    if (h->dist.on) {   // layout 1 <-> TMA-staged fused step on the halo-extended rows; layout 0 <-> stage kernels
+        if (h->dist.layout == 1) {
+            RS(plan_dia(h, Op, nv, 3));
+            if (!Op.plan_ok) return fail(h, RSVDT_ERR_ARG, "partition layout 1 needs an operator the fused band kernel supports");
+            *path = 3;
+        }
+        return RSVDT_OK;
+    }
     if (!h->use_banded) return RSVDT_OK;
     if (h->use_banded >= 3) {
         RS(plan_dia(h, Op, nv, 3));
@@ -448,6 +505,8 @@ int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **yc
     Bracket br(h, &h->ev_stage);
     BandedStepArgs a;
     a.y_in = *ycur; a.y_out = *ynext; a.f_prev = f_prev; a.f_half = f_half; a.f_next = f_next; a.snap = snap; a.dt = h->g.dt;
+    a.own_begin = h->own0;
+    a.own_end = h->own0 + h->N;
     if (path >= 2) {
         if (path == 3)
             CU(launch_rk4_dia_tma_step(Op.dia.as<cplx>(), Op.dia_lo, Op.dia_hi, Op.tile_ok.as<unsigned char>(), Op.ntiles, Op.d.nrows, nv, (int)h->tma_variant, a, h->stream));
@@ -463,6 +522,7 @@ int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **yc
         h->launches += 1;
     }
     std::swap(*ycur, *ynext);
+    RS(dist_exchange(h, *ycur, nv));
     return RSVDT_OK;
 }
 
@@ -479,7 +539,7 @@ int64_t max_harmonic(const rsvdt_grid &g)
 int synth_forcing(rsvdt_handle h, const cplx *Fhat, cplx *slices, int Sc, int64_t j_start, int dir, cplx *prev)
 {
     const rsvdt_grid &g = h->g;
-    const int64_t U = h->N * g.k;
+    const int64_t U = h->n_ext * g.k;
     Bracket br(h, &h->ev_idft);
     const double PI = 3.14159265358979323846;
     const double hh = 0.5 * (double)Sc;
@@ -517,7 +577,7 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
     const rsvdt_grid &g = h->g;
     CsrOwned &Op = direct ? h->A : h->AH;
     const int nv = (int)g.k;
-    const int64_t U = h->N * g.k;
+    const int64_t U = h->n_ext * g.k;
     const int64_t Tc = std::max<int64_t>(1, h->chunk_steps);
     const int S = (int)(2 * Tc);
     int path = 0;
@@ -531,6 +591,11 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
         RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
     }
     cplx *ycur = y, *ynext = h->xa.as<cplx>();
+    if (h->dist.on && h->dist.layout == 1) {
+        // halo rows of the forcing: the fused step recomputes the stages on the halo rows, so F_hat is needed there too
+        for (int64_t w = 0; w < g.Nw_eff; w++) RS(dist_exchange(h, const_cast<cplx *>(Fhat) + w * U, nv));
+    }
+    if (h->dist.on) RS(dist_exchange(h, ycur, nv));
 
     int cur = 0;
     // forcing at t_n of the first step of the chunk (F3 carried over, TSRK4.c:18); for the very first chunk it is the
@@ -570,7 +635,7 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
 int unforced_steps(rsvdt_handle h, bool direct, int nv, cplx *y, int64_t nsteps)
 {
     CsrOwned &Op = direct ? h->A : h->AH;
-    const int64_t U = h->N * nv;
+    const int64_t U = h->n_ext * nv;
     int path = 0;
     RS(step_path(h, Op, nv, &path));
     const bool banded = path != 0;
@@ -589,7 +654,7 @@ int unforced_steps(rsvdt_handle h, bool direct, int nv, cplx *y, int64_t nsteps)
 int dft_snapshots(rsvdt_handle h, const cplx *snaps, cplx *Yhat_out)
 {
     const rsvdt_grid &g = h->g;
-    const int64_t U = h->N * g.k;
+    const int64_t U = h->n_ext * g.k;
     RS(ensure(h, h->coef, (size_t)std::max<int64_t>(g.Nw_eff * g.Nw, 2 * h->chunk_steps * g.Nw_eff) * sizeof(cplx)));
     Bracket br(h, &h->ev_dft);
     CU(launch_dft_coef(h->coef.as<cplx>(), (int)g.Nw_eff, (int)g.Nw, g.ResRatio, h->stream));
@@ -613,7 +678,7 @@ int ts_action(rsvdt_handle h, bool direct)
     const rsvdt_grid &g = h->g;
     if (h->yhat_rows != h->N || !h->Yhat.p) return fail(h, RSVDT_ERR_STATE, "Y_hat not set or wrong row count");
     if (g.TransientRemoval) return fail(h, RSVDT_ERR_USER, "TransientRemoval is not implemented yet in this build");
-    const int64_t U = h->N * g.k;
+    const int64_t U = h->n_ext * g.k;
     int64_t rend = g.Nt + g.Ns;                                   // TSActionRK4.c:41
     rend += g.TransientRemoval ? g.ResRatio : 0;                  // :42
     const int64_t Nstore = g.TransientRemoval ? g.Nw + 1 : g.Nw;  // :43
@@ -679,28 +744,50 @@ int action_with_weights(rsvdt_handle h, bool direct)
     return RSVDT_OK;
 }
 
-int gram_all(rsvdt_handle h, const cplx *Y, int64_t rows)
+int dist_allreduce(rsvdt_handle h, void *dev_ptr, int64_t n_doubles)
+{
+    if (!h->dist.on || h->dist.nranks == 1) return RSVDT_OK;
+    if (!h->dist.allreduce) return fail(h, RSVDT_ERR_STATE, "row-partitioned run: no all-reduce registered (rsvdt_set_allreduce)");
+    const int rc = h->dist.allreduce(dev_ptr, n_doubles, (void *)h->stream, h->dist.allreduce_user);
+    if (rc) return fail(h, RSVDT_ERR_CUDA, "all-reduce callback failed (%d)", rc);
+    return RSVDT_OK;
+}
+
+// Gram matrices of the per-frequency blocks of a stack with `srows` rows per slot, summed over the owned rows
+// [roff, roff + rows) and over the ranks
+int gram_all(rsvdt_handle h, const cplx *Y, int64_t rows, int64_t srows = -1, int64_t roff = 0)
 {
     const rsvdt_grid &g = h->g;
+    if (srows < 0) srows = rows;
     const int nblk = gram_num_blocks(rows);
     RS(ensure(h, h->gram_partial, (size_t)nblk * g.Nw_eff * g.k * g.k * sizeof(cplx)));
     RS(ensure(h, h->small, (size_t)g.Nw_eff * g.k * g.k * sizeof(cplx)));
     RS(ensure(h, h->smallM, (size_t)g.Nw_eff * g.k * g.k * sizeof(cplx)));
     RS(ensure(h, h->status, (size_t)g.Nw_eff * sizeof(int)));
-    CU(launch_gram(Y, rows, (int)g.k, (int)g.Nw_eff, h->gram_partial.as<cplx>(), h->small.as<cplx>(), h->stream));
+    CU(launch_gram(Y + roff * g.k, rows, (int)g.k, (int)g.Nw_eff, srows * g.k, h->gram_partial.as<cplx>(), h->small.as<cplx>(), h->stream));
     h->launches += 2;
+    RS(dist_allreduce(h, h->small.p, 2 * g.Nw_eff * g.k * g.k));
     return RSVDT_OK;
+}
+
+// slot geometry of a stack holding `rows` owned rows: N-row matrices live on the halo-extended rows
+void stack_geom(rsvdt_handle h, int64_t rows, int64_t *srows, int64_t *roff)
+{
+    if (rows == h->N) { *srows = h->n_ext; *roff = h->own0; }
+    else { *srows = rows; *roff = 0; }
 }
 
 // per-frequency cross-product SVD: Y_w <- left singular vectors; sigma -> dst_sigma (device, k x Nw_eff) if not null
 int svd_all(rsvdt_handle h, DevBuf &Y, int64_t rows, double *dst_sigma)
 {
     const rsvdt_grid &g = h->g;
-    RS(gram_all(h, Y.as<cplx>(), rows));
+    int64_t srows, roff;
+    stack_geom(h, rows, &srows, &roff);
+    RS(gram_all(h, Y.as<cplx>(), rows, srows, roff));
     DevBuf sig;
     CU(sig.alloc((size_t)g.Nw_eff * g.k * sizeof(double)));
     CU(launch_cross_svd_small(h->small.as<cplx>(), (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), sig.as<double>(), h->stream));
-    CU(launch_apply_right(Y.as<cplx>(), rows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
+    CU(launch_apply_right(Y.as<cplx>(), srows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
     h->launches += 2;
     if (dst_sigma) CU(cudaMemcpyAsync(dst_sigma, sig.p, (size_t)g.Nw_eff * g.k * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -743,6 +830,14 @@ int rsvdt_destroy(rsvdt_handle h)
     drain(h->ev_stage, &n); drain(h->ev_idft, &n); drain(h->ev_dft, &n);
     h->A.release(); h->AH.release();
     for (int i = 0; i < 5; i++) { h->W[i].release(); h->WH[i].release(); }
+    for (auto &m : h->dist.out) m.rows.release();
+    for (int p = 0; p < (int)h->dist.peer_mailbox.size(); p++) {
+        if (p == h->dist.rank) continue;
+        if (h->dist.peer_mailbox[(size_t)p]) cudaIpcCloseMemHandle(h->dist.peer_mailbox[(size_t)p]);
+        if (h->dist.peer_flags[(size_t)p]) cudaIpcCloseMemHandle(h->dist.peer_flags[(size_t)p]);
+    }
+    DevBuf *dbufs[] = {&h->dist.mailbox, &h->dist.flags, &h->dist.msgs_dev, &h->dist.ins_dev, &h->dist.peer_flags_dev};
+    for (DevBuf *b : dbufs) b->release();
     DevBuf *bufs[] = {&h->Yhat, &h->Uhat, &h->Vhat, &h->Shat, &h->y, &h->xa, &h->xb, &h->acc, &h->slices[0], &h->slices[1],
                       &h->coef, &h->snaps, &h->small, &h->smallM, &h->status, &h->gram_partial, &h->scalars};
     for (DevBuf *b : bufs) b->release();
@@ -781,6 +876,10 @@ int rsvdt_set_operator_csr(rsvdt_handle h, int64_t N, const int64_t *rowptr, con
     if (real_operator) *real_operator = h->real_operator ? 1 : 0;
     const double shift = disc_flg ? beta : 0.0;               // LNSStructure.c:53-56
     h->N = N;
+    h->n_ext = N;
+    h->own0 = 0;
+    h->N_global = N;
+    h->dist = rsvdt_context::Dist();
     RS(upload_csr(h, h->A, N, N, rowptr, col, v, false, shift));
     RS(upload_csr(h, h->AH, N, N, rowptr, col, v, true, shift));
     return RSVDT_OK;
@@ -805,6 +904,7 @@ int rsvdt_set_weight_csr(rsvdt_handle h, int which, int64_t nrows, int64_t ncols
     RS(bind(h));
     if (which < 0 || which > 4 || !rowptr || !col || !val) return fail(h, RSVDT_ERR_ARG, "bad weight arguments");
     if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "set the operator before the weights");
+    if (h->dist.on) return fail(h, RSVDT_ERR_ARG, "weight / input / output matrices are not supported in row-partitioned runs yet");
     static const char *names[5] = {"W_f_sqrt_inv", "B", "W_q_sqrt_inv", "W_q_sqrt", "C"};
     if ((which == 0 || which == 2 || which == 3) && nrows != ncols)   // ReadWeightMats.c:34,64,75
         return fail(h, RSVDT_ERR_USER, "weight matrix (%s) must be square, current size = %lld x %lld", names[which], (long long)nrows, (long long)ncols);
@@ -823,7 +923,10 @@ int rsvdt_set_yhat(rsvdt_handle h, const double *Y_host, int64_t nrows)
     RS(bind(h));
     if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "grid not set");
     if (!Y_host || nrows <= 0) return fail(h, RSVDT_ERR_ARG, "bad Y_hat arguments");
-    RS(upload_stack(h, h->Yhat, Y_host, nrows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1));
+    int64_t srows, roff;
+    stack_geom(h, nrows, &srows, &roff);
+    if (h->dist.on && nrows != h->N) return fail(h, RSVDT_ERR_ARG, "row-partitioned runs take Y_hat with the %lld owned rows", (long long)h->N);
+    RS(upload_stack(h, h->Yhat, Y_host, nrows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1, srows, roff));
     h->yhat_rows = nrows;
     return RSVDT_OK;
 }
@@ -832,7 +935,9 @@ int rsvdt_get_yhat(rsvdt_handle h, double *Y_host, int64_t nrows)
 {
     RS(bind(h));
     if (!Y_host || nrows != h->yhat_rows || !h->Yhat.p) return fail(h, RSVDT_ERR_STATE, "Y_hat not available with %lld rows", (long long)nrows);
-    return download_stack(h, h->Yhat, Y_host, nrows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1);
+    int64_t srows, roff;
+    stack_geom(h, nrows, &srows, &roff);
+    return download_stack(h, h->Yhat, Y_host, nrows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1, srows, roff);
 }
 
 int rsvdt_direct_action_rk4(rsvdt_handle h) { RS(bind(h)); return action_with_weights(h, true); }
@@ -855,10 +960,12 @@ int rsvdt_qr_all_freqs(rsvdt_handle h)
     if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
     const rsvdt_grid &g = h->g;
     std::vector<int> st((size_t)g.Nw_eff);
+    int64_t srows, roff;
+    stack_geom(h, h->yhat_rows, &srows, &roff);
     for (int pass = 0; pass < 2; pass++) {  // CholeskyQR2 (QRAllFreqs.c:22-32 semantics: Q with diag(R) > 0)
-        RS(gram_all(h, h->Yhat.as<cplx>(), h->yhat_rows));
+        RS(gram_all(h, h->Yhat.as<cplx>(), h->yhat_rows, srows, roff));
         CU(launch_chol_inverse(h->small.as<cplx>(), (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->status.as<int>(), h->stream));
-        CU(launch_apply_right(h->Yhat.as<cplx>(), h->yhat_rows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
+        CU(launch_apply_right(h->Yhat.as<cplx>(), srows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
         h->launches += 2;
         CU(cudaMemcpyAsync(st.data(), h->status.p, st.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -892,7 +999,9 @@ int rsvdt_store_u(rsvdt_handle h)
 {
     RS(bind(h));
     if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
-    const size_t bytes = stack_bytes(h->g.Nw_eff, h->yhat_rows, h->g.k);
+    int64_t srows, roff;
+    stack_geom(h, h->yhat_rows, &srows, &roff);
+    const size_t bytes = stack_bytes(h->g.Nw_eff, srows, h->g.k);
     RS(ensure(h, h->Uhat, bytes));
     CU(cudaMemcpyAsync(h->Uhat.p, h->Yhat.p, bytes, cudaMemcpyDeviceToDevice, h->stream));  // StoreU.c:15
     CU(cudaStreamSynchronize(h->stream));
@@ -938,14 +1047,18 @@ int rsvdt_get_u_hat(rsvdt_handle h, double *U_host)
 {
     RS(bind(h));
     if (!U_host || !h->Uhat.p) return fail(h, RSVDT_ERR_STATE, "U_hat not available");
-    return download_stack(h, h->Uhat, U_host, h->uhat_rows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1);
+    int64_t srows, roff;
+    stack_geom(h, h->uhat_rows, &srows, &roff);
+    return download_stack(h, h->Uhat, U_host, h->uhat_rows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1, srows, roff);
 }
 
 int rsvdt_get_v_hat(rsvdt_handle h, double *V_host)
 {
     RS(bind(h));
     if (!V_host || !h->Vhat.p) return fail(h, RSVDT_ERR_STATE, "V_hat not available");
-    return download_stack(h, h->Vhat, V_host, h->vhat_rows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1);
+    int64_t srows, roff;
+    stack_geom(h, h->vhat_rows, &srows, &roff);
+    return download_stack(h, h->Vhat, V_host, h->vhat_rows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1, srows, roff);
 }
 
 int rsvdt_get_s_hat(rsvdt_handle h, double *S_host)
@@ -965,9 +1078,10 @@ int rsvdt_ts_exp_a_deltat(rsvdt_handle h, int direct, double *U_host, int64_t nc
     if (!U_host || ncols <= 0) return fail(h, RSVDT_ERR_ARG, "bad arguments");
     // columns batched: block vector [row][col] ; host column-major N x ncols = stack with na=1, nb=ncols, cb=1
     DevBuf blk;
-    RS(upload_stack(h, blk, U_host, h->N, 1, (int)ncols, 0, 1));
-    int rc = unforced_steps(h, direct != 0, (int)ncols, blk.as<cplx>(), h->g.ResRatio);   // TSExpADeltaT.c:25-34
-    if (rc == RSVDT_OK) rc = download_stack(h, blk, U_host, h->N, 1, (int)ncols, 0, 1);
+    RS(upload_stack(h, blk, U_host, h->N, 1, (int)ncols, 0, 1, h->n_ext, h->own0));
+    int rc = dist_exchange(h, blk.as<cplx>(), (int)ncols);
+    if (rc == RSVDT_OK) rc = unforced_steps(h, direct != 0, (int)ncols, blk.as<cplx>(), h->g.ResRatio);   // TSExpADeltaT.c:25-34
+    if (rc == RSVDT_OK) rc = download_stack(h, blk, U_host, h->N, 1, (int)ncols, 0, 1, h->n_ext, h->own0);
     blk.release();
     return rc;
 }
@@ -982,13 +1096,17 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
     if (!q0_host || rend < 0 || TransSaveMod <= 0 || !norms_out) return fail(h, RSVDT_ERR_ARG, "bad arguments");
     const int64_t N = h->N;
     DevBuf q;
-    CU(q.alloc((size_t)N * sizeof(cplx)));
+    CU(q.alloc((size_t)h->n_ext * sizeof(cplx)));
+    CU(cudaMemsetAsync(q.p, 0, (size_t)h->n_ext * sizeof(cplx), h->stream));
     RS(ensure(h, h->scalars, 512 * sizeof(double)));
     double *partial = h->scalars.as<double>();
     double *d_norm = partial + 400;
-    CU(cudaMemcpyAsync(q.p, q0_host, (size_t)N * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    cplx *q_own = q.as<cplx>() + h->own0;
+    CU(cudaMemcpyAsync(q_own, q0_host, (size_t)N * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    RS(dist_exchange(h, q.as<cplx>(), 1));
     double n2 = 0;
-    CU(launch_norm2(q.as<cplx>(), N, partial, d_norm, h->stream));
+    CU(launch_norm2(q_own, N, partial, d_norm, h->stream));
+    RS(dist_allreduce(h, d_norm, 1));
     CU(cudaMemcpyAsync(&n2, d_norm, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     norms_out[0] = std::sqrt(n2);                              // TransientRunRK4.c:106-108
@@ -1002,8 +1120,9 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
         i = next_stop + 1;
         if (next_stop % TransSaveMod == 0) {                   // :137
             const int64_t pos = next_stop / TransSaveMod;
-            CU(launch_norm2(q.as<cplx>(), N, partial, d_norm, h->stream));
+            CU(launch_norm2(q_own, N, partial, d_norm, h->stream));
             h->launches += 2;
+            RS(dist_allreduce(h, d_norm, 1));
             CU(cudaMemcpyAsync(&n2, d_norm, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
             const double norm = std::sqrt(n2);
@@ -1012,7 +1131,7 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
             if (norm < TransConVal) { why = 3; i = next_stop; break; }       // :152-156
             if (cb) {                                                        // :160-164
                 snap_host.resize((size_t)2 * N);
-                CU(cudaMemcpyAsync(snap_host.data(), q.p, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaMemcpyAsync(snap_host.data(), q_own, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
                 CU(cudaStreamSynchronize(h->stream));
                 int crc = cb(pos, snap_host.data(), N, user);
                 if (crc != 0) { q.release(); return fail(h, RSVDT_ERR_USER, "snapshot callback failed (%d)", crc); }
@@ -1022,11 +1141,190 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
     }
     if (steps_done) *steps_done = why ? i : rend;
     if (reason) *reason = why;
-    CU(cudaMemcpyAsync(q0_host, q.p, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(q0_host, q_own, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     q.release();
     return RSVDT_OK;
 }
+
+// ---- row partition across GPUs ---------------------------------------------------------------------------------------
+int rsvdt_plan_partition(int64_t N, int nranks, int rank, int64_t *row_begin, int64_t *row_end)
+{
+    if (N < 0 || nranks <= 0 || rank < 0 || rank >= nranks || !row_begin || !row_end) return RSVDT_ERR_ARG;
+    // PetscSplitOwnership (PETSC_DECIDE): n = N/P + (rank < N%P)
+    const int64_t q = N / nranks, r = N % nranks;
+    *row_begin = rank * q + std::min<int64_t>(rank, r);
+    *row_end = *row_begin + q + (rank < r ? 1 : 0);
+    return RSVDT_OK;
+}
+
+int rsvdt_dist_init(rsvdt_handle h, int rank, int nranks, int layout)
+{
+    RS(bind(h));
+    if (nranks <= 0 || rank < 0 || rank >= nranks || layout < 0 || layout > 1) return fail(h, RSVDT_ERR_ARG, "bad partition arguments");
+    h->dist = rsvdt_context::Dist();
+    h->dist.on = true;
+    h->dist.rank = rank;
+    h->dist.nranks = nranks;
+    h->dist.layout = layout;
+    return RSVDT_OK;
+}
+
+int rsvdt_set_operator_csr_local(rsvdt_handle h, int64_t N_global, int64_t n_own, int64_t own0, int64_t n_ext, int64_t n_rows,
+                                 const int64_t *rowptr, const int64_t *col, const double *val, const int64_t *rowptr_H,
+                                 const int64_t *col_H, const double *val_H, int disc_flg, double beta, int real_operator)
+{
+    RS(bind(h));
+    if (!h->dist.on) return fail(h, RSVDT_ERR_STATE, "call rsvdt_dist_init first");
+    if (n_own <= 0 || own0 < 0 || own0 + n_own > n_ext || !rowptr || !col || !val || !rowptr_H || !col_H || !val_H)
+        return fail(h, RSVDT_ERR_ARG, "bad local operator arguments");
+    if (h->dist.layout == 0 && (own0 != 0 || n_rows != n_own)) return fail(h, RSVDT_ERR_ARG, "layout 0 stores exactly the owned rows");
+    if (h->dist.layout == 1 && n_rows != n_ext) return fail(h, RSVDT_ERR_ARG, "layout 1 stores the halo-extended rows");
+    if (disc_flg && beta < 0) return fail(h, RSVDT_ERR_USER, "'beta' must be positive, current value: %g", beta);
+    h->N = n_own;
+    h->n_ext = n_ext;
+    h->own0 = own0;
+    h->N_global = N_global;
+    h->real_operator = real_operator != 0;
+    // A - beta*I: the local diagonal of stored row r is local column r (layout 1) or r (layout 0, owned rows first)
+    const double shift = disc_flg ? beta : 0.0;
+    RS(upload_csr(h, h->A, n_rows, n_ext, rowptr, col, reinterpret_cast<const cplx *>(val), false, shift));
+    RS(upload_csr(h, h->AH, n_rows, n_ext, rowptr_H, col_H, reinterpret_cast<const cplx *>(val_H), false, shift));
+    return RSVDT_OK;
+}
+
+int rsvdt_dist_set_messages(rsvdt_handle h, int nout, const int *out_peer, const int *out_count, const int64_t *out_rows,
+                            const int64_t *out_dest_row0, int nin, const int *in_peer, const int *in_count,
+                            const int64_t *in_dest_row0)
+{
+    RS(bind(h));
+    auto &D = h->dist;
+    if (!D.on) return fail(h, RSVDT_ERR_STATE, "call rsvdt_dist_init first");
+    if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "set the grid before the halo messages (the mailbox is sized for k)");
+    D.out.clear();
+    D.in.clear();
+    D.connected = false;
+    D.nvec_max = (int)std::max<int64_t>(h->g.k, 1);
+    int64_t off = 0;
+    D.max_out = D.max_in = 0;
+    for (int i = 0; i < nout; i++) {
+        rsvdt_context::DistMsg m;
+        m.peer = out_peer[i];
+        m.count = out_count[i];
+        m.dest_row0 = out_dest_row0[i];
+        m.mb_off_rows = -1;
+        std::vector<int32_t> rows((size_t)m.count);
+        for (int j = 0; j < m.count; j++) {
+            const int64_t r = out_rows[off + j];
+            if (r < 0 || r >= h->n_ext) return fail(h, RSVDT_ERR_ARG, "halo send row out of range");
+            rows[(size_t)j] = (int32_t)r;
+        }
+        off += m.count;
+        CU(m.rows.alloc(std::max<size_t>(rows.size(), 1) * sizeof(int32_t)));
+        if (m.count) CU(cudaMemcpy(m.rows.p, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        D.max_out = std::max(D.max_out, m.count);
+        D.out.push_back(std::move(m));
+    }
+    D.in_rows_total = 0;
+    for (int i = 0; i < nin; i++) {
+        rsvdt_context::DistIn m;
+        m.peer = in_peer[i];
+        m.count = in_count[i];
+        m.dest_row0 = in_dest_row0[i];
+        m.mb_off_rows = D.in_rows_total;
+        if (m.dest_row0 < 0 || m.dest_row0 + m.count > h->n_ext) return fail(h, RSVDT_ERR_ARG, "ghost rows out of range");
+        D.in_rows_total += m.count;
+        D.max_in = std::max(D.max_in, m.count);
+        D.in.push_back(m);
+    }
+    // mailbox: two epoch-parity slots per incoming message; flags: one counter per rank
+    CU(D.mailbox.alloc(std::max<size_t>((size_t)2 * D.in_rows_total * D.nvec_max * sizeof(cplx), 256)));
+    CU(D.flags.alloc((size_t)D.nranks * sizeof(unsigned long long)));
+    CU(cudaMemset(D.flags.p, 0, (size_t)D.nranks * sizeof(unsigned long long)));
+    D.epoch = 0;
+    return RSVDT_OK;
+}
+
+int rsvdt_dist_get_in_offsets(rsvdt_handle h, int64_t *in_off)
+{
+    if (!h || !in_off) return RSVDT_ERR_ARG;
+    for (size_t i = 0; i < h->dist.in.size(); i++) in_off[i] = h->dist.in[i].mb_off_rows;
+    return RSVDT_OK;
+}
+
+int rsvdt_dist_ipc_export(rsvdt_handle h, unsigned char *bytes128)
+{
+    RS(bind(h));
+    auto &D = h->dist;
+    if (!D.on || !D.mailbox.p || !D.flags.p) return fail(h, RSVDT_ERR_STATE, "halo messages not set");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+    cudaIpcMemHandle_t hm, hf;
+    CU(cudaIpcGetMemHandle(&hm, D.mailbox.p));
+    CU(cudaIpcGetMemHandle(&hf, D.flags.p));
+    memcpy(bytes128, &hm, 64);
+    memcpy(bytes128 + 64, &hf, 64);
+    return RSVDT_OK;
+}
+
+int rsvdt_dist_ipc_import(rsvdt_handle h, const unsigned char *all_bytes, const int64_t *out_mb_off)
+{
+    RS(bind(h));
+    auto &D = h->dist;
+    if (!D.on || !D.mailbox.p) return fail(h, RSVDT_ERR_STATE, "halo messages not set");
+    D.peer_mailbox.assign((size_t)D.nranks, nullptr);
+    D.peer_flags.assign((size_t)D.nranks, nullptr);
+    for (int p = 0; p < D.nranks; p++) {
+        if (p == D.rank) { D.peer_mailbox[(size_t)p] = D.mailbox.p; D.peer_flags[(size_t)p] = D.flags.p; continue; }
+        bool needed = false;
+        for (auto &m : D.out) needed |= (m.peer == p);
+        if (!needed) continue;
+        cudaIpcMemHandle_t hm, hf;
+        memcpy(&hm, all_bytes + (size_t)p * 128, 64);
+        memcpy(&hf, all_bytes + (size_t)p * 128 + 64, 64);
+        CU(cudaIpcOpenMemHandle(&D.peer_mailbox[(size_t)p], hm, cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&D.peer_flags[(size_t)p], hf, cudaIpcMemLazyEnablePeerAccess));
+    }
+    std::vector<HaloMsgHost> mh(D.out.size());
+    std::vector<unsigned long long *> pf(D.out.size());
+    for (size_t i = 0; i < D.out.size(); i++) {
+        auto &m = D.out[i];
+        m.mb_off_rows = out_mb_off[i];
+        mh[i].peer_mailbox = reinterpret_cast<cplx *>(D.peer_mailbox[(size_t)m.peer]) + (int64_t)2 * m.mb_off_rows * D.nvec_max;
+        mh[i].rows = m.rows.as<int32_t>();
+        mh[i].count = m.count;
+        mh[i].pad = 0;
+        pf[i] = reinterpret_cast<unsigned long long *>(D.peer_flags[(size_t)m.peer]) + D.rank;
+    }
+    std::vector<HaloInHost> ih(D.in.size());
+    for (size_t i = 0; i < D.in.size(); i++) {
+        auto &m = D.in[i];
+        ih[i].mailbox = D.mailbox.as<cplx>() + (int64_t)2 * m.mb_off_rows * D.nvec_max;
+        ih[i].flag = D.flags.as<unsigned long long>() + m.peer;
+        ih[i].dest_row0 = m.dest_row0;
+        ih[i].count = m.count;
+        ih[i].pad = 0;
+    }
+    CU(D.msgs_dev.alloc(std::max<size_t>(mh.size(), 1) * sizeof(HaloMsgHost)));
+    CU(D.peer_flags_dev.alloc(std::max<size_t>(pf.size(), 1) * sizeof(void *)));
+    CU(D.ins_dev.alloc(std::max<size_t>(ih.size(), 1) * sizeof(HaloInHost)));
+    if (!mh.empty()) {
+        CU(cudaMemcpy(D.msgs_dev.p, mh.data(), mh.size() * sizeof(HaloMsgHost), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(D.peer_flags_dev.p, pf.data(), pf.size() * sizeof(void *), cudaMemcpyHostToDevice));
+    }
+    if (!ih.empty()) CU(cudaMemcpy(D.ins_dev.p, ih.data(), ih.size() * sizeof(HaloInHost), cudaMemcpyHostToDevice));
+    D.connected = true;
+    return RSVDT_OK;
+}
+
+int rsvdt_set_allreduce(rsvdt_handle h, rsvdt_allreduce_fn fn, void *user)
+{
+    if (!h) return RSVDT_ERR_ARG;
+    h->dist.allreduce = fn;
+    h->dist.allreduce_user = user;
+    return RSVDT_OK;
+}
+
+void *rsvdt_cuda_stream(rsvdt_handle h) { return h ? (void *)h->stream : nullptr; }
 
 int rsvdt_keep_snapshots(rsvdt_handle h, int keep)
 {
@@ -1040,7 +1338,7 @@ int rsvdt_get_snapshots(rsvdt_handle h, double *Yall_host)
     RS(bind(h));
     if (!Yall_host || !h->snaps.p || h->snaps_nstore <= 0) return fail(h, RSVDT_ERR_STATE, "snapshots not kept (rsvdt_keep_snapshots)");
     // device [pos][row][ik] -> reference test-vector-major column ik*Nstore + pos  (TSActionRK4.c:126-130)
-    return download_stack(h, h->snaps, Yall_host, h->N, (int)h->snaps_nstore, (int)h->g.k, 1, h->snaps_nstore);
+    return download_stack(h, h->snaps, Yall_host, h->N, (int)h->snaps_nstore, (int)h->g.k, 1, h->snaps_nstore, h->n_ext, h->own0);
 }
 
 int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *ms_total)
@@ -1049,7 +1347,7 @@ int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *m
     RS(check_ready(h));
     if (nsteps <= 0 || !ms_total) return fail(h, RSVDT_ERR_ARG, "bad arguments");
     if (!h->Yhat.p || h->yhat_rows != h->N) return fail(h, RSVDT_ERR_STATE, "Y_hat (forcing) not set");
-    const int64_t U = h->N * h->g.k;
+    const int64_t U = h->n_ext * h->g.k;
     RS(ensure(h, h->y, (size_t)U * sizeof(cplx)));
     CU(launch_fill_zero(h->y.as<cplx>(), U, h->stream));
     // allocate work buffers outside the timed region

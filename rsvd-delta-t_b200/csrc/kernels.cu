@@ -452,7 +452,8 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
     cplx *At = BB + n_e;                // operator diagonals [row][d]
     cplx *Fp = At + E0 * ND, *Fh = Fp + n_e, *Fn = Fh + n_e;   // forcing tiles (FORCED only)
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(FORCED ? (Fn + n_e) : Fp);
-    const int64_t base = (int64_t)blockIdx.x * TR - 4 * LO;
+    const int64_t own_end = a.own_end < 0 ? N : a.own_end;
+    const int64_t base = a.own_begin + (int64_t)blockIdx.x * TR - 4 * LO;
     const int lr_lo = (int)max((int64_t)0, -base), lr_hi = (int)min((int64_t)E0, N - base);   // tile rows inside [0, N)
     const double dt = a.dt;
     const double c_half = dt / 2, c_full = dt, w1 = dt / 6, w2 = dt / 6 * 2;
@@ -558,7 +559,7 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
     fence_proxy_async();   // make the generic-proxy writes to BA visible to the bulk-copy engine
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int o_lo = 4 * LO, o_hi = min(4 * LO + TR, lr_hi);
+        const int o_lo = 4 * LO, o_hi = (int)min((int64_t)(4 * LO + TR), own_end - base);
         if (o_hi > o_lo) {
             const unsigned ob = (unsigned)(o_hi - o_lo) * nv * sizeof(cplx);
             const int64_t g = (base + o_lo) * nv;
@@ -1007,9 +1008,10 @@ cudaError_t launch_idft_taylor(cplx *out, int64_t out_stride, const cplx *coef, 
 // =====================================================================================================
 // Layout conversion at the C-ABI boundary: reference column-major (column c = a*ca + b*cb) <-> stack T[a][row][b]
 // =====================================================================================================
+// stack side: slot stride `srows` rows, the nrows host rows map to stack rows [roff, roff + nrows)
 template <bool TO_STACK>
 __global__ void relayout_kernel(cplx *__restrict__ dst, const cplx *__restrict__ src, int64_t nrows, int na, int nb,
-                                int64_t ca, int64_t cb)
+                                int64_t ca, int64_t cb, int64_t srows, int64_t roff)
 {
     // tile: 32 rows x 32 columns of one slot a; the shared tile keeps both global sides coalesced
     __shared__ cplx tile[32][33];
@@ -1024,13 +1026,13 @@ __global__ void relayout_kernel(cplx *__restrict__ dst, const cplx *__restrict__
             if (r < nr) tile[r][b] = src[((int64_t)a * ca + (int64_t)(b0 + b) * cb) * nrows + r0 + r];
         }
         __syncthreads();
-        cplx *d = dst + ((int64_t)a * nrows + r0) * nb + b0;
+        cplx *d = dst + ((int64_t)a * srows + roff + r0) * nb + b0;
         for (int t = threadIdx.x; t < nr * nbt; t += blockDim.x) {
             const int r = t / nbt, b = t - r * nbt;
             d[(int64_t)r * nb + b] = tile[r][b];
         }
     } else {
-        const cplx *sp = src + ((int64_t)a * nrows + r0) * nb + b0;
+        const cplx *sp = src + ((int64_t)a * srows + roff + r0) * nb + b0;
         for (int t = threadIdx.x; t < nr * nbt; t += blockDim.x) {
             const int r = t / nbt, b = t - r * nbt;
             tile[r][b] = sp[(int64_t)r * nb + b];
@@ -1044,20 +1046,20 @@ __global__ void relayout_kernel(cplx *__restrict__ dst, const cplx *__restrict__
 }
 
 cudaError_t launch_host_to_stack(cplx *dst, const cplx *src, int64_t nrows, int na, int nb, int64_t ca, int64_t cb,
-                                 cudaStream_t s)
+                                 int64_t srows, int64_t roff, cudaStream_t s)
 {
     if (nrows == 0 || na == 0 || nb == 0) return cudaSuccess;
     dim3 grid((unsigned)((nrows + 31) / 32), (unsigned)na, (unsigned)((nb + 31) / 32));
-    relayout_kernel<true><<<grid, 256, 0, s>>>(dst, src, nrows, na, nb, ca, cb);
+    relayout_kernel<true><<<grid, 256, 0, s>>>(dst, src, nrows, na, nb, ca, cb, srows, roff);
     return cudaGetLastError();
 }
 
 cudaError_t launch_stack_to_host(cplx *dst, const cplx *src, int64_t nrows, int na, int nb, int64_t ca, int64_t cb,
-                                 cudaStream_t s)
+                                 int64_t srows, int64_t roff, cudaStream_t s)
 {
     if (nrows == 0 || na == 0 || nb == 0) return cudaSuccess;
     dim3 grid((unsigned)((nrows + 31) / 32), (unsigned)na, (unsigned)((nb + 31) / 32));
-    relayout_kernel<false><<<grid, 256, 0, s>>>(dst, src, nrows, na, nb, ca, cb);
+    relayout_kernel<false><<<grid, 256, 0, s>>>(dst, src, nrows, na, nb, ca, cb, srows, roff);
     return cudaGetLastError();
 }
 
@@ -1068,13 +1070,13 @@ static const int GRAM_ROWS_PER_BLOCK = 2048;
 int gram_num_blocks(int64_t nrows) { return (int)((nrows + GRAM_ROWS_PER_BLOCK - 1) / GRAM_ROWS_PER_BLOCK); }
 
 __global__ void __launch_bounds__(128)
-gram_partial_kernel(const cplx *__restrict__ Y, int64_t nrows, int k, cplx *__restrict__ partial)
+gram_partial_kernel(const cplx *__restrict__ Y, int64_t nrows, int k, int64_t slot_stride, cplx *__restrict__ partial)
 {
     extern __shared__ cplx tile[];  // [64][k]
     const int w = blockIdx.y, nw = gridDim.y;
     const int64_t r_begin = (int64_t)blockIdx.x * GRAM_ROWS_PER_BLOCK;
     const int64_t r_end = min(nrows, r_begin + GRAM_ROWS_PER_BLOCK);
-    const cplx *Yw = Y + (int64_t)w * nrows * k;
+    const cplx *Yw = Y + (int64_t)w * slot_stride;
     const int npairs = k * k;
     // each thread owns up to 8 (i,j) pairs (k <= 32 -> 1024 pairs / 128 threads)
     cplx acc[8];
@@ -1116,12 +1118,13 @@ __global__ void gram_reduce_kernel(const cplx *__restrict__ partial, int nblk, i
     G[t] = s;
 }
 
-cudaError_t launch_gram(const cplx *Y, int64_t nrows, int k, int nw, cplx *partial, cplx *G, cudaStream_t s)
+cudaError_t launch_gram(const cplx *Y, int64_t nrows, int k, int nw, int64_t slot_stride, cplx *partial, cplx *G,
+                        cudaStream_t s)
 {
     if (k > 32) return cudaErrorInvalidValue;
     const int nblk = gram_num_blocks(nrows);
     dim3 grid((unsigned)nblk, (unsigned)nw);
-    gram_partial_kernel<<<grid, 128, (size_t)64 * k * sizeof(cplx), s>>>(Y, nrows, k, partial);
+    gram_partial_kernel<<<grid, 128, (size_t)64 * k * sizeof(cplx), s>>>(Y, nrows, k, slot_stride, partial);
     const int64_t n_out = (int64_t)nw * k * k;
     gram_reduce_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, s>>>(partial, nblk, n_out, G);
     return cudaGetLastError();
@@ -1346,5 +1349,95 @@ cudaError_t launch_spmm_stack(const CsrDev &M, const cplx *in, cplx *out, int na
     if (M.nrows == 0 || na == 0 || nb == 0) return cudaSuccess;
     dim3 grid((unsigned)((M.nrows * nb + 255) / 256), (unsigned)na);
     spmm_stack_kernel<<<grid, 256, 0, s>>>(M.rowptr, M.col, M.val, M.nrows, M.ncols, in, out, nb);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Halo exchange over NVLink peer memory (row-partitioned runs, one process per GPU; PETSc's VecScatter of MPIAIJ).
+//   push : for every outgoing message, gather the rows the peer needs and store them straight into the peer's
+//          mailbox (peer pointer obtained through CUDA IPC) -- remote stores ride NVLink, no staging copy;
+//   signal: one thread per peer publishes the epoch with a system-scope fence (release) in the peer's flag array;
+//   wait+unpack: every CTA spins (acquire) until all expected peers have published the epoch, then copies the
+//          mailbox rows into the ghost rows of the destination block vector.
+// =====================================================================================================
+struct HaloMsgDev {
+    cplx *peer_mailbox;        // base of my region in the peer's mailbox slot (already offset for this epoch parity)
+    const int32_t *rows;       // local rows to send
+    int count;
+};
+
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const cplx *__restrict__ src, int nvec, const HaloMsgDev *__restrict__ msgs, int parity, int nvec_max)
+{
+    const HaloMsgDev m = msgs[blockIdx.y];
+    const int64_t n = (int64_t)m.count * nvec;
+    cplx *dst = m.peer_mailbox + (int64_t)parity * m.count * nvec_max;   // two slots per message, chosen by epoch parity
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / nvec;
+        const int iv = (int)(e - r * nvec);
+        dst[e] = src[(int64_t)m.rows[r] * nvec + iv];
+    }
+}
+
+__global__ void halo_signal_kernel(unsigned long long *const *__restrict__ peer_flags, int npeers, unsigned long long epoch)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npeers) return;
+    __threadfence_system();   // the push kernel's stores (previous kernel in this stream) are ordered before the flag
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(peer_flags[p]), "l"(epoch) : "memory");
+}
+
+struct HaloInDev {
+    const cplx *mailbox;       // my mailbox region holding this peer's rows (slot 0)
+    const unsigned long long *flag;
+    int64_t dest_row0;
+    int count;
+};
+
+__global__ void __launch_bounds__(256)
+halo_wait_unpack_kernel(cplx *__restrict__ dst, int nvec, const HaloInDev *__restrict__ ins, int parity, int nvec_max,
+                        unsigned long long epoch)
+{
+    const HaloInDev m = ins[blockIdx.y];
+    if (threadIdx.x == 0) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(m.flag) : "memory");
+        } while (v < epoch);
+    }
+    __syncthreads();
+    const int64_t n = (int64_t)m.count * nvec;
+    const cplx *src = m.mailbox + (int64_t)parity * m.count * nvec_max;
+    cplx *d = dst + m.dest_row0 * nvec;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        d[e] = __ldcv(src + e);   // bypass caches: the data were written by another GPU
+}
+
+cudaError_t launch_halo_push(const cplx *src, int nvec, const void *msgs_dev, int nmsgs, int max_count, int parity,
+                             int nvec_max, cudaStream_t s)
+{
+    if (nmsgs == 0) return cudaSuccess;
+    const int64_t n = (int64_t)max_count * nvec;
+    const unsigned gx = (unsigned)min((int64_t)64, (n + 255) / 256);
+    dim3 grid(gx ? gx : 1, (unsigned)nmsgs);
+    halo_push_kernel<<<grid, 256, 0, s>>>(src, nvec, (const HaloMsgDev *)msgs_dev, parity, nvec_max);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_halo_signal(void *peer_flags_dev, int npeers, unsigned long long epoch, cudaStream_t s)
+{
+    if (npeers == 0) return cudaSuccess;
+    halo_signal_kernel<<<1, 32, 0, s>>>((unsigned long long *const *)peer_flags_dev, npeers, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_halo_wait_unpack(cplx *dst, int nvec, const void *ins_dev, int nin, int max_count, int parity,
+                                    int nvec_max, unsigned long long epoch, cudaStream_t s)
+{
+    if (nin == 0) return cudaSuccess;
+    const int64_t n = (int64_t)max_count * nvec;
+    const unsigned gx = (unsigned)min((int64_t)64, (n + 255) / 256);
+    dim3 grid(gx ? gx : 1, (unsigned)nin);
+    halo_wait_unpack_kernel<<<grid, 256, 0, s>>>(dst, nvec, (const HaloInDev *)ins_dev, parity, nvec_max, epoch);
     return cudaGetLastError();
 }

@@ -48,6 +48,9 @@ struct BandedStepArgs {
     const cplx *f_prev = nullptr, *f_half = nullptr, *f_next = nullptr;
     cplx *snap = nullptr;
     double dt = 0;
+    // rows [own_begin, own_end) of the local arrays are advanced by this rank; rows outside are halo copies of the
+    // neighbours' rows (row-partitioned runs).  own_end < 0 means "all rows".
+    int64_t own_begin = 0, own_end = -1;
 };
 bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, int variant);
 int banded_tile_rows(int64_t lo_bw, int64_t hi_bw, int nv, int variant);
@@ -90,15 +93,19 @@ cudaError_t launch_idft_taylor(cplx *out, int64_t out_stride, const cplx *coef, 
                                int P, int K, int64_t U, cplx *out_prev, cudaStream_t s);
 
 // reference (column-major, column c = a*ca + b*cb) <-> device stack T[a][row][b]
+// The stack has `srows` rows per slot; the nrows host rows are its rows [roff, roff + nrows) (row-partitioned runs keep
+// halo rows around the owned ones).
 cudaError_t launch_host_to_stack(cplx *dst, const cplx *src_colmajor, int64_t nrows, int na, int nb, int64_t ca,
-                                 int64_t cb, cudaStream_t s);
+                                 int64_t cb, int64_t srows, int64_t roff, cudaStream_t s);
 cudaError_t launch_stack_to_host(cplx *dst_colmajor, const cplx *src, int64_t nrows, int na, int nb, int64_t ca,
-                                 int64_t cb, cudaStream_t s);
+                                 int64_t cb, int64_t srows, int64_t roff, cudaStream_t s);
 
 // ---- per-frequency small dense work (QRAllFreqs.c, SVDAllFreqs*.c) -----------------------------------
 // G[w] = Y_w^H Y_w for all w (k x k each, row-major), deterministic two-stage reduction. partial: nblk*nw*k*k
 int gram_num_blocks(int64_t nrows);
-cudaError_t launch_gram(const cplx *Y, int64_t nrows, int k, int nw, cplx *partial, cplx *G, cudaStream_t s);
+// Y_w starts at Y + w*slot_stride (complex elements); only the nrows rows given are summed (owned rows of a partition)
+cudaError_t launch_gram(const cplx *Y, int64_t nrows, int k, int nw, int64_t slot_stride, cplx *partial, cplx *G,
+                        cudaStream_t s);
 // M[w] = R_w^{-1} with G_w = R_w^H R_w (Cholesky, upper R, positive diagonal); status[w] != 0 on breakdown
 cudaError_t launch_chol_inverse(const cplx *G, int k, int nw, cplx *M, int *status, cudaStream_t s);
 // eigen-decomposition of G_w (Hermitian Jacobi): sigma[w][m] = sqrt(lambda_m) descending, M[w] = V * diag(1/sigma)
@@ -114,3 +121,13 @@ cudaError_t launch_fill_zero(cplx *p, int64_t n, cudaStream_t s);
 
 // sparse (CSR, nrows x ncols) times stack: out[a][r][b] = sum_c M[r][c] in[a][c][b]  (ApplyWeightMats.c:18-76)
 cudaError_t launch_spmm_stack(const CsrDev &M, const cplx *in, cplx *out, int na, int nb, cudaStream_t s);
+
+// ---- halo exchange over peer memory (row-partitioned runs) ---------------------------------------------------------
+// device-side descriptors (layout must match kernels.cu)
+struct HaloMsgHost { cplx *peer_mailbox; const int32_t *rows; int count; int pad; };
+struct HaloInHost { const cplx *mailbox; const unsigned long long *flag; int64_t dest_row0; int count; int pad; };
+cudaError_t launch_halo_push(const cplx *src, int nvec, const void *msgs_dev, int nmsgs, int max_count, int parity,
+                             int nvec_max, cudaStream_t s);
+cudaError_t launch_halo_signal(void *peer_flags_dev, int npeers, unsigned long long epoch, cudaStream_t s);
+cudaError_t launch_halo_wait_unpack(cplx *dst, int nvec, const void *ins_dev, int nin, int max_count, int parity,
+                                    int nvec_max, unsigned long long epoch, cudaStream_t s);

@@ -31,28 +31,39 @@ import numpy as np
 GL_PARAMS = dict(nu=2.0 + 0.2j, gamma=1.0 - 1.0j, mu2=-0.01, mu_max=-0.02, dx=200.0 / 499.0)
 
 
-def ginzburg_landau(N: int, **over):
+def ginzburg_landau(N: int, row_range=None, **over):
+    """row_range=(r0, r1) builds only those rows (global column indices), for per-GPU generation"""
     p = {**GL_PARAMS, **over}
     nu, gamma, mu2, mu_max, dx = p["nu"], p["gamma"], p["mu2"], p["mu_max"], p["dx"]
+    if row_range is not None:
+        r0, r1 = row_range
+        Nf, rp, ci, va = _gl_rows(N, np.arange(r0, r1, dtype=np.int64), nu, gamma, mu2, mu_max, dx)
+        return Nf, rp, ci, va
     r = np.arange(N, dtype=np.int64)
+    return _gl_rows(N, r, nu, gamma, mu2, mu_max, dx)
+
+
+def _gl_rows(N, r, nu, gamma, mu2, mu_max, dx):
+    n = r.size
     xi = -100.0 + 200.0 * r / max(N - 1, 1)
     mu = mu_max + mu2 * xi * xi / 2.0
     # stencil coefficients for columns r-2, r-1, r, r+1
-    c_m2 = np.full(N, -nu * (1.0 / (2 * dx)), np.complex128)
-    c_m1 = np.full(N, -nu * (-4.0 / (2 * dx)) + gamma / dx**2, np.complex128)
+    c_m2 = np.full(n, -nu * (1.0 / (2 * dx)), np.complex128)
+    c_m1 = np.full(n, -nu * (-4.0 / (2 * dx)) + gamma / dx**2, np.complex128)
     c_0 = -nu * (3.0 / (2 * dx)) - 2.0 * gamma / dx**2 + mu.astype(np.complex128)
-    c_p1 = np.full(N, gamma / dx**2, np.complex128)
+    c_p1 = np.full(n, gamma / dx**2, np.complex128)
     # every row keeps exactly 4 stored entries (as A_GL does): the window is shifted at the ends
     # and the out-of-domain coefficients are dropped (Dirichlet) by storing explicit zeros.
     start = np.clip(r - 2, 0, N - 4)
     col = (start[:, None] + np.arange(4)[None, :]).astype(np.int64)
-    val = np.zeros((N, 4), np.complex128)
+    val = np.zeros((n, 4), np.complex128)
+    idx = np.arange(n)
     for off, c in ((-2, c_m2), (-1, c_m1), (0, c_0), (1, c_p1)):
         tgt = r + off
         ok = (tgt >= 0) & (tgt < N)
         slot = tgt - start
-        val[r[ok], slot[ok]] = c[ok]
-    rowptr = np.arange(N + 1, dtype=np.int64) * 4
+        val[idx[ok], slot[ok]] = c[ok]
+    rowptr = np.arange(n + 1, dtype=np.int64) * 4
     return N, rowptr, col.reshape(-1), val.reshape(-1)
 
 
