@@ -266,3 +266,18 @@ def test_kernel_variants_agree_with_oracle(pkg, O, A_GL, opts):
         assert rel_err(r.get_snapshots(), snaps_ref) < ACTION_TOL
         assert rel_err(got, ref) < ACTION_TOL
     r.close()
+
+
+def test_row_partition_two_gpus():
+    # the row-partitioned path (halo exchange by peer stores, both local layouts) against the single-GPU path;
+    # needs 2 GPUs -- on a 1-GPU box the same check is run by tools/dist_check.py under `gpurun --gpus 2`
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

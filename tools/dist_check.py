@@ -86,7 +86,7 @@ def main():
     full = pkg.synthetic.ginzburg_landau(N)
     gl = lambda a, b: pkg.synthetic.ginzburg_landau(N, row_range=(a, b))[1:]  # noqa: E731
     for layout in (1, 0):
-        ok &= run_case(pkg, "ginzburg-landau", N, gl, full, 3, layout, (2, 1), 5, 6, 2.0, 0.003, 0.4, rank, world, lrank)
+        ok &= run_case(pkg, "ginzburg-landau", N, gl, full, 3, layout, (2, 1), 6, 6, 2.0, 0.003, 0.4, rank, world, lrank)
     # 2-D LNS-like block stencil (45 nnz/row): layout 0
     shape = (24, 20)
     fullL = pkg.synthetic.lns_stencil(shape, nvar=5)
