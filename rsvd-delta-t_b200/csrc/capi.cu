@@ -48,11 +48,16 @@ struct CsrOwned {
     int dia_lo = 0, dia_hi = 0;
     bool dia_valid = false;
     std::vector<unsigned char> row_regular;
+    // block-CSR form (dense B x B blocks) for the LNS-type operators
+    BcsrDev bcsr;
+    DevBuf b_rowptr, b_col, b_val;
+    bool bcsr_valid = false;
     int plan_nv = -1, plan_variant = -1, plan_mode = -1, ntiles = 0, nslow = 0;
     bool plan_ok = false;
     void release()
     {
         rowptr.release(); col.release(); val.release(); dia.release(); tile_ok.release(); slow_ranges.release();
+        b_rowptr.release(); b_col.release(); b_val.release(); bcsr = BcsrDev(); bcsr_valid = false;
         d = CsrDev(); set = false; dia_valid = false; plan_nv = -1; plan_ok = false; row_regular.clear();
     }
 };
@@ -114,6 +119,7 @@ struct rsvdt_context {
     int64_t idft_variant = 0;
     int64_t use_banded = 3;   // 0: stage kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged DIA step
     int64_t tma_variant = 0;  // 0: tiles sized for 3 CTAs/SM, 1: for 2 CTAs/SM
+    int64_t use_bcsr = 1;     // block-CSR stage kernel when the operator has dense B x B blocks
 
     // instrumentation
     int64_t launches = 0;
@@ -264,6 +270,59 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
     dst.lo_bw = lo;
     dst.hi_bw = hi;
     dst.set = true;
+    // ---- block structure analysis: dense B x B blocks on an aligned block grid (B = 5, 4, 3) ------------------------
+    for (int B : {5, 4, 3}) {
+        if (out_rows % B || out_cols % B || nnz == 0 || maxnnz < 2 * B) continue;
+        bool okb = true;
+        int64_t nblocks = 0;
+        for (int64_t br = 0; br < out_rows / B && okb; br++) {
+            const int64_t p0 = rp[br * B], len = rp[br * B + 1] - p0;
+            if (len % B) { okb = false; break; }
+            for (int r = 1; r < B && okb; r++) {
+                const int64_t q0 = rp[br * B + r];
+                if (rp[br * B + r + 1] - q0 != len) { okb = false; break; }
+                for (int64_t i = 0; i < len; i++)
+                    if (ci[q0 + i] != ci[p0 + i]) { okb = false; break; }
+            }
+            for (int64_t i = 0; i < len && okb; i += B) {
+                if (ci[p0 + i] % B) { okb = false; break; }
+                for (int j = 1; j < B; j++)
+                    if (ci[p0 + i + j] != ci[p0 + i] + j) { okb = false; break; }
+                if (i && ci[p0 + i] <= ci[p0 + i - B]) okb = false;   // ascending blocks
+            }
+            nblocks += len / B;
+        }
+        if (!okb) continue;
+        const int64_t nbrows = out_rows / B;
+        std::vector<int64_t> brp((size_t)nbrows + 1, 0);
+        std::vector<int32_t> bc((size_t)nblocks);
+        const int BS = (B * B + 1) & ~1;   // padded to an even number of entries: 32-byte aligned blocks
+        std::vector<cplx> bv((size_t)nblocks * BS, make_double2(0.0, 0.0));
+        int64_t pb = 0;
+        for (int64_t br = 0; br < nbrows; br++) {
+            const int64_t p0 = rp[br * B], len = rp[br * B + 1] - p0;
+            for (int64_t i = 0; i < len; i += B, pb++) {
+                bc[(size_t)pb] = (int32_t)(ci[p0 + i] / B);
+                for (int r = 0; r < B; r++)
+                    for (int j = 0; j < B; j++) bv[(size_t)(pb * BS + j * B + r)] = va[rp[br * B + r] + i + j];   // column-major block
+            }
+            brp[(size_t)br + 1] = pb;
+        }
+        CU(dst.b_rowptr.alloc(brp.size() * sizeof(int64_t)));
+        CU(dst.b_col.alloc(std::max<size_t>(bc.size(), 1) * sizeof(int32_t)));
+        CU(dst.b_val.alloc(std::max<size_t>(bv.size(), 1) * sizeof(cplx)));
+        CU(cudaMemcpy(dst.b_rowptr.p, brp.data(), brp.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dst.b_col.p, bc.data(), bc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dst.b_val.p, bv.data(), bv.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+        dst.bcsr.B = B;
+        dst.bcsr.nbrows = nbrows;
+        dst.bcsr.nblocks = nblocks;
+        dst.bcsr.browptr = dst.b_rowptr.as<int64_t>();
+        dst.bcsr.bcol = dst.b_col.as<int32_t>();
+        dst.bcsr.bval = dst.b_val.as<cplx>();
+        dst.bcsr_valid = true;
+        break;
+    }
     // ---- diagonal pattern analysis (square, narrow-band operators only) ------------------------------------------
     if (out_rows == out_cols && lo <= 8 && hi <= 8 && out_rows >= 64) {
         std::vector<int64_t> cnt(17, 0);
@@ -414,6 +473,13 @@ int dist_exchange(rsvdt_handle h, cplx *buf, int nvec)
 
 // ---- one RK4 step on a block of nv vectors (TSRK4.c:18-47 / TSTransRK4.c:15-36) ---------------------------
 // y: state (in/out), xa/xb/acc: work, f_prev/f_half/f_next: forcing slices or nullptr, snap: optional copy of y_{n+1}
+cudaError_t launch_stage_any(rsvdt_handle h, const CsrOwned &Op, int nv, int mode, const StageArgs &a)
+{
+    if (h->use_bcsr && Op.bcsr_valid && bcsr_stage_supported(Op.bcsr.B, nv))
+        return launch_rk4_stage_bcsr(Op.bcsr, nv, mode, a, (int)h->stage_variant, h->stream);
+    return launch_rk4_stage(Op.d, nv, mode, a, (int)h->stage_variant, h->stream);
+}
+
 int rk4_step(rsvdt_handle h, const CsrOwned &Op, int nv, cplx *y, cplx *xa, cplx *xb, cplx *acc, const cplx *f_prev,
              const cplx *f_half, const cplx *f_next, cplx *snap)
 {
@@ -423,28 +489,28 @@ int rk4_step(rsvdt_handle h, const CsrOwned &Op, int nv, cplx *y, cplx *xa, cplx
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = y; a.ybase = y; a.f = f_prev; a.xout = xa; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6;
-        CU(launch_rk4_stage(Op.d, nv, 0, a, (int)h->stage_variant, h->stream));
+        CU(launch_stage_any(h, Op, nv, 0, a));
     }
     RS(dist_exchange(h, xa, nv));
     {   // k2 = Op x2 + F2 ; x3 = y + dt/2 k2 ; acc += dt/6*2 k2                   TSRK4.c:31-32,45
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xa; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xb; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6 * 2;
-        CU(launch_rk4_stage(Op.d, nv, 1, a, (int)h->stage_variant, h->stream));
+        CU(launch_stage_any(h, Op, nv, 1, a));
     }
     RS(dist_exchange(h, xb, nv));
     {   // k3 = Op x3 + F2 ; x4 = y + dt k3 ; acc += dt/6*2 k3                     TSRK4.c:33-34,46
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xb; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xa; a.acc_out = acc; a.cx = dt; a.ca = dt / 6 * 2;
-        CU(launch_rk4_stage(Op.d, nv, 1, a, (int)h->stage_variant, h->stream));
+        CU(launch_stage_any(h, Op, nv, 1, a));
     }
     RS(dist_exchange(h, xa, nv));
     {   // k4 = Op x4 + F3 ; y = acc + dt/6 k4 ; snapshot                         TSRK4.c:35,47 ; SaveSnapshots.c:26-28
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xa; a.f = f_next; a.acc_in = acc; a.acc_out = y; a.snap = snap; a.ca = dt / 6;
-        CU(launch_rk4_stage(Op.d, nv, 2, a, (int)h->stage_variant, h->stream));
+        CU(launch_stage_any(h, Op, nv, 2, a));
     }
     RS(dist_exchange(h, y, nv));
     h->launches += 4;
@@ -1395,6 +1461,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "idft_variant")) h->idft_variant = value;
     else if (!strcmp(name, "use_banded")) h->use_banded = value;
     else if (!strcmp(name, "tma_variant")) h->tma_variant = value;
+    else if (!strcmp(name, "use_bcsr")) h->use_bcsr = value;
     else return fail(h, RSVDT_ERR_ARG, "unknown option '%s'", name);
     return RSVDT_OK;
 }

@@ -78,6 +78,159 @@ rk4_stage_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
     }
 }
 
+// =====================================================================================================
+// K1e: the same stage on a block-CSR (BCSR) operator with dense B x B blocks (LNS operators: B = number of flow variables
+//   per grid point).  thread <-> (block row, CV consecutive test vectors): one column index per block instead of per entry
+//   (16.16 instead of 20 bytes per nonzero), each gathered x value feeds B rows and each operator entry feeds CV test
+//   vectors from registers -- the CSR kernel is bound by the L1 -> register-file fill rate (ncu: L1 wavefronts 72 %, DRAM
+//   30 % on the 3-D operator), this one needs (16/CV + 16/B) instead of 36 bytes of fill per complex FMA.
+//   Summation order per row = ascending columns, identical to the CSR kernel (bit-identical results).
+// =====================================================================================================
+// two complex numbers moved by one 256-bit access (LDG.E.256 / STG.E.256 on sm_100a)
+struct __align__(32) cplx2 { cplx a, b; };
+DEVFN cplx2 ldg2(const cplx *p)
+{
+    cplx2 v;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a.x), "=d"(v.a.y), "=d"(v.b.x), "=d"(v.b.y) : "l"(p));
+    return v;
+}
+DEVFN void st2(cplx *p, const cplx v0, const cplx v1)
+{
+    cplx2 v;
+    v.a = v0;
+    v.b = v1;
+    *reinterpret_cast<cplx2 *>(p) = v;
+}
+DEVFN cplx axpy1(double c, const cplx s, const cplx y) { return make_double2(fma(c, s.x, y.x), fma(c, s.y, y.y)); }
+
+// BS = padded block size in complex entries (B*B rounded up to even so that every block starts 32-byte aligned)
+template <int B, int CV, int MODE, bool HAS_F>
+__global__ void __launch_bounds__(128, 4)
+rk4_stage_bcsr_kernel(const int64_t *__restrict__ browptr, const int32_t *__restrict__ bcol, const cplx *__restrict__ bval,
+                      int nv, int nvp, int64_t n_threads, StageArgs a)
+{
+    constexpr int BS = (B * B + 1) & ~1;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    const int64_t br = t / nvp;
+    const int iv0 = (int)(t - br * nvp) * CV;
+    const int64_t u0 = br * B * nv + iv0;   // unit of (first row of the block row, iv0); next row: + nv
+    cplx s[B][CV];
+#pragma unroll
+    for (int r = 0; r < B; r++) {
+        if (CV == 2) {
+            cplx2 v;
+            v.a = v.b = make_double2(0.0, 0.0);
+            if (HAS_F) v = ldg2(a.f + u0 + r * nv);
+            s[r][0] = v.a;
+            s[r][CV - 1] = v.b;
+        } else {
+            s[r][0] = HAS_F ? ldg(a.f + u0 + r * nv) : make_double2(0.0, 0.0);
+        }
+    }
+    const int64_t p1 = __ldg(browptr + br + 1);
+    int64_t p = __ldg(browptr + br);
+    int32_t cnext = (p < p1) ? __ldg(bcol + p) : 0;
+    for (; p < p1; ++p) {
+        const cplx *__restrict__ xb = a.xin + (int64_t)cnext * B * nv + iv0;
+        if (p + 1 < p1) cnext = __ldg(bcol + p + 1);   // the next block's column index is in flight during this block's FMAs
+        const cplx *__restrict__ av = bval + p * BS;
+        // Block entries are stored column by column ([j][r]) and fetched two at a time; only one gathered x row (plus the
+        // prefetched next one) is live, which keeps the register count low enough for 4-5 CTAs per SM.
+        cplx xc[CV], xn[CV];
+        if (CV == 2) { const cplx2 v = ldg2(xb); xn[0] = v.a; xn[CV - 1] = v.b; } else { xn[0] = ldg(xb); }
+#pragma unroll
+        for (int e = 0; e < B * B; e += 2) {
+            const cplx2 aa = ldg2(av + e);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int ee = e + h;
+                if (ee < B * B) {
+                    const int j = ee / B, r = ee % B;
+                    if (r == 0) {
+#pragma unroll
+                        for (int c = 0; c < CV; c++) xc[c] = xn[c];
+                        if (j + 1 < B) {
+                            if (CV == 2) { const cplx2 v = ldg2(xb + (j + 1) * nv); xn[0] = v.a; xn[CV - 1] = v.b; }
+                            else { xn[0] = ldg(xb + (j + 1) * nv); }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < CV; c++) cfma(s[r][c], h ? aa.b : aa.a, xc[c]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < B; r++) {
+        const int64_t u = u0 + r * nv;
+        if (CV == 2) {
+            const cplx s0 = s[r][0], s1 = s[r][CV - 1];
+            if (MODE == 0) {
+                const cplx2 y = ldg2(a.ybase + u);
+                st2(a.xout + u, axpy1(a.cx, s0, y.a), axpy1(a.cx, s1, y.b));
+                st2(a.acc_out + u, axpy1(a.ca, s0, y.a), axpy1(a.ca, s1, y.b));
+            } else if (MODE == 1) {
+                const cplx2 y = ldg2(a.ybase + u);
+                const cplx2 ac = *reinterpret_cast<const cplx2 *>(a.acc_in + u);
+                st2(a.xout + u, axpy1(a.cx, s0, y.a), axpy1(a.cx, s1, y.b));
+                st2(a.acc_out + u, axpy1(a.ca, s0, ac.a), axpy1(a.ca, s1, ac.b));
+            } else {
+                const cplx2 ac = *reinterpret_cast<const cplx2 *>(a.acc_in + u);
+                const cplx y0 = axpy1(a.ca, s0, ac.a), y1 = axpy1(a.ca, s1, ac.b);
+                st2(a.acc_out + u, y0, y1);
+                if (a.snap) st2(a.snap + u, y0, y1);
+            }
+        } else {
+            const cplx sv = s[r][0];
+            if (MODE == 0) {
+                const cplx y = ldg(a.ybase + u);
+                a.xout[u] = axpy1(a.cx, sv, y);
+                a.acc_out[u] = axpy1(a.ca, sv, y);
+            } else if (MODE == 1) {
+                const cplx y = ldg(a.ybase + u);
+                const cplx ac = a.acc_in[u];
+                a.xout[u] = axpy1(a.cx, sv, y);
+                a.acc_out[u] = axpy1(a.ca, sv, ac);
+            } else {
+                const cplx yn = axpy1(a.ca, sv, a.acc_in[u]);
+                a.acc_out[u] = yn;
+                if (a.snap) a.snap[u] = yn;
+            }
+        }
+    }
+}
+
+template <int B, int CV>
+static cudaError_t bcsr_launch(const BcsrDev &Op, int nv, int mode, const StageArgs &a, cudaStream_t s)
+{
+    const int nvp = nv / CV;
+    const int64_t n_threads = Op.nbrows * nvp;
+    if (n_threads == 0) return cudaSuccess;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n_threads + threads - 1) / threads);
+    const bool hf = a.f != nullptr;
+#define LAUNCH(M, F) rk4_stage_bcsr_kernel<B, CV, M, F><<<blocks, threads, 0, s>>>(Op.browptr, Op.bcol, Op.bval, nv, nvp, n_threads, a)
+    if (mode == 0) { if (hf) LAUNCH(0, true); else LAUNCH(0, false); }
+    else if (mode == 1) { if (hf) LAUNCH(1, true); else LAUNCH(1, false); }
+    else { if (hf) LAUNCH(2, true); else LAUNCH(2, false); }
+#undef LAUNCH
+    return cudaGetLastError();
+}
+
+bool bcsr_stage_supported(int B, int nv) { return (B == 3 || B == 4 || B == 5) && nv >= 1; }
+
+cudaError_t launch_rk4_stage_bcsr(const BcsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s)
+{
+    const bool two = (nv % 2 == 0) && variant != 1;
+    switch (Op.B) {
+        case 3: return two ? bcsr_launch<3, 2>(Op, nv, mode, a, s) : bcsr_launch<3, 1>(Op, nv, mode, a, s);
+        case 4: return two ? bcsr_launch<4, 2>(Op, nv, mode, a, s) : bcsr_launch<4, 1>(Op, nv, mode, a, s);
+        case 5: return two ? bcsr_launch<5, 2>(Op, nv, mode, a, s) : bcsr_launch<5, 1>(Op, nv, mode, a, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s)
 {
     (void)variant;

@@ -40,6 +40,20 @@ struct StageArgs {
 
 cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s);
 
+// Block-CSR form (dense B x B blocks, e.g. the 5 flow variables of an LNS operator): browptr[nbrows+1], bcol[nblocks]
+// (block column), bval[nblocks][BS] with the B*B entries column-major ([j][r]) and BS = B*B rounded up to even (32-byte aligned
+// blocks for 256-bit loads).
+struct BcsrDev {
+    int B = 0;
+    int64_t nbrows = 0, nblocks = 0;
+    int64_t *browptr = nullptr;
+    int32_t *bcol = nullptr;
+    cplx *bval = nullptr;
+};
+bool bcsr_stage_supported(int B, int nv);
+// variant 1 forces one test vector per thread (default: two when nv is even)
+cudaError_t launch_rk4_stage_bcsr(const BcsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s);
+
 // Whole RK4 step in one kernel for narrow-band operators (all 4 stages, halo recomputation in shared memory).
 //   f_prev / f_half / f_next : forcing slices at t_n, t_n + dt/2, t_n + dt (nullptr -> unforced)
 struct BandedStepArgs {

@@ -70,14 +70,22 @@ def test_action_faithful_twiddles_within_reference_tolerance(pkg, O, A_GL):
     r.close()
 
 
-@pytest.mark.parametrize("shape,cplx", [((9, 11), True), ((7, 8), False), ((4, 5, 6), True)])
-def test_action_lns_stencil(pkg, O, shape, cplx):
-    N, rp, ci, va = pkg.synthetic.lns_stencil(shape, nvar=5, complex_coupling=cplx)
+@pytest.mark.parametrize("shape,cplx,nvar,k,opts", [((9, 11), True, 5, 4, {}), ((7, 8), False, 5, 4, {}),
+                                                      ((4, 5, 6), True, 5, 4, {}), ((9, 11), True, 5, 3, {}),
+                                                      ((9, 11), True, 5, 4, dict(use_bcsr=0)),
+                                                      ((9, 11), True, 5, 4, dict(stage_variant=1)),
+                                                      ((6, 7), True, 4, 6, {}), ((5, 6), True, 3, 2, {})])
+def test_action_lns_stencil(pkg, O, shape, cplx, nvar, k, opts):
+    # block-stencil operators: the block-CSR stage kernel (B = 5, 4, 3; one or two test vectors per thread) and the
+    # plain CSR kernel against the oracle
+    N, rp, ci, va = pkg.synthetic.lns_stencil(shape, nvar=nvar, complex_coupling=cplx)
     A = O.Csr(N, N, rp, ci, va)
-    k, Nw = 4, 8
+    Nw = 8
     v = make_vars(O, pkg, N, k, Nw, 2.0, 0.003, 0.5, real=not cplx)
     F = _forcing(N, k * v.Nw_eff, 3)
     r = _handle(pkg, A, v)
+    for name, val in opts.items():
+        r.set_option(name, val)
     for direct in (True, False):
         ref = _oracle_action(O, A, v, F, direct)
         assert rel_err(r.TSActionRK4(F, direct=direct), ref) < ACTION_TOL
