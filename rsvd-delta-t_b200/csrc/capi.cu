@@ -729,6 +729,96 @@ int dft_snapshots(rsvdt_handle h, const cplx *snaps, cplx *Yhat_out)
     return RSVDT_OK;
 }
 
+// TransientRemovalStrategy.c:30-40 on the device.  snaps: Y_all as a stack [Nw+1][row][ik]; Yhat_out: stack [Nw_eff][row][ik].
+//   CreateMtilde.c:41-54      V = QR(Y_all_k) -> shifted CholeskyQR3 per test vector (the snapshot matrices reach cond ~1e7,
+//                             beyond plain CholeskyQR2; any orthonormal basis of the same span gives the same projection),
+//                             MV = exp(A dT) V by ResRatio unforced RK4 steps on every slot, Mt = V^H MV
+//   GalerkinProj.c:26-74      y1, y2 = ResRatio * Y_all[:, 0:Nw | 1:Nw+1] * dft[:, iw]; b = V^H (alpha y1 - y2);
+//                             (alpha I - Mt) c = b;  Y_hat[:, iw] = y1 - V c
+int transient_removal(rsvdt_handle h, bool direct, const cplx *snaps, cplx *Yhat_out)
+{
+    const rsvdt_grid &g = h->g;
+    if (h->dist.on) return fail(h, RSVDT_ERR_USER, "transient removal is not available in row-partitioned runs yet");
+    const int m = (int)g.Nw + 1, nv = (int)g.k, nw = (int)g.Nw_eff;
+    const int64_t rows = h->n_ext, U = rows * nv;
+    DevBuf V, W, Y1, Y2, G, Minv, B1, B2, Cc, part, scratch, alpha_d, status;
+    int rc = RSVDT_OK;
+    auto cleanup = [&]() { for (DevBuf *b : {&V, &W, &Y1, &Y2, &G, &Minv, &B1, &B2, &Cc, &part, &scratch, &alpha_d, &status}) b->release(); };
+#define TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(h, e__ == cudaErrorMemoryAllocation ? RSVDT_ERR_MEM : RSVDT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return rc; } } while (0)
+    const int chunks = stack_gram2_chunks(rows);
+    const int mbmax = std::max(m, nw);
+    TRY(V.alloc((size_t)m * U * sizeof(cplx)));
+    TRY(W.alloc((size_t)m * U * sizeof(cplx)));
+    TRY(G.alloc((size_t)nv * m * mbmax * sizeof(cplx)));
+    TRY(Minv.alloc((size_t)nv * m * m * sizeof(cplx)));
+    TRY(part.alloc((size_t)chunks * nv * m * mbmax * sizeof(cplx)));
+    TRY(status.alloc((size_t)nv * std::max(nw, 1) * sizeof(int)));
+    TRY(cudaMemcpyAsync(V.p, snaps, (size_t)m * U * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
+    std::vector<int> st((size_t)nv * nw);
+    // ---- V = QR(Y_all_k): shifted CholeskyQR3 ---------------------------------------------------------------------
+    for (int pass = 0; pass < 3; pass++) {
+        TRY(launch_stack_gram2(V.as<cplx>(), U, m, V.as<cplx>(), U, m, nv, 0, rows, part.as<cplx>(), G.as<cplx>(), h->stream));
+        // shift of Fukaya et al. (2020): 11 (m n + n (n+1)) u ||X||_2^2, with ||X||_2^2 <= trace(G)
+        const double shift = pass == 0 ? 11.0 * ((double)rows * m + (double)m * (m + 1)) * 1.1e-16 : 0.0;
+        TRY(launch_chol_inverse_big(G.as<cplx>(), m, nv, shift, Minv.as<cplx>(), status.as<int>(), h->stream));
+        TRY(launch_stack_rmul(W.as<cplx>(), U, nullptr, 0, 0.0, V.as<cplx>(), U, m, Minv.as<cplx>(), m, 1.0, nv, rows, h->stream));
+        h->launches += 4;
+        TRY(cudaMemcpyAsync(st.data(), status.p, (size_t)nv * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        TRY(cudaStreamSynchronize(h->stream));
+        for (int z = 0; z < nv; z++)
+            if (st[(size_t)z]) { cleanup(); return fail(h, RSVDT_ERR_NUMERIC, "transient removal: QR breakdown for test vector %d (column %d, pass %d)", z, st[(size_t)z] - 1, pass); }
+        V.swap(W);
+    }
+    // ---- MV = exp(A dT) V (TSExpADeltaT.c:25-34), slot by slot with the fused step kernels ---------------------------
+    TRY(cudaMemcpyAsync(W.p, V.p, (size_t)m * U * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
+    for (int a = 0; a < m; a++) {
+        rc = unforced_steps(h, direct, nv, W.as<cplx>() + (int64_t)a * U, g.ResRatio);
+        if (rc != RSVDT_OK) { cleanup(); return rc; }
+    }
+    // ---- Mt = V^H MV (CreateMtilde.c:49-51) -> Minv buffer reused -----------------------------------------------------
+    TRY(launch_stack_gram2(V.as<cplx>(), U, m, W.as<cplx>(), U, m, nv, 0, rows, part.as<cplx>(), Minv.as<cplx>(), h->stream));
+    W.release();
+    // ---- y1, y2 (GalerkinProj.c:30-46) -----------------------------------------------------------------------------------
+    TRY(Y1.alloc((size_t)nw * U * sizeof(cplx)));
+    TRY(Y2.alloc((size_t)nw * U * sizeof(cplx)));
+    rc = ensure(h, h->coef, (size_t)std::max<int64_t>(g.Nw_eff * g.Nw, 2 * h->chunk_steps * g.Nw_eff) * sizeof(cplx));
+    if (rc != RSVDT_OK) { cleanup(); return rc; }
+    TRY(launch_dft_coef(h->coef.as<cplx>(), nw, (int)g.Nw, g.ResRatio, h->stream));
+    const cplx *s1 = snaps + (direct ? 0 : U), *s2 = snaps + (direct ? U : 0);
+    TRY(launch_small_cgemm(Y1.as<cplx>(), U, h->coef.as<cplx>(), s1, U, nw, (int)g.Nw, U, 0, h->stream));
+    TRY(launch_small_cgemm(Y2.as<cplx>(), U, h->coef.as<cplx>(), s2, U, nw, (int)g.Nw, U, 0, h->stream));
+    // ---- b = V^H (alpha y1 - y2) through B1 = V^H Y1, B2 = V^H Y2 (:55) -------------------------------------------------
+    TRY(B1.alloc((size_t)nv * m * nw * sizeof(cplx)));
+    TRY(B2.alloc((size_t)nv * m * nw * sizeof(cplx)));
+    TRY(launch_stack_gram2(V.as<cplx>(), U, m, Y1.as<cplx>(), U, nw, nv, 0, rows, part.as<cplx>(), B1.as<cplx>(), h->stream));
+    TRY(launch_stack_gram2(V.as<cplx>(), U, m, Y2.as<cplx>(), U, nw, nv, 0, rows, part.as<cplx>(), B2.as<cplx>(), h->stream));
+    Y2.release();
+    // ---- (alpha I - Mt) c = b (:48-62), alpha = exp(+-i w iw dT), dT = dt*ResRatio (:17,49-54) --------------------------------
+    std::vector<cplx> alpha((size_t)nw);
+    const double deltaT = g.dt * (double)g.ResRatio;
+    for (int iw = 0; iw < nw; iw++) {
+        const double ph = (direct ? 1.0 : -1.0) * g.w * (double)iw * deltaT;
+        alpha[(size_t)iw] = make_double2(std::cos(ph), std::sin(ph));
+    }
+    TRY(alpha_d.alloc((size_t)nw * sizeof(cplx)));
+    TRY(cudaMemcpyAsync(alpha_d.p, alpha.data(), (size_t)nw * sizeof(cplx), cudaMemcpyHostToDevice, h->stream));
+    TRY(scratch.alloc((size_t)nv * nw * m * (m + 1) * sizeof(cplx)));
+    TRY(Cc.alloc((size_t)nv * m * nw * sizeof(cplx)));
+    TRY(cudaMemsetAsync(status.p, 0, (size_t)nv * nw * sizeof(int), h->stream));
+    TRY(launch_galerkin_solve(Minv.as<cplx>(), B1.as<cplx>(), B2.as<cplx>(), alpha_d.as<cplx>(), m, nw, nv, scratch.as<cplx>(),
+                              Cc.as<cplx>(), status.as<int>(), h->stream));
+    // ---- Y_hat[:, iw] = y1 - V c (:65-71) ---------------------------------------------------------------------------------
+    TRY(launch_stack_rmul(Yhat_out, U, Y1.as<cplx>(), U, 1.0, V.as<cplx>(), U, m, Cc.as<cplx>(), nw, -1.0, nv, rows, h->stream));
+    h->launches += 12;
+    TRY(cudaMemcpyAsync(st.data(), status.p, (size_t)nv * nw * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < st.size(); i++)
+        if (st[i]) { cleanup(); return fail(h, RSVDT_ERR_NUMERIC, "transient removal: singular Galerkin system (test vector %d, frequency %d)", (int)(i / nw), (int)(i % nw)); }
+#undef TRY
+    cleanup();
+    return RSVDT_OK;
+}
+
 int check_ready(rsvdt_handle h)
 {
     if (!h) return RSVDT_ERR_ARG;
@@ -743,7 +833,6 @@ int ts_action(rsvdt_handle h, bool direct)
     RS(check_ready(h));
     const rsvdt_grid &g = h->g;
     if (h->yhat_rows != h->N || !h->Yhat.p) return fail(h, RSVDT_ERR_STATE, "Y_hat not set or wrong row count");
-    if (g.TransientRemoval) return fail(h, RSVDT_ERR_USER, "TransientRemoval is not implemented yet in this build");
     const int64_t U = h->n_ext * g.k;
     int64_t rend = g.Nt + g.Ns;                                   // TSActionRK4.c:41
     rend += g.TransientRemoval ? g.ResRatio : 0;                  // :42
@@ -762,7 +851,11 @@ int ts_action(rsvdt_handle h, bool direct)
         if (e != cudaSuccess) { rc = fail(h, RSVDT_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e)); break; }
         if ((rc = forced_steps(h, direct, Fhat.as<cplx>(), h->y.as<cplx>(), h->snaps.as<cplx>(), Nstore, 1, rend)) != RSVDT_OK) break;
         // the forcing is no longer needed (:139); its storage becomes the new Y_hat
-        if ((rc = dft_snapshots(h, h->snaps.as<cplx>(), Fhat.as<cplx>())) != RSVDT_OK) break;   // :148
+        if (g.TransientRemoval) {
+            h->slices[0].release();   // the forcing slices are dead: make room for the snapshot-sized work matrices
+            h->slices[1].release();
+            if ((rc = transient_removal(h, direct, h->snaps.as<cplx>(), Fhat.as<cplx>())) != RSVDT_OK) break;   // :147
+        } else if ((rc = dft_snapshots(h, h->snaps.as<cplx>(), Fhat.as<cplx>())) != RSVDT_OK) break;       // :148
         cudaError_t es = cudaStreamSynchronize(h->stream);
         if (es != cudaSuccess) { rc = fail(h, RSVDT_ERR_CUDA, "action failed: %s", cudaGetErrorString(es)); break; }
     } while (0);

@@ -1594,3 +1594,288 @@ cudaError_t launch_halo_wait_unpack(cplx *dst, int nvec, const void *ins_dev, in
     halo_wait_unpack_kernel<<<grid, 256, 0, s>>>(dst, nvec, (const HaloInDev *)ins_dev, parity, nvec_max, epoch);
     return cudaGetLastError();
 }
+
+// =====================================================================================================
+// Transient removal (TransientRemovalStrategy.c:30-40): tall-skinny products on snapshot stacks, batched over test vectors.
+//   A stack element (slot a, row, vector z) lives at  base[a*slot_stride + row*nv + z].
+//   These run once per action (the RK4 loop runs ~45,000 steps), so they are written for clarity and determinism.
+// =====================================================================================================
+// partial[chunk][z][a][b] = sum_{rows of chunk} conj(X[a][row][z]) * Y[b][row][z]
+template <int PB>
+__global__ void __launch_bounds__(256)
+stack_gram2_kernel(const cplx *__restrict__ X, int64_t xs, int ma, const cplx *__restrict__ Y, int64_t ys, int mb, int nv,
+                   int64_t row0, int64_t nrows, int rows_per_chunk, cplx *__restrict__ partial)
+{
+    extern __shared__ cplx sm[];   // Xt[32][ma] then Yt[32][mb]
+    cplx *Xt = sm, *Yt = sm + 32 * ma;
+    const int z = blockIdx.y;
+    const int batch = blockIdx.z;
+    const int npairs = ma * mb;
+    const int64_t rb = row0 + (int64_t)blockIdx.x * rows_per_chunk;
+    const int64_t re = min(row0 + nrows, rb + rows_per_chunk);
+    cplx acc[PB];
+    int pa[PB], pbq[PB];
+#pragma unroll
+    for (int q = 0; q < PB; q++) {
+        acc[q] = make_double2(0.0, 0.0);
+        const int pr = batch * 256 * PB + q * 256 + threadIdx.x;
+        pa[q] = pr < npairs ? pr / mb : -1;
+        pbq[q] = pr < npairs ? pr - (pr / mb) * mb : 0;
+    }
+    for (int64_t r0 = rb; r0 < re; r0 += 32) {
+        const int nr = (int)min((int64_t)32, re - r0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < 32 * ma; t += blockDim.x) {
+            const int a = t / 32, r = t - a * 32;
+            Xt[r * ma + a] = r < nr ? X[(int64_t)a * xs + (r0 + r) * nv + z] : make_double2(0.0, 0.0);
+        }
+        for (int t = threadIdx.x; t < 32 * mb; t += blockDim.x) {
+            const int b = t / 32, r = t - b * 32;
+            Yt[r * mb + b] = r < nr ? Y[(int64_t)b * ys + (r0 + r) * nv + z] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PB; q++) {
+            if (pa[q] >= 0) {
+                cplx s = acc[q];
+                for (int r = 0; r < 32; r++) cfma_conj(s, Xt[r * ma + pa[q]], Yt[r * mb + pbq[q]]);
+                acc[q] = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PB; q++) {
+        const int pr = batch * 256 * PB + q * 256 + threadIdx.x;
+        if (pr < npairs) partial[((int64_t)blockIdx.x * nv + z) * npairs + pr] = acc[q];
+    }
+}
+
+int stack_gram2_chunks(int64_t nrows) { return (int)((nrows + 8191) / 8192); }
+
+// G: [nv][ma][mb]; partial: chunks*nv*ma*mb
+cudaError_t launch_stack_gram2(const cplx *X, int64_t xs, int ma, const cplx *Y, int64_t ys, int mb, int nv, int64_t row0,
+                               int64_t nrows, cplx *partial, cplx *G, cudaStream_t s)
+{
+    constexpr int PB = 8;
+    const int chunks = stack_gram2_chunks(nrows);
+    const int npairs = ma * mb;
+    const size_t smem = (size_t)32 * (ma + mb) * sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(stack_gram2_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)chunks, (unsigned)nv, (unsigned)((npairs + 256 * PB - 1) / (256 * PB)));
+    stack_gram2_kernel<PB><<<grid, 256, smem, s>>>(X, xs, ma, Y, ys, mb, nv, row0, nrows, 8192, partial);
+    const int64_t n_out = (int64_t)nv * npairs;
+    gram_reduce_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, s>>>(partial, chunks, n_out, G);
+    return cudaGetLastError();
+}
+
+// Out[b][row][z] = beta * Z[b][row][z] + alpha * sum_a X[a][row][z] * M[z][a][b]     (M: [nv][ma][mb] row-major)
+template <int BT>
+__global__ void __launch_bounds__(128)
+stack_rmul_kernel(cplx *__restrict__ Out, int64_t os, const cplx *__restrict__ Z, int64_t zs, double beta,
+                  const cplx *__restrict__ X, int64_t xs, int ma, const cplx *__restrict__ M, int mb, double alpha, int nv,
+                  int64_t nrows)
+{
+    extern __shared__ cplx sM[];   // [ma][BT]
+    const int z = blockIdx.z, b0 = blockIdx.y * BT;
+    for (int t = threadIdx.x; t < ma * BT; t += blockDim.x) {
+        const int a = t / BT, j = t - a * BT;
+        sM[t] = (b0 + j < mb) ? M[((int64_t)z * ma + a) * mb + b0 + j] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const int64_t u = row * nv + z;
+    cplx acc[BT];
+#pragma unroll
+    for (int j = 0; j < BT; j++) acc[j] = make_double2(0.0, 0.0);
+    for (int a = 0; a < ma; a++) {
+        const cplx x = ldg(X + (int64_t)a * xs + u);
+#pragma unroll
+        for (int j = 0; j < BT; j++) cfma(acc[j], x, sM[a * BT + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < BT; j++) {
+        if (b0 + j < mb) {
+            cplx o = make_double2(alpha * acc[j].x, alpha * acc[j].y);
+            if (Z) {
+                const cplx zv = Z[(int64_t)(b0 + j) * zs + u];
+                o.x = fma(beta, zv.x, o.x);
+                o.y = fma(beta, zv.y, o.y);
+            }
+            Out[(int64_t)(b0 + j) * os + u] = o;
+        }
+    }
+}
+
+cudaError_t launch_stack_rmul(cplx *Out, int64_t os, const cplx *Z, int64_t zs, double beta, const cplx *X, int64_t xs,
+                              int ma, const cplx *M, int mb, double alpha, int nv, int64_t nrows, cudaStream_t s)
+{
+    constexpr int BT = 16;
+    const size_t smem = (size_t)ma * BT * sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(stack_rmul_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((nrows + 127) / 128), (unsigned)((mb + BT - 1) / BT), (unsigned)nv);
+    stack_rmul_kernel<BT><<<grid, 128, smem, s>>>(Out, os, Z, zs, beta, X, xs, ma, M, mb, alpha, nv, nrows);
+    return cudaGetLastError();
+}
+
+// Cholesky G_z + shift_z*I = R^H R (upper R, positive diagonal) and Minv_z = R^{-1}; one CTA per z, matrices in global
+// memory (m up to a few hundred).  G is overwritten by R.  status[z] = failing column + 1, or 0.
+__global__ void __launch_bounds__(128)
+chol_inverse_big_kernel(cplx *__restrict__ G, int m, double shift_scale, cplx *__restrict__ Minv, int *__restrict__ status)
+{
+    const int z = blockIdx.x;
+    cplx *g = G + (int64_t)z * m * m;
+    cplx *mi = Minv + (int64_t)z * m * m;
+    __shared__ double s_piv;
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) {
+        s_bad = 0;
+        double tr = 0.0;
+        for (int i = 0; i < m; i++) tr += g[i * m + i].x;
+        s_piv = shift_scale * tr;
+    }
+    __syncthreads();
+    const double shift = s_piv;
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) g[i * m + i].x += shift;
+    __syncthreads();
+    for (int j = 0; j < m; j++) {
+        if (threadIdx.x == 0) {
+            double d = g[j * m + j].x;
+            if (!(d > 0.0)) { if (!s_bad) s_bad = j + 1; d = 1.0; }
+            s_piv = sqrt(d);
+        }
+        __syncthreads();
+        const double rjj = s_piv;
+        for (int c = j + threadIdx.x; c < m; c += blockDim.x) {   // row j of R
+            const cplx v = g[j * m + c];
+            g[j * m + c] = (c == j) ? make_double2(rjj, 0.0) : make_double2(v.x / rjj, v.y / rjj);
+        }
+        __syncthreads();
+        // trailing update: G[i][c] -= conj(R[j][i]) * R[j][c], i > j, c >= i
+        const int nt = m - j - 1;
+        for (int t = threadIdx.x; t < nt * nt; t += blockDim.x) {
+            const int i = j + 1 + t / nt, c = j + 1 + t % nt;
+            if (c >= i) {
+                const cplx a = g[j * m + i], b = g[j * m + c];
+                g[i * m + c].x -= a.x * b.x + a.y * b.y;
+                g[i * m + c].y -= a.x * b.y - a.y * b.x;
+            }
+        }
+        __syncthreads();
+    }
+    // Minv = R^{-1}: column c by back substitution, one thread per column
+    for (int c = threadIdx.x; c < m; c += blockDim.x) {
+        for (int r = m - 1; r >= 0; r--) {
+            if (r > c) { mi[r * m + c] = make_double2(0.0, 0.0); continue; }
+            cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
+            for (int p = r + 1; p <= c; p++) {
+                const cplx a = g[r * m + p], b = mi[p * m + c];
+                sacc.x -= a.x * b.x - a.y * b.y;
+                sacc.y -= a.x * b.y + a.y * b.x;
+            }
+            const double rr = g[r * m + r].x;
+            mi[r * m + c] = make_double2(sacc.x / rr, sacc.y / rr);
+        }
+    }
+    if (threadIdx.x == 0) status[z] = s_bad;
+}
+
+cudaError_t launch_chol_inverse_big(cplx *G, int m, int nz, double shift_scale, cplx *Minv, int *status, cudaStream_t s)
+{
+    chol_inverse_big_kernel<<<nz, 128, 0, s>>>(G, m, shift_scale, Minv, status);
+    return cudaGetLastError();
+}
+
+// Galerkin systems (GalerkinProj.c:48-62): for every (z, iw) solve (alpha_iw I - Mt_z) c = alpha_iw B1_z[:,iw] - B2_z[:,iw]
+// by LU with partial pivoting; C_z[a][iw] = c[a].  One CTA per system, the matrix in a global scratch slab.
+__global__ void __launch_bounds__(128)
+galerkin_solve_kernel(const cplx *__restrict__ Mt, const cplx *__restrict__ B1, const cplx *__restrict__ B2,
+                      const cplx *__restrict__ alpha, int m, int nw, cplx *__restrict__ scratch, cplx *__restrict__ C,
+                      int *__restrict__ status)
+{
+    const int iw = blockIdx.x, z = blockIdx.y;
+    cplx *T = scratch + ((int64_t)z * nw + iw) * ((int64_t)m * (m + 1));
+    cplx *rhs = T + (int64_t)m * m;
+    const cplx al = alpha[iw];
+    const cplx *mt = Mt + (int64_t)z * m * m;
+    for (int t = threadIdx.x; t < m * m; t += blockDim.x) {
+        const int r = t / m, c = t - r * m;
+        cplx v = make_double2(-mt[t].x, -mt[t].y);
+        if (r == c) { v.x += al.x; v.y += al.y; }
+        T[t] = v;
+    }
+    for (int r = threadIdx.x; r < m; r += blockDim.x) {
+        const cplx b1 = B1[((int64_t)z * m + r) * nw + iw], b2 = B2[((int64_t)z * m + r) * nw + iw];
+        rhs[r] = make_double2(al.x * b1.x - al.y * b1.y - b2.x, al.x * b1.y + al.y * b1.x - b2.y);
+    }
+    __shared__ int s_p;
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    for (int c = 0; c < m; c++) {
+        if (threadIdx.x == 0) {
+            int p = c;
+            double best = T[c * m + c].x * T[c * m + c].x + T[c * m + c].y * T[c * m + c].y;
+            for (int r = c + 1; r < m; r++) {
+                const double v = T[r * m + c].x * T[r * m + c].x + T[r * m + c].y * T[r * m + c].y;
+                if (v > best) { best = v; p = r; }
+            }
+            if (best == 0.0) s_bad = c + 1;
+            s_p = p;
+        }
+        __syncthreads();
+        const int p = s_p;
+        if (p != c) {
+            for (int cc = threadIdx.x; cc <= m; cc += blockDim.x) {
+                cplx *x = (cc < m) ? &T[c * m + cc] : &rhs[c];
+                cplx *y = (cc < m) ? &T[p * m + cc] : &rhs[p];
+                const cplx tmp = *x;
+                *x = *y;
+                *y = tmp;
+            }
+        }
+        __syncthreads();
+        const cplx piv = T[c * m + c];
+        const double pn = piv.x * piv.x + piv.y * piv.y;
+        const cplx pinv = pn > 0.0 ? make_double2(piv.x / pn, -piv.y / pn) : make_double2(0.0, 0.0);
+        for (int r = c + 1 + threadIdx.x; r < m; r += blockDim.x) {
+            const cplx l = cmul(T[r * m + c], pinv);
+            for (int cc = c + 1; cc < m; cc++) {
+                const cplx u = T[c * m + cc];
+                T[r * m + cc].x -= l.x * u.x - l.y * u.y;
+                T[r * m + cc].y -= l.x * u.y + l.y * u.x;
+            }
+            const cplx bc = rhs[c];
+            rhs[r].x -= l.x * bc.x - l.y * bc.y;
+            rhs[r].y -= l.x * bc.y + l.y * bc.x;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int r = m - 1; r >= 0; r--) {
+            cplx sacc = rhs[r];
+            for (int cc = r + 1; cc < m; cc++) {
+                const cplx u = T[r * m + cc], x = rhs[cc];
+                sacc.x -= u.x * x.x - u.y * x.y;
+                sacc.y -= u.x * x.y + u.y * x.x;
+            }
+            const cplx piv = T[r * m + r];
+            const double pn = piv.x * piv.x + piv.y * piv.y;
+            rhs[r] = pn > 0.0 ? make_double2((sacc.x * piv.x + sacc.y * piv.y) / pn, (sacc.y * piv.x - sacc.x * piv.y) / pn)
+                              : make_double2(0.0, 0.0);
+        }
+        for (int r = 0; r < m; r++) C[((int64_t)z * m + r) * nw + iw] = rhs[r];
+        if (s_bad) status[z * nw + iw] = s_bad;
+    }
+}
+
+cudaError_t launch_galerkin_solve(const cplx *Mt, const cplx *B1, const cplx *B2, const cplx *alpha, int m, int nw, int nz,
+                                  cplx *scratch, cplx *C, int *status, cudaStream_t s)
+{
+    dim3 grid((unsigned)nw, (unsigned)nz);
+    galerkin_solve_kernel<<<grid, 128, 0, s>>>(Mt, B1, B2, alpha, m, nw, scratch, C, status);
+    return cudaGetLastError();
+}

@@ -145,3 +145,18 @@ cudaError_t launch_halo_push(const cplx *src, int nvec, const void *msgs_dev, in
 cudaError_t launch_halo_signal(void *peer_flags_dev, int npeers, unsigned long long epoch, cudaStream_t s);
 cudaError_t launch_halo_wait_unpack(cplx *dst, int nvec, const void *ins_dev, int nin, int max_count, int parity,
                                     int nvec_max, unsigned long long epoch, cudaStream_t s);
+
+// ---- transient removal (TransientRemovalStrategy.c): batched tall-skinny algebra on snapshot stacks ---------------------
+// stack element (slot a, row, vector z) at base[a*slot_stride + row*nv + z]
+int stack_gram2_chunks(int64_t nrows);
+// G[z][a][b] = sum_{row0 <= row < row0+nrows} conj(X[a][row][z]) * Y[b][row][z]; partial: chunks*nv*ma*mb elements
+cudaError_t launch_stack_gram2(const cplx *X, int64_t xs, int ma, const cplx *Y, int64_t ys, int mb, int nv, int64_t row0,
+                               int64_t nrows, cplx *partial, cplx *G, cudaStream_t s);
+// Out[b][row][z] = beta*Z[b][row][z] + alpha * sum_a X[a][row][z] * M[z][a][b]   (Z may be null)
+cudaError_t launch_stack_rmul(cplx *Out, int64_t os, const cplx *Z, int64_t zs, double beta, const cplx *X, int64_t xs,
+                              int ma, const cplx *M, int mb, double alpha, int nv, int64_t nrows, cudaStream_t s);
+// G_z + shift_scale*trace(G_z)*I = R^H R; Minv_z = R^{-1}; G overwritten; status[z] != 0 on breakdown
+cudaError_t launch_chol_inverse_big(cplx *G, int m, int nz, double shift_scale, cplx *Minv, int *status, cudaStream_t s);
+// C_z[:, iw] = (alpha_iw I - Mt_z)^{-1} (alpha_iw B1_z[:, iw] - B2_z[:, iw]); scratch: nz*nw*m*(m+1) elements
+cudaError_t launch_galerkin_solve(const cplx *Mt, const cplx *B1, const cplx *B2, const cplx *alpha, int m, int nw, int nz,
+                                  cplx *scratch, cplx *C, int *status, cudaStream_t s);

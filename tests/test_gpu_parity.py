@@ -289,3 +289,52 @@ def test_row_partition_two_gpus():
                           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("direct", [True, False])
+def test_transient_removal_action(pkg, O, A_GL, direct):
+    # TransientRemovalStrategy.c on the device (shifted CholeskyQR3 basis, batched Galerkin solves) against the oracle's
+    # Gram-Schmidt / LU restatement; the projection depends only on span(V), so the two agree to ~cond(Y_all) * eps
+    k, Nw, w = 3, 8, 0.6
+    A = A_GL.shifted(0.3)
+    v = make_vars(O, pkg, 500, k, Nw, w, 0.003, 1.0, TR=True)
+    F = _forcing(500, k * Nw, 12)
+    ref, snaps_ref = _oracle_action(O, A, v, F, direct, snaps=True)
+    r = _handle(pkg, A, v)
+    r.keep_snapshots(True)
+    got = r.TSActionRK4(F, direct=direct)
+    assert rel_err(r.get_snapshots(), snaps_ref) < ACTION_TOL
+    err = rel_err(got, ref)
+    print(f"transient-removal action ({'direct' if direct else 'adjoint'}): rel err vs oracle = {err:.2e}")
+    assert err < 1e-8
+    r.close()
+
+
+def test_tutorial_config_full_solve_with_transient_removal(pkg, O, A_GL):
+    # BASELINE.json configs[0]: the tutorial as shipped (variables.yaml: w = 0.05, Nw = 42, dt = 0.003, TransientLength = 10,
+    # TransientRemoval = true, q = 1), with k = 3 instead of 10 to keep the oracle run short; F_hat fed to both sides
+    k, Nw, w = 3, 42, 0.05
+    v = make_vars(O, pkg, 500, k, Nw, w, 0.003, 10.0, TR=True)
+    assert (v.Ns, v.Nt, v.ResRatio) == (41916, 3336, 998)
+    F = pkg.synthetic.random_forcing(500, k, Nw, seed=14)
+    S_ref, U_ref, V_ref = O.full_solve(A_GL, v, 1, F)
+    r = _handle(pkg, A_GL, v)
+    r.set_Y_hat(F)
+    r.DirectActionRK4()
+    r.PowerIterationRK4(1)
+    r.SVDAllFreqsBeforeAdjoint()
+    r.StoreU()
+    r.AdjointActionRK4()
+    r.SVDAllFreqs()
+    S, U, V = r.get_S_hat(), r.get_U_hat(), r.get_V_hat()
+    gerr = np.abs(S / S_ref - 1)
+    print("tutorial full solve: max gain rel err (leading mode) =", gerr[0].max(), " all modes =", gerr.max())
+    # leading gains to the north-star tolerance; the peak of the tutorial (sigma_1 ~ 1.67e3 at w = -0.65) included
+    assert gerr[0].max() <= 1e-8
+    iw_peak = Nw - 13                       # -0.65 = -13 w  ->  slot Nw - 13 (FFT ordering)
+    assert S[0, iw_peak] == pytest.approx(1672.0219, rel=2e-3)   # exact resolvent gain
+    ang = max(principal_angle(U[:, i * k:i * k + 1], U_ref[:, i * k:i * k + 1]) for i in range(Nw))
+    angv = max(principal_angle(V[:, i * k:i * k + 1], V_ref[:, i * k:i * k + 1]) for i in range(Nw))
+    print("tutorial full solve: max principal angle of the leading modes U, V =", ang, angv)
+    assert ang <= 1e-6 and angv <= 1e-6
+    r.close()
