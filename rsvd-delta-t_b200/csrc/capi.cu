@@ -114,7 +114,7 @@ struct rsvdt_context {
     int64_t snaps_nstore = 0;
 
     // options
-    int64_t chunk_steps = 32;
+    int64_t chunk_steps = 0;   // RK4 steps per forcing-synthesis chunk; 0 = automatic (up to 64, bounded by free memory)
     int64_t stage_variant = 0;
     int64_t idft_variant = 0;
     int64_t use_banded = 3;   // 0: stage kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged DIA step
@@ -644,13 +644,24 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
     CsrOwned &Op = direct ? h->A : h->AH;
     const int nv = (int)g.k;
     const int64_t U = h->n_ext * g.k;
-    const int64_t Tc = std::max<int64_t>(1, h->chunk_steps);
+    int64_t Tc = h->chunk_steps;
+    if (Tc <= 0) {
+        // automatic: the two slice buffers (2 x 2*Tc block vectors) may take a quarter of the free memory, Tc <= 64
+        if (h->slices[0].p && h->slices[1].p && h->slices[0].bytes == h->slices[1].bytes && h->slices[0].bytes >= (size_t)16 * U * sizeof(cplx)) {
+            Tc = (int64_t)(h->slices[0].bytes / ((size_t)2 * U * sizeof(cplx)));
+        } else {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            Tc = (int64_t)((double)free_b * 0.25 / ((double)4 * U * sizeof(cplx)));
+        }
+        Tc = std::max<int64_t>(8, std::min<int64_t>(64, Tc));
+    }
     const int S = (int)(2 * Tc);
     int path = 0;
     RS(step_path(h, Op, nv, &path));
     const bool banded = path != 0;
     for (int b = 0; b < 2; b++) RS(ensure(h, h->slices[b], (size_t)S * U * sizeof(cplx)));
-    RS(ensure(h, h->coef, (size_t)std::max<int64_t>((int64_t)S * g.Nw_eff, g.Nw_eff * g.Nw) * sizeof(cplx)));
+    RS(ensure(h, h->coef, (size_t)std::max<int64_t>((int64_t)128 * g.Nw_eff, g.Nw_eff * g.Nw) * sizeof(cplx)));
     RS(ensure(h, h->xa, (size_t)U * sizeof(cplx)));
     if (!banded) {
         RS(ensure(h, h->xb, (size_t)U * sizeof(cplx)));
@@ -721,7 +732,7 @@ int dft_snapshots(rsvdt_handle h, const cplx *snaps, cplx *Yhat_out)
 {
     const rsvdt_grid &g = h->g;
     const int64_t U = h->n_ext * g.k;
-    RS(ensure(h, h->coef, (size_t)std::max<int64_t>(g.Nw_eff * g.Nw, 2 * h->chunk_steps * g.Nw_eff) * sizeof(cplx)));
+    RS(ensure(h, h->coef, (size_t)std::max<int64_t>(g.Nw_eff * g.Nw, 128 * g.Nw_eff) * sizeof(cplx)));
     Bracket br(h, &h->ev_dft);
     CU(launch_dft_coef(h->coef.as<cplx>(), (int)g.Nw_eff, (int)g.Nw, g.ResRatio, h->stream));
     CU(launch_small_cgemm(Yhat_out, U, h->coef.as<cplx>(), snaps, U, (int)g.Nw_eff, (int)g.Nw, U, 0, h->stream));
@@ -781,7 +792,7 @@ int transient_removal(rsvdt_handle h, bool direct, const cplx *snaps, cplx *Yhat
     // ---- y1, y2 (GalerkinProj.c:30-46) -----------------------------------------------------------------------------------
     TRY(Y1.alloc((size_t)nw * U * sizeof(cplx)));
     TRY(Y2.alloc((size_t)nw * U * sizeof(cplx)));
-    rc = ensure(h, h->coef, (size_t)std::max<int64_t>(g.Nw_eff * g.Nw, 2 * h->chunk_steps * g.Nw_eff) * sizeof(cplx));
+    rc = ensure(h, h->coef, (size_t)std::max<int64_t>(g.Nw_eff * g.Nw, 128 * g.Nw_eff) * sizeof(cplx));
     if (rc != RSVDT_OK) { cleanup(); return rc; }
     TRY(launch_dft_coef(h->coef.as<cplx>(), nw, (int)g.Nw, g.ResRatio, h->stream));
     const cplx *s1 = snaps + (direct ? 0 : U), *s2 = snaps + (direct ? U : 0);
@@ -1510,7 +1521,7 @@ int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *m
     RS(ensure(h, h->y, (size_t)U * sizeof(cplx)));
     CU(launch_fill_zero(h->y.as<cplx>(), U, h->stream));
     // allocate work buffers outside the timed region
-    RS(forced_steps(h, direct != 0, h->Yhat.as<cplx>(), h->y.as<cplx>(), nullptr, h->g.Nw, 1, std::min<int64_t>(nsteps, h->chunk_steps)));
+    RS(forced_steps(h, direct != 0, h->Yhat.as<cplx>(), h->y.as<cplx>(), nullptr, h->g.Nw, 1, std::min<int64_t>(nsteps, 64)));
     CU(cudaStreamSynchronize(h->stream));
     CU(launch_fill_zero(h->y.as<cplx>(), U, h->stream));
     int64_t n;
@@ -1549,7 +1560,7 @@ int64_t rsvdt_kernel_launches(rsvdt_handle h, int reset)
 int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
 {
     if (!h || !name) return RSVDT_ERR_ARG;
-    if (!strcmp(name, "chunk_steps")) { if (value < 1 || value > 64) return fail(h, RSVDT_ERR_ARG, "chunk_steps out of range"); h->chunk_steps = value; }
+    if (!strcmp(name, "chunk_steps")) { if (value < 0 || value > 64) return fail(h, RSVDT_ERR_ARG, "chunk_steps out of range"); h->chunk_steps = value; }
     else if (!strcmp(name, "stage_variant")) h->stage_variant = value;
     else if (!strcmp(name, "idft_variant")) h->idft_variant = value;
     else if (!strcmp(name, "use_banded")) h->use_banded = value;

@@ -592,7 +592,7 @@ DEVFN void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n"
 //   R*nv congruent to nv modulo the 8 16-byte slots of a shared-memory wavefront: conflict-free sliding-window accesses.
 // =====================================================================================================
 template <int LO, int HI, int R, int MINB, bool FORCED>
-__global__ void __launch_bounds__(MINB >= 3 ? 192 : 320, MINB)
+__global__ void __launch_bounds__(MINB >= 3 ? 160 : 320) __maxnreg__(MINB >= 3 ? 112 : 96)
 rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict__ tile_ok, int64_t N, int nv, int nq,
                    int TR, BandedStepArgs a)
 {
@@ -649,12 +649,18 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
     const int iv = active ? threadIdx.x - q * nv : 0;
     const int r_first = q * R;
     const int own = r_first * nv + iv;   // slot of the thread's first row; consecutive rows are nv slots apart
-    cplx yo[R], acc[R];
+    // The thread's own R rows of the current stage vector stay in registers from one stage to the next (xs); only the rows
+    // a neighbouring row block needs (the first HI and the last LO of the block) go through shared memory, and only the
+    // LO + HI rows of the neighbouring blocks are read back: 3 + 3 instead of 8 + 5 shared accesses per stage for the
+    // Ginzburg-Landau band.
+    cplx yo[R], acc[R], xs[R];
 #pragma unroll
     for (int rr = 0; rr < R; rr++) {
         yo[rr] = BA[own + rr * nv];
         acc[rr] = yo[rr];
+        xs[rr] = yo[rr];
     }
+    constexpr bool ALLROWS = (R < LO + HI);   // tiny blocks: every row is needed by a neighbour
 #pragma unroll
     for (int st = 1; st <= 3; st++) {
         const cplx *Xin = (st == 2) ? BB : BA;
@@ -667,8 +673,12 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
             cplx xw[WN];
 #pragma unroll
             for (int j = 0; j < WN; j++) {
-                const int lr = r_first - LO + j;
-                xw[j] = (lr >= 0 && lr < E0) ? Xin[own + (j - LO) * nv] : make_double2(0.0, 0.0);
+                if (j >= LO && j < LO + R) {
+                    xw[j] = xs[j - LO];
+                } else {
+                    const int lr = r_first - LO + j;
+                    xw[j] = (lr >= 0 && lr < E0) ? Xin[own + (j - LO) * nv] : make_double2(0.0, 0.0);
+                }
             }
 #pragma unroll
             for (int rr = 0; rr < R; rr++) {
@@ -681,10 +691,13 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
                 acc[rr] = make_double2(fma(ca, s.x, acc[rr].x), fma(ca, s.y, acc[rr].y));
             }
         }
-        if (st == 1) __syncthreads();   // every thread has read its y window before BA... (BA is written in stage 2 only)
+        if (st == 1) __syncthreads();   // every thread has read its y halo before BA is overwritten (stage 2 writes BA)
         if (active) {
 #pragma unroll
-            for (int rr = 0; rr < R; rr++) Xout[own + rr * nv] = xo[rr];
+            for (int rr = 0; rr < R; rr++) {
+                if (ALLROWS || rr < HI || rr >= R - LO) Xout[own + rr * nv] = xo[rr];
+                xs[rr] = xo[rr];
+            }
         }
         __syncthreads();
     }
@@ -693,8 +706,12 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
         cplx xw[WN];
 #pragma unroll
         for (int j = 0; j < WN; j++) {
-            const int lr = r_first - LO + j;
-            xw[j] = (lr >= 0 && lr < E0) ? BB[own + (j - LO) * nv] : make_double2(0.0, 0.0);
+            if (j >= LO && j < LO + R) {
+                xw[j] = xs[j - LO];
+            } else {
+                const int lr = r_first - LO + j;
+                xw[j] = (lr >= 0 && lr < E0) ? BB[own + (j - LO) * nv] : make_double2(0.0, 0.0);
+            }
         }
 #pragma unroll
         for (int rr = 0; rr < R; rr++) {
@@ -734,11 +751,11 @@ inline int tma_R(int nv)
 }
 inline int tma_nq(int nv, int R, int nd, bool forced, int minb)
 {
-    // shared memory per CTA = ((nbuf*nv + nd) * E0) * 16 + 16, E0 = R*nq; threads = nq*nv <= 192 (3 CTAs/SM) or 320 (2)
+    // shared memory per CTA = ((nbuf*nv + nd) * E0) * 16 + 16, E0 = R*nq; threads = nq*nv <= 160 (3 CTAs/SM) or 320 (2)
     const int budget = (minb >= 3 ? 74 : 112) * 1024;
     const int per_row = ((forced ? 5 : 2) * nv + nd) * 16;
     int nq = (budget - 64) / (per_row * R);
-    const int tmax = (minb >= 3 ? 192 : 320) / nv;
+    const int tmax = (minb >= 3 ? 160 : 320) / nv;
     return nq < tmax ? nq : tmax;
 }
 
@@ -756,11 +773,13 @@ cudaError_t dia_tma_launch(const cplx *dia, const unsigned char *tile_ok, int nt
         auto kfn = rk4_dia_tma_kernel<LO, HI, R, MINB, true>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         kfn<<<(unsigned)ntiles, threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
     } else {
         auto kfn = rk4_dia_tma_kernel<LO, HI, R, MINB, false>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         kfn<<<(unsigned)ntiles, threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
     }
     return cudaGetLastError();

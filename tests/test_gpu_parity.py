@@ -338,3 +338,58 @@ def test_tutorial_config_full_solve_with_transient_removal(pkg, O, A_GL):
     print("tutorial full solve: max principal angle of the leading modes U, V =", ang, angv)
     assert ang <= 1e-6 and angv <= 1e-6
     r.close()
+
+
+def _rand_sparse(rng, nrows, ncols, per_row, diag=False):
+    rp = [0]
+    ci, va = [], []
+    for r in range(nrows):
+        cols = np.sort(rng.choice(ncols, size=min(per_row, ncols), replace=False))
+        if diag and r < ncols and r not in cols:
+            cols = np.sort(np.append(cols[:-1], r))
+        ci.append(cols)
+        va.append(rng.standard_normal(cols.size) + 1j * rng.standard_normal(cols.size))
+        rp.append(rp[-1] + cols.size)
+    return np.array(rp, np.int64), np.concatenate(ci).astype(np.int64), np.concatenate(va)
+
+
+def test_weighted_actions(pkg, O, A_GL):
+    # DirectActionRK4.c:24-28 / AdjointActionRK4.c:24-28 with ApplyWeightMats.c:16-80: W_q^{1/2} C R B W_f^{-1/2} and its
+    # Hermitian transpose, B: N x Nb, C: Nc x N (Nb, Nc < N), plus the final W^{-1/2} scalings of SVDAllFreqs.c:63-64
+    rng = np.random.default_rng(17)
+    N, Nb, Nc, k, Nw = 500, 120, 90, 3, 4
+    v = make_vars(O, pkg, N, k, Nw, 1.0, 0.003, 1.0)
+    mats = {"B": _rand_sparse(rng, N, Nb, 3), "C": _rand_sparse(rng, Nc, N, 4),
+            "W_f_sqrt_inv": _rand_sparse(rng, Nb, Nb, 2, diag=True), "W_q_sqrt": _rand_sparse(rng, Nc, Nc, 2, diag=True),
+            "W_q_sqrt_inv": _rand_sparse(rng, Nc, Nc, 2, diag=True)}
+    shapes = {"B": (N, Nb), "C": (Nc, N), "W_f_sqrt_inv": (Nb, Nb), "W_q_sqrt": (Nc, Nc), "W_q_sqrt_inv": (Nc, Nc)}
+    Oc = {n: O.Csr(shapes[n][0], shapes[n][1], *mats[n]) for n in mats}
+    r = _handle(pkg, A_GL, v)
+    for n in mats:
+        r.ReadWeightMats(n, shapes[n][0], shapes[n][1], *mats[n])
+    dft, idft = O.create_dft_idft_mats(Nw, Nw, v.Ns, False, False)
+    # direct: Y <- W_q_sqrt C R (B W_f_sqrt_inv Y)
+    F = _forcing(Nb, k * Nw, 18)
+    X = O.mat_mat_mult(Oc["B"], O.mat_mat_mult(Oc["W_f_sqrt_inv"], F))
+    Y = O.ts_action_rk4(A_GL, v, dft, idft, X)
+    ref = O.mat_mat_mult(Oc["W_q_sqrt"], O.mat_mat_mult(Oc["C"], Y))
+    r.set_Y_hat(F)
+    r.DirectActionRK4()
+    got = r.get_Y_hat()
+    assert got.shape == (Nc, k * Nw) and rel_err(got, ref) < ACTION_TOL
+    # adjoint: Y <- W_f_sqrt_inv^H B^H R^H (C^H W_q_sqrt^H Y)
+    G = _forcing(Nc, k * Nw, 19)
+    X = O.mat_mat_mult(Oc["C"], O.mat_mat_mult(Oc["W_q_sqrt"], G, True), True)
+    va = O.Vars(**{**v.__dict__, "DirAdj": False})
+    Y = O.ts_action_rk4(A_GL.hermitian_transpose(), va, dft, idft, X)
+    ref = O.mat_mat_mult(Oc["W_f_sqrt_inv"], O.mat_mat_mult(Oc["B"], Y, True), True)
+    r.set_Y_hat(G)
+    r.AdjointActionRK4()
+    got = r.get_Y_hat()
+    assert got.shape == (Nb, k * Nw) and rel_err(got, ref) < ACTION_TOL
+    # dimension checks of ReadWeightMats.c:34-98
+    with pytest.raises(pkg.capi.RsvdtError):
+        r.ReadWeightMats("B", N - 1, Nb, *_rand_sparse(rng, N - 1, Nb, 2))
+    with pytest.raises(pkg.capi.RsvdtError):
+        r.ReadWeightMats("W_q_sqrt", Nc, Nc + 1, *_rand_sparse(rng, Nc, Nc + 1, 2))
+    r.close()
