@@ -288,7 +288,6 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
                 if (ci[p0 + i] % B) { okb = false; break; }
                 for (int j = 1; j < B; j++)
                     if (ci[p0 + i + j] != ci[p0 + i] + j) { okb = false; break; }
-                if (i && ci[p0 + i] <= ci[p0 + i - B]) okb = false;   // ascending blocks
             }
             nblocks += len / B;
         }
