@@ -563,7 +563,7 @@ int step_path(rsvdt_handle h, CsrOwned &Op, int nv, int *path)
 // one whole RK4 step, dispatching between the fused kernels (y ping-pongs between *ycur and *ynext) and the
 // stage-by-stage kernels (in place on *ycur)
 int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **ycur, cplx **ynext, const cplx *f_prev,
-                 const cplx *f_half, const cplx *f_next, cplx *snap)
+                 const cplx *f_half, const cplx *f_next, cplx *snap, int nbatch = 1, int64_t batch_stride = 0)
 {
     if (path == 0)
         return rk4_step(h, Op, nv, *ycur, h->xa.as<cplx>(), h->xb.as<cplx>(), h->acc.as<cplx>(), f_prev, f_half, f_next, snap);
@@ -572,6 +572,8 @@ int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **yc
     a.y_in = *ycur; a.y_out = *ynext; a.f_prev = f_prev; a.f_half = f_half; a.f_next = f_next; a.snap = snap; a.dt = h->g.dt;
     a.own_begin = h->own0;
     a.own_end = h->own0 + h->N;
+    a.nbatch = nbatch;
+    a.batch_stride = batch_stride;
     if (path >= 2) {
         if (path == 3)
             CU(launch_rk4_dia_tma_step(Op.dia.as<cplx>(), Op.dia_lo, Op.dia_hi, Op.tile_ok.as<unsigned char>(), Op.ntiles, Op.d.nrows, nv, (int)h->tma_variant, a, h->stream));
@@ -721,8 +723,37 @@ int unforced_steps(rsvdt_handle h, bool direct, int nv, cplx *y, int64_t nsteps)
         RS(ensure(h, h->acc, (size_t)U * sizeof(cplx)));
     }
     cplx *ycur = y, *ynext = h->xa.as<cplx>();
+    if (h->dist.on) RS(dist_exchange(h, ycur, nv));   // the ghost rows of the initial vector
     for (int64_t i = 0; i < nsteps; i++) RS(rk4_step_any(h, Op, nv, path, &ycur, &ynext, nullptr, nullptr, nullptr, nullptr));
     if (ycur != y) CU(cudaMemcpyAsync(y, ycur, (size_t)U * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
+    return RSVDT_OK;
+}
+
+// unforced steps on `nslots` independent block vectors (stride U) with ONE launch per step when the fused band kernel
+// applies and the second buffer is affordable; otherwise slot by slot (TSExpADeltaT.c:25-34 applied to every snapshot slot)
+int unforced_steps_slots(rsvdt_handle h, bool direct, int nv, cplx *base, int nslots, int64_t nsteps)
+{
+    CsrOwned &Op = direct ? h->A : h->AH;
+    const int64_t U = h->n_ext * nv;
+    int path = 0;
+    RS(step_path(h, Op, nv, &path));
+    const size_t bytes = (size_t)nslots * U * sizeof(cplx);
+    if (path == 3 && !h->dist.on && bytes <= ((size_t)1 << 30)) {
+        DevBuf tmp;
+        CU(tmp.alloc(bytes));
+        cplx *ycur = base, *ynext = tmp.as<cplx>();
+        int rc = RSVDT_OK;
+        for (int64_t i = 0; i < nsteps && rc == RSVDT_OK; i++)
+            rc = rk4_step_any(h, Op, nv, path, &ycur, &ynext, nullptr, nullptr, nullptr, nullptr, nslots, U);
+        cudaError_t e = cudaSuccess;
+        if (rc == RSVDT_OK && ycur != base) e = cudaMemcpyAsync(base, ycur, bytes, cudaMemcpyDeviceToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        tmp.release();
+        if (rc != RSVDT_OK) return rc;
+        CU(e);
+        return RSVDT_OK;
+    }
+    for (int a = 0; a < nslots; a++) RS(unforced_steps(h, direct, nv, base + (int64_t)a * U, nsteps));
     return RSVDT_OK;
 }
 
@@ -739,6 +770,8 @@ int dft_snapshots(rsvdt_handle h, const cplx *snaps, cplx *Yhat_out)
     return RSVDT_OK;
 }
 
+int dist_allreduce(rsvdt_handle h, void *dev_ptr, int64_t n_doubles);
+
 // TransientRemovalStrategy.c:30-40 on the device.  snaps: Y_all as a stack [Nw+1][row][ik]; Yhat_out: stack [Nw_eff][row][ik].
 //   CreateMtilde.c:41-54      V = QR(Y_all_k) -> shifted CholeskyQR3 per test vector (the snapshot matrices reach cond ~1e7,
 //                             beyond plain CholeskyQR2; any orthonormal basis of the same span gives the same projection),
@@ -748,14 +781,16 @@ int dft_snapshots(rsvdt_handle h, const cplx *snaps, cplx *Yhat_out)
 int transient_removal(rsvdt_handle h, bool direct, const cplx *snaps, cplx *Yhat_out)
 {
     const rsvdt_grid &g = h->g;
-    if (h->dist.on) return fail(h, RSVDT_ERR_USER, "transient removal is not available in row-partitioned runs yet");
     const int m = (int)g.Nw + 1, nv = (int)g.k, nw = (int)g.Nw_eff;
+    // row-partitioned runs: the Gram-type products sum over the owned rows and are all-reduced; everything else is row-local
+    const int64_t grow0 = h->own0, grows = h->N;
+#define ALLRED(buf, n) do { rc = dist_allreduce(h, (buf), (n)); if (rc != RSVDT_OK) { cleanup(); return rc; } } while (0)
     const int64_t rows = h->n_ext, U = rows * nv;
     DevBuf V, W, Y1, Y2, G, Minv, B1, B2, Cc, part, scratch, alpha_d, status;
     int rc = RSVDT_OK;
     auto cleanup = [&]() { for (DevBuf *b : {&V, &W, &Y1, &Y2, &G, &Minv, &B1, &B2, &Cc, &part, &scratch, &alpha_d, &status}) b->release(); };
 #define TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(h, e__ == cudaErrorMemoryAllocation ? RSVDT_ERR_MEM : RSVDT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); cleanup(); return rc; } } while (0)
-    const int chunks = stack_gram2_chunks(rows);
+    const int chunks = stack_gram2_chunks(grows);
     const int mbmax = std::max(m, nw);
     TRY(V.alloc((size_t)m * U * sizeof(cplx)));
     TRY(W.alloc((size_t)m * U * sizeof(cplx)));
@@ -767,9 +802,10 @@ int transient_removal(rsvdt_handle h, bool direct, const cplx *snaps, cplx *Yhat
     std::vector<int> st((size_t)nv * nw);
     // ---- V = QR(Y_all_k): shifted CholeskyQR3 ---------------------------------------------------------------------
     for (int pass = 0; pass < 3; pass++) {
-        TRY(launch_stack_gram2(V.as<cplx>(), U, m, V.as<cplx>(), U, m, nv, 0, rows, part.as<cplx>(), G.as<cplx>(), h->stream));
+        TRY(launch_stack_gram2(V.as<cplx>(), U, m, V.as<cplx>(), U, m, nv, grow0, grows, part.as<cplx>(), G.as<cplx>(), h->stream));
+        ALLRED(G.p, (int64_t)2 * nv * m * m);
         // shift of Fukaya et al. (2020): 11 (m n + n (n+1)) u ||X||_2^2, with ||X||_2^2 <= trace(G)
-        const double shift = pass == 0 ? 11.0 * ((double)rows * m + (double)m * (m + 1)) * 1.1e-16 : 0.0;
+        const double shift = pass == 0 ? 11.0 * ((double)h->N_global * m + (double)m * (m + 1)) * 1.1e-16 : 0.0;
         TRY(launch_chol_inverse_big(G.as<cplx>(), m, nv, shift, Minv.as<cplx>(), status.as<int>(), h->stream));
         TRY(launch_stack_rmul(W.as<cplx>(), U, nullptr, 0, 0.0, V.as<cplx>(), U, m, Minv.as<cplx>(), m, 1.0, nv, rows, h->stream));
         h->launches += 4;
@@ -781,12 +817,11 @@ int transient_removal(rsvdt_handle h, bool direct, const cplx *snaps, cplx *Yhat
     }
     // ---- MV = exp(A dT) V (TSExpADeltaT.c:25-34), slot by slot with the fused step kernels ---------------------------
     TRY(cudaMemcpyAsync(W.p, V.p, (size_t)m * U * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
-    for (int a = 0; a < m; a++) {
-        rc = unforced_steps(h, direct, nv, W.as<cplx>() + (int64_t)a * U, g.ResRatio);
-        if (rc != RSVDT_OK) { cleanup(); return rc; }
-    }
+    rc = unforced_steps_slots(h, direct, nv, W.as<cplx>(), m, g.ResRatio);
+    if (rc != RSVDT_OK) { cleanup(); return rc; }
     // ---- Mt = V^H MV (CreateMtilde.c:49-51) -> Minv buffer reused -----------------------------------------------------
-    TRY(launch_stack_gram2(V.as<cplx>(), U, m, W.as<cplx>(), U, m, nv, 0, rows, part.as<cplx>(), Minv.as<cplx>(), h->stream));
+    TRY(launch_stack_gram2(V.as<cplx>(), U, m, W.as<cplx>(), U, m, nv, grow0, grows, part.as<cplx>(), Minv.as<cplx>(), h->stream));
+    ALLRED(Minv.p, (int64_t)2 * nv * m * m);
     W.release();
     // ---- y1, y2 (GalerkinProj.c:30-46) -----------------------------------------------------------------------------------
     TRY(Y1.alloc((size_t)nw * U * sizeof(cplx)));
@@ -800,8 +835,10 @@ int transient_removal(rsvdt_handle h, bool direct, const cplx *snaps, cplx *Yhat
     // ---- b = V^H (alpha y1 - y2) through B1 = V^H Y1, B2 = V^H Y2 (:55) -------------------------------------------------
     TRY(B1.alloc((size_t)nv * m * nw * sizeof(cplx)));
     TRY(B2.alloc((size_t)nv * m * nw * sizeof(cplx)));
-    TRY(launch_stack_gram2(V.as<cplx>(), U, m, Y1.as<cplx>(), U, nw, nv, 0, rows, part.as<cplx>(), B1.as<cplx>(), h->stream));
-    TRY(launch_stack_gram2(V.as<cplx>(), U, m, Y2.as<cplx>(), U, nw, nv, 0, rows, part.as<cplx>(), B2.as<cplx>(), h->stream));
+    TRY(launch_stack_gram2(V.as<cplx>(), U, m, Y1.as<cplx>(), U, nw, nv, grow0, grows, part.as<cplx>(), B1.as<cplx>(), h->stream));
+    ALLRED(B1.p, (int64_t)2 * nv * m * nw);
+    TRY(launch_stack_gram2(V.as<cplx>(), U, m, Y2.as<cplx>(), U, nw, nv, grow0, grows, part.as<cplx>(), B2.as<cplx>(), h->stream));
+    ALLRED(B2.p, (int64_t)2 * nv * m * nw);
     Y2.release();
     // ---- (alpha I - Mt) c = b (:48-62), alpha = exp(+-i w iw dT), dT = dt*ResRatio (:17,49-54) --------------------------------
     std::vector<cplx> alpha((size_t)nw);
@@ -825,6 +862,7 @@ int transient_removal(rsvdt_handle h, bool direct, const cplx *snaps, cplx *Yhat
     for (size_t i = 0; i < st.size(); i++)
         if (st[i]) { cleanup(); return fail(h, RSVDT_ERR_NUMERIC, "transient removal: singular Galerkin system (test vector %d, frequency %d)", (int)(i / nw), (int)(i % nw)); }
 #undef TRY
+#undef ALLRED
     cleanup();
     return RSVDT_OK;
 }

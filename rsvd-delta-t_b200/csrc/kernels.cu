@@ -260,6 +260,8 @@ rk4_banded_step_kernel(const int64_t *__restrict__ rowptr, const int32_t *__rest
                        int64_t N, int nv, int b, int TR, int E0, const int64_t *__restrict__ ranges, BandedStepArgs a)
 {
     extern __shared__ cplx sm[];
+    a.y_in += (int64_t)blockIdx.y * a.batch_stride;
+    a.y_out += (int64_t)blockIdx.y * a.batch_stride;
     const int n_e = E0 * nv;
     cplx *Y = sm, *B1 = sm + n_e, *B2 = sm + 2 * n_e;
     // owned rows: [row0, row0 + nown) -- either the regular tiling or an explicit list of row ranges
@@ -384,12 +386,12 @@ cudaError_t banded_launch(const CsrDev &Op, int b, int nv, int E0, const BandedS
         auto kfn = rk4_banded_step_kernel<BT, UPT, MINB, true>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kfn<<<grid, BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, ranges, a);
+        kfn<<<dim3(grid, (unsigned)a.nbatch), BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, ranges, a);
     } else {
         auto kfn = rk4_banded_step_kernel<BT, UPT, MINB, false>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kfn<<<grid, BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, ranges, a);
+        kfn<<<dim3(grid, (unsigned)a.nbatch), BT, smem, s>>>(Op.rowptr, Op.col, Op.val, Op.nrows, nv, b, TR, E0, ranges, a);
     }
     return cudaGetLastError();
 }
@@ -598,6 +600,8 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
 {
     constexpr int ND = LO + HI + 1, WN = R + LO + HI;
     if (!tile_ok[blockIdx.x]) return;
+    a.y_in += (int64_t)blockIdx.y * a.batch_stride;
+    a.y_out += (int64_t)blockIdx.y * a.batch_stride;
     extern __shared__ __align__(128) cplx sm[];
     const int T = nq * nv, E0 = nq * R, n_e = E0 * nv;
     cplx *BA = sm;                      // y, later x3, finally y_{n+1}
@@ -774,13 +778,13 @@ cudaError_t dia_tma_launch(const cplx *dia, const unsigned char *tile_ok, int nt
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        kfn<<<(unsigned)ntiles, threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
+        kfn<<<dim3((unsigned)ntiles, (unsigned)a.nbatch), threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
     } else {
         auto kfn = rk4_dia_tma_kernel<LO, HI, R, MINB, false>;
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        kfn<<<(unsigned)ntiles, threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
+        kfn<<<dim3((unsigned)ntiles, (unsigned)a.nbatch), threads, smem, s>>>(dia, tile_ok, N, nv, nq, TR, a);
     }
     return cudaGetLastError();
 }

@@ -65,6 +65,9 @@ struct BandedStepArgs {
     // rows [own_begin, own_end) of the local arrays are advanced by this rank; rows outside are halo copies of the
     // neighbours' rows (row-partitioned runs).  own_end < 0 means "all rows".
     int64_t own_begin = 0, own_end = -1;
+    // batch of independent block vectors advanced by one launch (blockIdx.y): vector b lives at y_in/y_out + b*batch_stride
+    int nbatch = 1;
+    int64_t batch_stride = 0;
 };
 bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, int variant);
 int banded_tile_rows(int64_t lo_bw, int64_t hi_bw, int nv, int variant);
