@@ -69,6 +69,8 @@ struct EventPair { cudaEvent_t a, b; };
 struct rsvdt_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;          // runs the few irregular tiles of a fused step next to the main kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
 
     // LNS_vars (Variables.h:59-62).  N = rows owned by this rank (all rows on one GPU); the local arrays hold n_ext rows:
@@ -575,15 +577,21 @@ int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **yc
     a.nbatch = nbatch;
     a.batch_stride = batch_stride;
     if (path >= 2) {
+        if (Op.nslow > 0) {
+            // the tiles holding rows off the diagonal pattern (domain boundaries) go through the CSR kernel on a side stream,
+            // concurrently with the main kernel: both read y_n and write disjoint rows of y_{n+1}
+            CU(cudaEventRecord(h->ev_fork, h->stream));
+            CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+            CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, Op.slow_ranges.as<int64_t>(), Op.nslow, h->side));
+            CU(cudaEventRecord(h->ev_join, h->side));
+            h->launches += 1;
+        }
         if (path == 3)
             CU(launch_rk4_dia_tma_step(Op.dia.as<cplx>(), Op.dia_lo, Op.dia_hi, Op.tile_ok.as<unsigned char>(), Op.ntiles, Op.d.nrows, nv, (int)h->tma_variant, a, h->stream));
         else
             CU(launch_rk4_dia_step(Op.dia.as<cplx>(), Op.dia_lo, Op.dia_hi, Op.tile_ok.as<unsigned char>(), Op.ntiles, Op.d.nrows, nv, a, h->stream));
         h->launches += 1;
-        if (Op.nslow > 0) {
-            CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, Op.slow_ranges.as<int64_t>(), Op.nslow, h->stream));
-            h->launches += 1;
-        }
+        if (Op.nslow > 0) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     } else {
         CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, nullptr, 0, h->stream));
         h->launches += 1;
@@ -1020,7 +1028,10 @@ int rsvdt_create(int device, rsvdt_handle *hout)
     rsvdt_handle h = new (std::nothrow) rsvdt_context();
     if (!h) return RSVDT_ERR_MEM;
     h->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete h;
         return RSVDT_ERR_CUDA;
     }
@@ -1048,6 +1059,9 @@ int rsvdt_destroy(rsvdt_handle h)
     DevBuf *bufs[] = {&h->Yhat, &h->Uhat, &h->Vhat, &h->Shat, &h->y, &h->xa, &h->xb, &h->acc, &h->slices[0], &h->slices[1],
                       &h->coef, &h->snaps, &h->small, &h->smallM, &h->status, &h->gram_partial, &h->scalars};
     for (DevBuf *b : bufs) b->release();
+    cudaEventDestroy(h->ev_fork);
+    cudaEventDestroy(h->ev_join);
+    cudaStreamDestroy(h->side);
     cudaStreamDestroy(h->stream);
     delete h;
     return RSVDT_OK;
