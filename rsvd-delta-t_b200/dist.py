@@ -214,16 +214,20 @@ def connect(r, plan: Plan, group=None):
 # ----------------------------------------------------------------------------------------------------------------------
 # convenience: build the local A and A^H of one rank from a row generator
 # ----------------------------------------------------------------------------------------------------------------------
-def local_operator(N, nranks, rank, gen_rows, max_bw, layout, band=None):
+def local_operator(N, nranks, rank, gen_rows, max_bw, layout, band=None, with_adjoint=True):
     """gen_rows(r_lo, r_hi) -> (rowptr, col_global, val) of global rows [r_lo, r_hi).  max_bw bounds |col - row|.
     band = (lo, hi) half widths of the dominant diagonal pattern (layout 1 only).
     -> (plan, (rowptr, col_local, val) of A, same of A^H, local sum of Im(A)^2 over the owned rows)"""
     r0, r1 = split_ownership(N, nranks, rank)
     if layout == 0:
         rp, cg, va = gen_rows(r0, r1)
-        s0, s1 = max(0, r0 - max_bw), min(N, r1 + max_bw)
-        srp, scg, sva = gen_rows(s0, s1)
-        hrp, hcg, hva = transpose_slab(srp, scg, sva, s0, r0, r1)
+        if with_adjoint:
+            s0, s1 = max(0, r0 - max_bw), min(N, r1 + max_bw)
+            srp, scg, sva = gen_rows(s0, s1)
+            hrp, hcg, hva = transpose_slab(srp, scg, sva, s0, r0, r1)
+            del srp, scg, sva
+        else:   # measurement runs that only use the direct operator: A stands in for A^H (never applied)
+            hrp, hcg, hva = rp, cg, va
         plan = plan_general(N, nranks, rank, np.concatenate([cg, hcg]))
         A = (rp, localize_general(plan, cg), va)
         AH = (hrp, localize_general(plan, hcg), hva)
@@ -245,13 +249,14 @@ def local_operator(N, nranks, rank, gen_rows, max_bw, layout, band=None):
     return plan, A, AH, im2
 
 
-def setup_rank(pkg, device, N, gen_rows, max_bw, layout, band, grid, group=None, DiscFlg=False, beta=0.0):
+def setup_rank(pkg, device, N, gen_rows, max_bw, layout, band, grid, group=None, DiscFlg=False, beta=0.0,
+               with_adjoint=True):
     """one-stop construction of a row-partitioned handle; grid = dict(k, Nw, Ns, Nt, ResRatio, dt, w, TransientRemoval)"""
     import torch
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    plan, A, AH, im2 = local_operator(N, world, rank, gen_rows, max_bw, layout, band)
+    plan, A, AH, im2 = local_operator(N, world, rank, gen_rows, max_bw, layout, band, with_adjoint)
     t = torch.tensor([im2], dtype=torch.float64, device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
     dist.all_reduce(t, group=group)
     real = float(t.item()) ** 0.5 < 1e-12                      # LNSStructure.c:37-40 on the whole matrix

@@ -27,6 +27,7 @@ ap.add_argument("--k", type=int, default=8)
 ap.add_argument("--Nw", type=int, default=32)
 ap.add_argument("--steps", type=int, default=16)
 ap.add_argument("--passes", type=int, default=2)
+ap.add_argument("--no-adjoint", action="store_true", help="do not build A^H (direct-only timing, halves the setup memory)")
 args = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0"))
@@ -60,7 +61,7 @@ if world == 1:
     r.set_grid(args.k, args.Nw, Ns, Nt, RR, dt, 0.05)
     n_own, nnz_own = N, int(rp[-1])
 else:
-    r, plan = pkg.dist.setup_rank(pkg, lrank, N, gen_rows, bw, 0, None, grid)
+    r, plan = pkg.dist.setup_rank(pkg, lrank, N, gen_rows, bw, 0, None, grid, with_adjoint=not args.no_adjoint)
     n_own = plan.n_own
     nnz_own = None
 setup_s = time.time() - t0
