@@ -122,6 +122,7 @@ struct rsvdt_context {
     int64_t use_banded = 3;   // 0: stage kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged DIA step
     int64_t tma_variant = 0;  // 0: tiles sized for 3 CTAs/SM, 1: for 2 CTAs/SM
     int64_t use_bcsr = 1;     // block-CSR stage kernel when the operator has dense B x B blocks
+    int64_t use_small = 1;    // single-CTA persistent kernel when the whole block vector fits in one SM's shared memory
 
     // instrumentation
     int64_t launches = 0;
@@ -577,13 +578,16 @@ int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **yc
     a.nbatch = nbatch;
     a.batch_stride = batch_stride;
     if (path >= 2) {
+        const bool fork = Op.nslow > 0;
         if (Op.nslow > 0) {
-            // the tiles holding rows off the diagonal pattern (domain boundaries) go through the CSR kernel on a side stream,
-            // concurrently with the main kernel: both read y_n and write disjoint rows of y_{n+1}
-            CU(cudaEventRecord(h->ev_fork, h->stream));
-            CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-            CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, Op.slow_ranges.as<int64_t>(), Op.nslow, h->side));
-            CU(cudaEventRecord(h->ev_join, h->side));
+            // the tiles holding rows off the diagonal pattern (domain boundaries) go through the CSR kernel -- on a side
+            // stream, concurrently with the main kernel, when the grid is large: both read y_n and write disjoint rows
+            if (fork) {
+                CU(cudaEventRecord(h->ev_fork, h->stream));
+                CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+            }
+            CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, Op.slow_ranges.as<int64_t>(), Op.nslow, fork ? h->side : h->stream));
+            if (fork) CU(cudaEventRecord(h->ev_join, h->side));
             h->launches += 1;
         }
         if (path == 3)
@@ -591,7 +595,7 @@ int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **yc
         else
             CU(launch_rk4_dia_step(Op.dia.as<cplx>(), Op.dia_lo, Op.dia_hi, Op.tile_ok.as<unsigned char>(), Op.ntiles, Op.d.nrows, nv, a, h->stream));
         h->launches += 1;
-        if (Op.nslow > 0) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        if (fork) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     } else {
         CU(launch_rk4_banded_step(Op.d, Op.lo_bw, Op.hi_bw, nv, a, (int)h->stage_variant, nullptr, 0, h->stream));
         h->launches += 1;
@@ -669,6 +673,10 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
     int path = 0;
     RS(step_path(h, Op, nv, &path));
     const bool banded = path != 0;
+    // measured on the tutorial size (5,000 units): one persistent CTA needs 28 us per forced step, the tiled kernels 21 us;
+    // the persistent kernel wins when a thread owns one or two units, or when many independent vectors run at once (below)
+    const bool small = !h->dist.on && small_persistent_supported(Op.d, nv) &&
+                       (h->use_small >= 2 || (h->use_small == 1 && h->n_ext * (int64_t)nv <= 1024));
     for (int b = 0; b < 2; b++) RS(ensure(h, h->slices[b], (size_t)S * U * sizeof(cplx)));
     RS(ensure(h, h->coef, (size_t)std::max<int64_t>((int64_t)128 * g.Nw_eff, g.Nw_eff * g.Nw) * sizeof(cplx)));
     RS(ensure(h, h->xa, (size_t)U * sizeof(cplx)));
@@ -698,6 +706,17 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
             f_carry = first_prev;
         }
         RS(synth_forcing(h, Fhat, sl, Sc, j_start, direct ? 1 : -1, first_prev));
+        if (small) {   // the whole chunk in one launch of the persistent single-CTA kernel
+            Bracket br(h, &h->ev_stage);
+            SmallStepArgs sa;
+            sa.y = ycur; sa.nsteps = (int)nsteps; sa.dt = g.dt; sa.slices = sl; sa.f_carry = f_carry; sa.snaps = snaps;
+            sa.i0 = i0; sa.Nt = g.Nt; sa.ResRatio = g.ResRatio; sa.Nstore = Nstore; sa.direct = direct ? 1 : 0;
+            CU(launch_rk4_small_persistent(Op.d, nv, sa, 1, h->stream));
+            h->launches += 1;
+            f_carry = sl + (int64_t)(Sc - 1) * U;
+            cur ^= 1;
+            continue;
+        }
         for (int64_t c = 0; c < nsteps; c++) {
             const int64_t i = i0 + c;
             const cplx *f_prev = (c == 0) ? f_carry : sl + (2 * c - 1) * U;
@@ -722,6 +741,15 @@ int unforced_steps(rsvdt_handle h, bool direct, int nv, cplx *y, int64_t nsteps)
 {
     CsrOwned &Op = direct ? h->A : h->AH;
     const int64_t U = h->n_ext * nv;
+    if (h->use_small && !h->dist.on && small_persistent_supported(Op.d, nv)) {
+        for (int64_t done = 0; done < nsteps; done += 4096) {
+            SmallStepArgs sa;
+            sa.y = y; sa.nsteps = (int)std::min<int64_t>(4096, nsteps - done); sa.dt = h->g.dt;
+            CU(launch_rk4_small_persistent(Op.d, nv, sa, 1, h->stream));
+            h->launches += 1;
+        }
+        return RSVDT_OK;
+    }
     int path = 0;
     RS(step_path(h, Op, nv, &path));
     const bool banded = path != 0;
@@ -743,6 +771,15 @@ int unforced_steps_slots(rsvdt_handle h, bool direct, int nv, cplx *base, int ns
 {
     CsrOwned &Op = direct ? h->A : h->AH;
     const int64_t U = h->n_ext * nv;
+    if (h->use_small && !h->dist.on && small_persistent_supported(Op.d, nv)) {   // one persistent CTA per slot
+        for (int64_t done = 0; done < nsteps; done += 4096) {
+            SmallStepArgs sa;
+            sa.y = base; sa.batch_stride = U; sa.nsteps = (int)std::min<int64_t>(4096, nsteps - done); sa.dt = h->g.dt;
+            CU(launch_rk4_small_persistent(Op.d, nv, sa, nslots, h->stream));
+            h->launches += 1;
+        }
+        return RSVDT_OK;
+    }
     int path = 0;
     RS(step_path(h, Op, nv, &path));
     const size_t bytes = (size_t)nslots * U * sizeof(cplx);
@@ -1617,6 +1654,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "use_banded")) h->use_banded = value;
     else if (!strcmp(name, "tma_variant")) h->tma_variant = value;
     else if (!strcmp(name, "use_bcsr")) h->use_bcsr = value;
+    else if (!strcmp(name, "use_small")) h->use_small = value;
     else return fail(h, RSVDT_ERR_ARG, "unknown option '%s'", name);
     return RSVDT_OK;
 }

@@ -1902,3 +1902,142 @@ cudaError_t launch_galerkin_solve(const cplx *Mt, const cplx *B1, const cplx *B2
     galerkin_solve_kernel<<<grid, 128, 0, s>>>(Mt, B1, B2, alpha, m, nw, scratch, C, status);
     return cudaGetLastError();
 }
+
+// =====================================================================================================
+// K1s: latency path for small problems (the tutorial operator: N = 500, k = 10).  The whole block vector and the operator
+//   fit in the shared memory of ONE CTA, so a single persistent CTA advances many RK4 steps per launch: the four stages are
+//   separated by __syncthreads() instead of kernel launches (the ~760,000 dependent stages of the shipped configuration
+//   cannot each pay a launch).  y and the RK4 accumulator live in registers, the two stage vectors ping-pong in shared
+//   memory, the forcing slices come from L2.  blockIdx.x selects an independent block vector (snapshot slots of the
+//   transient-removal step).  Arithmetic and summation order per row are those of K1.
+// =====================================================================================================
+template <int BT, int UPT, bool FORCED>
+__global__ void __launch_bounds__(BT)
+rk4_small_persistent_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const cplx *__restrict__ val,
+                            int n, int nnz, int nv, SmallStepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int nu = n * nv;
+    cplx *sval = reinterpret_cast<cplx *>(smraw);
+    cplx *XA = sval + nnz, *XB = XA + nu;
+    int *scol = reinterpret_cast<int *>(XB + nu);
+    int *srp = scol + nnz;
+    cplx *yg = a.y + (int64_t)blockIdx.x * a.batch_stride;
+    for (int t = threadIdx.x; t < nnz; t += BT) { sval[t] = val[t]; scol[t] = col[t]; }
+    for (int t = threadIdx.x; t <= n; t += BT) srp[t] = (int)rowptr[t];
+    cplx yv[UPT], acc[UPT];
+#pragma unroll
+    for (int i = 0; i < UPT; i++) {
+        const int e = threadIdx.x + i * BT;
+        yv[i] = (e < nu) ? yg[e] : make_double2(0.0, 0.0);
+        if (e < nu) XA[e] = yv[i];
+    }
+    __syncthreads();
+    const double dt = a.dt;
+    const double c_half = dt / 2, c_full = dt, w1 = dt / 6, w2 = dt / 6 * 2;
+    for (int c = 0; c < a.nsteps; c++) {
+        const cplx *f_prev = nullptr, *f_half = nullptr, *f_next = nullptr;
+        if (FORCED) {
+            f_prev = (c == 0) ? a.f_carry : a.slices + (int64_t)(2 * c - 1) * nu;
+            f_half = a.slices + (int64_t)(2 * c) * nu;
+            f_next = a.slices + (int64_t)(2 * c + 1) * nu;
+        }
+#pragma unroll
+        for (int st = 1; st <= 4; st++) {
+            const cplx *Xin = (st & 1) ? XA : XB;
+            cplx *Xout = (st & 1) ? XB : XA;
+            const cplx *fsl = (st == 1) ? f_prev : (st == 4 ? f_next : f_half);
+            // the units of a thread are processed in groups of FG: the forcing values of a group are requested together, so
+            // one L2 round trip is exposed per group instead of one per unit
+            constexpr int FG = 5;
+#pragma unroll
+            for (int i0 = 0; i0 < UPT; i0 += FG) {
+                cplx fv[FG];
+#pragma unroll
+                for (int j = 0; j < FG; j++) {
+                    const int e = threadIdx.x + (i0 + j) * BT;
+                    fv[j] = (FORCED && i0 + j < UPT && e < nu) ? ldg(fsl + e) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int j = 0; j < FG; j++) {
+                    const int i = i0 + j;
+                    const int e = threadIdx.x + i * BT;
+                    if (i < UPT && e < nu) {
+                        const int row = e / nv, iv = e - row * nv;
+                        cplx s = fv[j];
+                        const int p1 = srp[row + 1];
+                        for (int p = srp[row]; p < p1; ++p) cfma(s, sval[p], Xin[scol[p] * nv + iv]);
+                        if (st == 1) {
+                            Xout[e] = make_double2(fma(c_half, s.x, yv[i].x), fma(c_half, s.y, yv[i].y));
+                            acc[i] = make_double2(fma(w1, s.x, yv[i].x), fma(w1, s.y, yv[i].y));
+                        } else if (st == 2) {
+                            Xout[e] = make_double2(fma(c_half, s.x, yv[i].x), fma(c_half, s.y, yv[i].y));
+                            acc[i] = make_double2(fma(w2, s.x, acc[i].x), fma(w2, s.y, acc[i].y));
+                        } else if (st == 3) {
+                            Xout[e] = make_double2(fma(c_full, s.x, yv[i].x), fma(c_full, s.y, yv[i].y));
+                            acc[i] = make_double2(fma(w2, s.x, acc[i].x), fma(w2, s.y, acc[i].y));
+                        } else {
+                            yv[i] = make_double2(fma(w1, s.x, acc[i].x), fma(w1, s.y, acc[i].y));
+                            Xout[e] = yv[i];   // XA: stage-1 input of the next step
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (a.snaps) {   // SaveSnapshots.c:19-28
+            const int64_t i_step = a.i0 + c;
+            if (i_step > a.Nt) {
+                int64_t pos = i_step - a.Nt;
+                if (pos % a.ResRatio == 0) {
+                    pos = (pos / a.ResRatio - 1) % a.Nstore;
+                    if (!a.direct) pos = a.Nstore - 1 - pos;
+                    cplx *sn = a.snaps + pos * (int64_t)nu;
+#pragma unroll
+                    for (int i = 0; i < UPT; i++) {
+                        const int e = threadIdx.x + i * BT;
+                        if (e < nu) sn[e] = yv[i];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < UPT; i++) {
+        const int e = threadIdx.x + i * BT;
+        if (e < nu) yg[e] = yv[i];
+    }
+}
+
+namespace {
+constexpr int SMALL_BT = 512, SMALL_UPT = 10;
+inline size_t small_smem(int64_t n, int64_t nnz, int nv)
+{
+    return (size_t)(nnz + 2 * n * nv) * sizeof(cplx) + (size_t)(nnz + n + 1) * sizeof(int) + 16;
+}
+}  // namespace
+
+bool small_persistent_supported(const CsrDev &Op, int nv)
+{
+    if (Op.nrows != Op.ncols || Op.nrows <= 0) return false;
+    if (Op.nrows * (int64_t)nv > (int64_t)SMALL_BT * SMALL_UPT) return false;
+    return small_smem(Op.nrows, Op.nnz, nv) <= (size_t)200 * 1024;
+}
+
+cudaError_t launch_rk4_small_persistent(const CsrDev &Op, int nv, const SmallStepArgs &a, int nbatch, cudaStream_t s)
+{
+    const size_t smem = small_smem(Op.nrows, Op.nnz, nv);
+    cudaError_t e;
+    if (a.slices) {
+        auto kfn = rk4_small_persistent_kernel<SMALL_BT, SMALL_UPT, true>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<(unsigned)nbatch, SMALL_BT, smem, s>>>(Op.rowptr, Op.col, Op.val, (int)Op.nrows, (int)Op.nnz, nv, a);
+    } else {
+        auto kfn = rk4_small_persistent_kernel<SMALL_BT, SMALL_UPT, false>;
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kfn<<<(unsigned)nbatch, SMALL_BT, smem, s>>>(Op.rowptr, Op.col, Op.val, (int)Op.nrows, (int)Op.nnz, nv, a);
+    }
+    return cudaGetLastError();
+}

@@ -88,6 +88,22 @@ int dia_tma_tile_rows(int lo, int hi, int nv, int variant);
 cudaError_t launch_rk4_dia_tma_step(const cplx *dia, int lo, int hi, const unsigned char *tile_ok, int ntiles, int64_t N,
                                     int nv, int variant, const BandedStepArgs &a, cudaStream_t s);
 
+// Small problems: one persistent CTA advances `nsteps` RK4 steps of a whole block vector per launch (see kernels.cu, K1s).
+//   y: state in/out (block vector b at y + b*batch_stride); forced runs: slices[2*nsteps] + f_carry as in forced_steps();
+//   snapshots written by the kernel itself following SaveSnapshots.c:19-28 (i0 = 1-based index of the first step).
+struct SmallStepArgs {
+    cplx *y = nullptr;
+    int64_t batch_stride = 0;
+    int nsteps = 0;
+    double dt = 0;
+    const cplx *slices = nullptr, *f_carry = nullptr;
+    cplx *snaps = nullptr;
+    int64_t i0 = 0, Nt = 0, ResRatio = 1, Nstore = 1;
+    int direct = 1;
+};
+bool small_persistent_supported(const CsrDev &Op, int nv);
+cudaError_t launch_rk4_small_persistent(const CsrDev &Op, int nv, const SmallStepArgs &a, int nbatch, cudaStream_t s);
+
 // Twiddle coefficient tables (CreateDFTiDFTMats.c:42-58,76-84), generated on the device with exactly reduced phases.
 //   idft: coef[s][w] = (1/Ns) * exp(+2*pi*i * m(w) * j_s / (2Ns)),  j_s = (j_start + dir*s) mod 2Ns,  s < S, w < Nw_eff
 //   dft : coef[w'][j] = ResRatio * exp(-2*pi*i * w' * j / Nw),       w' < Nw_eff, j < Nw

@@ -20,11 +20,14 @@ def _need_gpu():
         pytest.fail("CUDA device required for -m gpu tests (there is no CPU fallback)")
 
 
-def _handle(pkg, A, v, DiscFlg=False, beta=0.0):
+def _handle(pkg, A, v, DiscFlg=False, beta=0.0, small=False):
+    # small=False switches the single-CTA persistent kernel off so that the test operators (a few hundred rows) exercise
+    # the kernels large problems use; test_small_persistent_kernel and the tutorial test cover the persistent path
     r = pkg.capi.RSVDt(0)
     real = r.LNSStructure(A.nrows, A.rowptr, A.col, A.val, DiscFlg, beta)
     assert real == v.RealOperator
     r.set_grid(v.k, v.Nw, v.Ns, v.Nt, v.ResRatio, v.dt, v.w, v.TransientRemoval)
+    r.set_option("use_small", 2 if small else 0)
     return r
 
 
@@ -318,7 +321,7 @@ def test_tutorial_config_full_solve_with_transient_removal(pkg, O, A_GL):
     assert (v.Ns, v.Nt, v.ResRatio) == (41916, 3336, 998)
     F = pkg.synthetic.random_forcing(500, k, Nw, seed=14)
     S_ref, U_ref, V_ref = O.full_solve(A_GL, v, 1, F)
-    r = _handle(pkg, A_GL, v)
+    r = _handle(pkg, A_GL, v, small=True)   # the latency path this configuration is meant for
     r.set_Y_hat(F)
     r.DirectActionRK4()
     r.PowerIterationRK4(1)
@@ -392,4 +395,54 @@ def test_weighted_actions(pkg, O, A_GL):
         r.ReadWeightMats("B", N - 1, Nb, *_rand_sparse(rng, N - 1, Nb, 2))
     with pytest.raises(pkg.capi.RsvdtError):
         r.ReadWeightMats("W_q_sqrt", Nc, Nc + 1, *_rand_sparse(rng, Nc, Nc + 1, 2))
+    r.close()
+
+
+@pytest.mark.parametrize("TR", [False, True])
+def test_small_persistent_kernel(pkg, O, A_GL, TR):
+    # K1s: one persistent CTA advances whole chunks of RK4 steps (forced, with in-kernel snapshots) and, for the transient
+    # removal, all snapshot slots at once; also the unforced entry points
+    k, Nw, w = 10, 8, 0.6
+    A = A_GL.shifted(0.3)
+    v = make_vars(O, pkg, 500, k, Nw, w, 0.003, 1.0, TR=TR)
+    F = _forcing(500, k * Nw, 31)
+    r = _handle(pkg, A, v, small=True)
+    r.keep_snapshots(True)
+    for direct in (True, False):
+        ref, snaps_ref = _oracle_action(O, A, v, F, direct, snaps=True)
+        n0 = r.kernel_launches(reset=True)
+        got = r.TSActionRK4(F, direct=direct)
+        launches = r.kernel_launches()
+        assert rel_err(r.get_snapshots(), snaps_ref) < ACTION_TOL
+        assert rel_err(got, ref) < (1e-8 if TR else ACTION_TOL)
+        rend = v.Nt + v.Ns + (v.ResRatio if TR else 0)
+        assert launches < rend / 8          # far fewer launches than RK4 steps
+    U = _forcing(500, 7, 32)
+    assert rel_err(r.TSExpADeltaT(U), O.ts_exp_a_deltat(A, v, U)) < 1e-12
+    q0 = _forcing(500, 1, 33)[:, 0]
+    q, norms, steps, reason = r.TransientRunRK4(q0, 900, 300, 1e3, 1e-12)
+    qr, nr, sr, rr = O.transient_run_rk4(A, v.dt, 900, 300, 1e3, 1e-12, q0)
+    assert rel_err(q, qr) < 1e-12 and np.allclose(norms, nr, rtol=1e-12)
+    r.close()
+
+
+@pytest.mark.parametrize("TR", [False, True])
+def test_committed_golden_vectors(pkg, O, A_GL, TR):
+    # the CUDA path against the committed fixture tests/golden/gl_small_golden.npz (no oracle call at test time)
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "gl_small_golden.npz"))
+    k, Nw, w = int(g["k"]), int(g["Nw"]), float(g["w"])
+    dt, Ns, Nt, RR = pkg.capi.setup_time_freq_grid(w, Nw, float(g["dt_in"]), float(g["TransientLength"]))
+    assert np.array_equal([dt, Ns, Nt, RR], g["grid"])
+    tag = "tr" if TR else "notr"
+    r = pkg.capi.RSVDt(0)
+    r.LNSStructure(500, A_GL.rowptr, A_GL.col, A_GL.val, True, float(g["beta"]))
+    r.set_grid(k, Nw, Ns, Nt, RR, dt, w, TR)
+    tol = 1e-9 if TR else ACTION_TOL
+    assert rel_err(r.TSActionRK4(g["F_hat"], direct=True), g[f"Y_direct_{tag}"]) < tol
+    assert rel_err(r.TSActionRK4(g["F_hat"], direct=False), g[f"Y_adjoint_{tag}"]) < tol
+    r.set_Y_hat(g["F_hat"])
+    r.DirectActionRK4(); r.PowerIterationRK4(1); r.SVDAllFreqsBeforeAdjoint(); r.StoreU(); r.AdjointActionRK4(); r.SVDAllFreqs()
+    assert np.abs(r.get_S_hat() / g[f"S_{tag}"] - 1).max() <= 1e-8
     r.close()

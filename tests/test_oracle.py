@@ -192,3 +192,16 @@ def test_full_solve_approximates_exact_gains(O, pkg, A_GL):
         sv = np.linalg.svd(np.linalg.inv(1j * m * w * np.eye(500) - Ad), compute_uv=False)
         assert S[0, iw] == pytest.approx(sv[0], rel=0.1)    # randomized estimate (k=4, q=1, weak gain separation)
         assert S[0, iw] <= sv[0] * (1 + 1e-6)               # and never above the exact optimal gain
+
+
+def test_oracle_reproduces_committed_golden_vectors(O, pkg, A_GL):
+    # tests/golden/gl_small_golden.npz (made by tests/golden/make_golden.py): pins the oracle against silent changes
+    g = np.load(os.path.join(GOLDEN, "gl_small_golden.npz"))
+    k, Nw, w = int(g["k"]), int(g["Nw"]), float(g["w"])
+    A = A_GL.shifted(float(g["beta"]))
+    v = make_vars(O, pkg, 500, k, Nw, w, float(g["dt_in"]), float(g["TransientLength"]))
+    assert np.allclose([v.dt, v.Ns, v.Nt, v.ResRatio], g["grid"], rtol=0, atol=0)
+    dft, idft = O.create_dft_idft_mats(Nw, Nw, v.Ns, False, False)
+    assert rel_err(O.ts_action_rk4(A, v, dft, idft, g["F_hat"]), g["Y_direct_notr"]) < 1e-13
+    vt = O.Vars(**{**v.__dict__, "TransientRemoval": True, "DirAdj": False})
+    assert rel_err(O.ts_action_rk4(A.hermitian_transpose(), vt, dft, idft, g["F_hat"]), g["Y_adjoint_tr"]) < 1e-11

@@ -17,6 +17,7 @@ ap.add_argument("--steps", type=int, default=32)
 ap.add_argument("--passes", type=int, default=2)
 ap.add_argument("--N", type=int, default=bench.WORKLOAD["N"])
 ap.add_argument("--option", action="append", default=[])
+ap.add_argument("--adjoint", action="store_true")
 ap.add_argument("--op", default="gl", help="gl | lns2d | lns3d")
 ap.add_argument("--shape", default="", help="grid shape for lns operators, e.g. 1000,1000 or 40,100,100")
 ap.add_argument("--k", type=int, default=0)
@@ -52,7 +53,7 @@ nnz_row = rowptr[-1] / N
 model_bytes = 4 * (nnz_row * 20 + 4) / c["k"] + 20 * 16
 r.set_Y_hat(F)
 for _ in range(args.passes):
-    ms = r.time_forced_steps(args.steps)
+    ms = r.time_forced_steps(args.steps, direct=not args.adjoint)
     st, n = r.last_kernel_ms("stage")
     idf, m = r.last_kernel_ms("idft")
     print(f"{args.steps} steps: {ms:.3f} ms total, stage {st:.3f} ms / {n} launches, idft {idf:.3f} ms / {m} launches")
