@@ -119,10 +119,18 @@ struct rsvdt_context {
     int64_t chunk_steps = 0;   // RK4 steps per forcing-synthesis chunk; 0 = automatic (up to 64, bounded by free memory)
     int64_t stage_variant = 0;
     int64_t idft_variant = 0;
-    int64_t use_banded = 3;   // 0: stage kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged DIA step
+    int64_t use_banded = -1;  // -1: automatic; 0: stage kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged DIA step
     int64_t tma_variant = 0;  // 0: tiles sized for 3 CTAs/SM, 1: for 2 CTAs/SM
     int64_t use_bcsr = 1;     // block-CSR stage kernel when the operator has dense B x B blocks
     int64_t use_small = 1;    // single-CTA persistent kernel when the whole block vector fits in one SM's shared memory
+
+    // CUDA graphs of a whole snapshot-free chunk of RK4 steps (launch-bound small problems): [direct][slice buffer]
+    struct ChunkGraph {
+        cudaGraphExec_t exec = nullptr;
+        const void *key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        int64_t nsteps = 0, launches = 0;
+    } graphs[2][2];
+    int64_t use_graph = 1;
 
     // instrumentation
     int64_t launches = 0;
@@ -550,12 +558,13 @@ int step_path(rsvdt_handle h, CsrOwned &Op, int nv, int *path)
         }
         return RSVDT_OK;
     }
-    if (!h->use_banded) return RSVDT_OK;
-    if (h->use_banded >= 3) {
+    const int64_t ub = h->use_banded < 0 ? 3 : h->use_banded;
+    if (!ub) return RSVDT_OK;
+    if (ub >= 3) {
         RS(plan_dia(h, Op, nv, 3));
         if (Op.plan_ok) { *path = 3; return RSVDT_OK; }
     }
-    if (h->use_banded >= 2) {
+    if (ub >= 2) {
         RS(plan_dia(h, Op, nv, 2));
         if (Op.plan_ok) { *path = 2; return RSVDT_OK; }
     }
@@ -672,6 +681,9 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
     const int S = (int)(2 * Tc);
     int path = 0;
     RS(step_path(h, Op, nv, &path));
+    // launch-bound sizes: four plain stage kernels per step replayed from a CUDA graph (9 us per step at 5,000 units) beat
+    // the fused tile kernels (16 us: TMA round trip, mbarrier and fork/join latencies dominate when the grid is a few CTAs)
+    if (h->use_banded < 0 && h->use_graph && !h->dist.on && U <= 262144) path = 0;
     const bool banded = path != 0;
     // measured on the tutorial size (5,000 units): one persistent CTA needs 28 us per forced step, the tiled kernels 21 us;
     // the persistent kernel wins when a thread owns one or two units, or when many independent vectors run at once (below)
@@ -713,6 +725,51 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
             sa.i0 = i0; sa.Nt = g.Nt; sa.ResRatio = g.ResRatio; sa.Nstore = Nstore; sa.direct = direct ? 1 : 0;
             CU(launch_rk4_small_persistent(Op.d, nv, sa, 1, h->stream));
             h->launches += 1;
+            f_carry = sl + (int64_t)(Sc - 1) * U;
+            cur ^= 1;
+            continue;
+        }
+        // launch-bound problems: a full chunk without snapshot steps is replayed as one CUDA graph (the kernel arguments of
+        // such a chunk depend only on the direction and on which of the two slice buffers it reads)
+        bool has_snap = false;
+        if (snaps)
+            for (int64_t c = 0; c < nsteps; c++) has_snap |= snapshot_slot(g, direct, Nstore, i0 + c) >= 0;
+        const bool graph_ok = h->use_graph && !h->dist.on && !has_snap && nsteps == Tc && (Tc % 2 == 0) &&
+                              U <= 262144 && f_carry == h->slices[cur ^ 1].as<cplx>() + (int64_t)(S - 1) * U;
+        if (graph_ok) {
+            auto &G = h->graphs[direct ? 1 : 0][cur];
+            const void *key[6] = {sl, f_carry, ycur, ynext, Op.d.val, (const void *)(intptr_t)(path * 1000 + nv)};
+            const bool hit = G.exec && G.nsteps == nsteps && !memcmp(G.key, key, sizeof key);
+            if (!hit) {
+                if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+                const int64_t l0 = h->launches;
+                cplx *yc = ycur, *yn = ynext;
+                const bool prof = h->profile;
+                h->profile = false;   // no timing events inside a capture
+                CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = RSVDT_OK;
+                for (int64_t c = 0; c < nsteps && rc == RSVDT_OK; c++) {
+                    const cplx *f_prev = (c == 0) ? f_carry : sl + (2 * c - 1) * U;
+                    rc = rk4_step_any(h, Op, nv, path, &yc, &yn, f_prev, sl + (2 * c) * U, sl + (2 * c + 1) * U, nullptr);
+                }
+                cudaGraph_t graph = nullptr;
+                cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                h->profile = prof;
+                if (rc != RSVDT_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                CU(ce);
+                ce = cudaGraphInstantiate(&G.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                CU(ce);
+                memcpy(G.key, key, sizeof key);
+                G.nsteps = nsteps;
+                G.launches = h->launches - l0;
+                h->launches = l0;   // the capture did not run anything
+            }
+            {
+                Bracket br(h, &h->ev_stage);
+                CU(cudaGraphLaunch(G.exec, h->stream));
+            }
+            h->launches += G.launches;
             f_carry = sl + (int64_t)(Sc - 1) * U;
             cur ^= 1;
             continue;
@@ -1096,6 +1153,9 @@ int rsvdt_destroy(rsvdt_handle h)
     DevBuf *bufs[] = {&h->Yhat, &h->Uhat, &h->Vhat, &h->Shat, &h->y, &h->xa, &h->xb, &h->acc, &h->slices[0], &h->slices[1],
                       &h->coef, &h->snaps, &h->small, &h->smallM, &h->status, &h->gram_partial, &h->scalars};
     for (DevBuf *b : bufs) b->release();
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++)
+            if (h->graphs[a][b].exec) cudaGraphExecDestroy(h->graphs[a][b].exec);
     cudaEventDestroy(h->ev_fork);
     cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->side);
@@ -1655,6 +1715,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "tma_variant")) h->tma_variant = value;
     else if (!strcmp(name, "use_bcsr")) h->use_bcsr = value;
     else if (!strcmp(name, "use_small")) h->use_small = value;
+    else if (!strcmp(name, "use_graph")) h->use_graph = value;
     else return fail(h, RSVDT_ERR_ARG, "unknown option '%s'", name);
     return RSVDT_OK;
 }

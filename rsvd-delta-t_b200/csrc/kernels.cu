@@ -1627,10 +1627,10 @@ cudaError_t launch_halo_wait_unpack(cplx *dst, int nvec, const void *ins_dev, in
 template <int PB>
 __global__ void __launch_bounds__(256)
 stack_gram2_kernel(const cplx *__restrict__ X, int64_t xs, int ma, const cplx *__restrict__ Y, int64_t ys, int mb, int nv,
-                   int64_t row0, int64_t nrows, int rows_per_chunk, cplx *__restrict__ partial)
+                   int64_t row0, int64_t nrows, int rows_per_chunk, int RT, cplx *__restrict__ partial)
 {
-    extern __shared__ cplx sm[];   // Xt[32][ma] then Yt[32][mb]
-    cplx *Xt = sm, *Yt = sm + 32 * ma;
+    extern __shared__ cplx sm[];   // Xt[RT][ma] then Yt[RT][mb]  (RT rows per tile, sized to the shared memory)
+    cplx *Xt = sm, *Yt = sm + RT * ma;
     const int z = blockIdx.y;
     const int batch = blockIdx.z;
     const int npairs = ma * mb;
@@ -1645,15 +1645,15 @@ stack_gram2_kernel(const cplx *__restrict__ X, int64_t xs, int ma, const cplx *_
         pa[q] = pr < npairs ? pr / mb : -1;
         pbq[q] = pr < npairs ? pr - (pr / mb) * mb : 0;
     }
-    for (int64_t r0 = rb; r0 < re; r0 += 32) {
-        const int nr = (int)min((int64_t)32, re - r0);
+    for (int64_t r0 = rb; r0 < re; r0 += RT) {
+        const int nr = (int)min((int64_t)RT, re - r0);
         __syncthreads();
-        for (int t = threadIdx.x; t < 32 * ma; t += blockDim.x) {
-            const int a = t / 32, r = t - a * 32;
+        for (int t = threadIdx.x; t < RT * ma; t += blockDim.x) {
+            const int a = t / RT, r = t - a * RT;
             Xt[r * ma + a] = r < nr ? X[(int64_t)a * xs + (r0 + r) * nv + z] : make_double2(0.0, 0.0);
         }
-        for (int t = threadIdx.x; t < 32 * mb; t += blockDim.x) {
-            const int b = t / 32, r = t - b * 32;
+        for (int t = threadIdx.x; t < RT * mb; t += blockDim.x) {
+            const int b = t / RT, r = t - b * RT;
             Yt[r * mb + b] = r < nr ? Y[(int64_t)b * ys + (r0 + r) * nv + z] : make_double2(0.0, 0.0);
         }
         __syncthreads();
@@ -1661,7 +1661,7 @@ stack_gram2_kernel(const cplx *__restrict__ X, int64_t xs, int ma, const cplx *_
         for (int q = 0; q < PB; q++) {
             if (pa[q] >= 0) {
                 cplx s = acc[q];
-                for (int r = 0; r < 32; r++) cfma_conj(s, Xt[r * ma + pa[q]], Yt[r * mb + pbq[q]]);
+                for (int r = 0; r < RT; r++) cfma_conj(s, Xt[r * ma + pa[q]], Yt[r * mb + pbq[q]]);
                 acc[q] = s;
             }
         }
@@ -1682,11 +1682,14 @@ cudaError_t launch_stack_gram2(const cplx *X, int64_t xs, int ma, const cplx *Y,
     constexpr int PB = 8;
     const int chunks = stack_gram2_chunks(nrows);
     const int npairs = ma * mb;
-    const size_t smem = (size_t)32 * (ma + mb) * sizeof(cplx);
+    int RT = (int)(((size_t)200 * 1024) / ((size_t)(ma + mb) * sizeof(cplx)));   // rows per shared-memory tile
+    RT = RT > 32 ? 32 : RT;
+    if (RT < 1) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)RT * (ma + mb) * sizeof(cplx);
     cudaError_t e = cudaFuncSetAttribute(stack_gram2_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)chunks, (unsigned)nv, (unsigned)((npairs + 256 * PB - 1) / (256 * PB)));
-    stack_gram2_kernel<PB><<<grid, 256, smem, s>>>(X, xs, ma, Y, ys, mb, nv, row0, nrows, 8192, partial);
+    stack_gram2_kernel<PB><<<grid, 256, smem, s>>>(X, xs, ma, Y, ys, mb, nv, row0, nrows, 8192, RT, partial);
     const int64_t n_out = (int64_t)nv * npairs;
     gram_reduce_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, s>>>(partial, chunks, n_out, G);
     return cudaGetLastError();

@@ -446,3 +446,26 @@ def test_committed_golden_vectors(pkg, O, A_GL, TR):
     r.DirectActionRK4(); r.PowerIterationRK4(1); r.SVDAllFreqsBeforeAdjoint(); r.StoreU(); r.AdjointActionRK4(); r.SVDAllFreqs()
     assert np.abs(r.get_S_hat() / g[f"S_{tag}"] - 1).max() <= 1e-8
     r.close()
+
+
+@pytest.mark.parametrize("opts", [dict(use_banded=3), dict(use_banded=1), dict(use_banded=0)])
+def test_cuda_graph_replay_is_bit_identical(pkg, O, A_GL, opts):
+    # chunks of RK4 steps without snapshot steps are replayed as CUDA graphs on launch-bound problems; same bits either way
+    k, Nw = 4, 6
+    dt, Ns, Nt, RR = O.setup_time_freq_grid(0.05, Nw, 0.02, 3.0)
+    v = O.Vars(N=500, k=k, Nw=Nw, Nw_eff=Nw, Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=0.05)
+    F = _forcing(500, k * Nw, 41)
+    A = A_GL.shifted(2.0)
+    res = {}
+    for ug in (0, 1):
+        r = _handle(pkg, A, v)
+        for name, val in opts.items():
+            r.set_option(name, val)
+        r.set_option("use_graph", ug)
+        r.set_option("chunk_steps", 16)
+        r.keep_snapshots(True)
+        res[ug] = (r.TSActionRK4(F, direct=True), r.TSActionRK4(F, direct=False), r.get_snapshots())
+        r.close()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert rel_err(res[1][0], _oracle_action(O, A, v, F, True)) < ACTION_TOL
