@@ -94,6 +94,9 @@ struct rsvdt_context {
         std::vector<void *> peer_mailbox, peer_flags;   // IPC-mapped peer pointers (index = rank)
         unsigned long long epoch = 0;
         int max_out = 0, max_in = 0;
+        // interior / boundary split of the owned rows (layout 0): rows [0, lo_end) and [hi_begin, N) are sent to peers
+        bool overlap = false;
+        int64_t lo_end = 0, hi_begin = 0;
         rsvdt_allreduce_fn allreduce = nullptr;
         void *allreduce_user = nullptr;
     } dist;
@@ -131,6 +134,7 @@ struct rsvdt_context {
         int64_t nsteps = 0, launches = 0;
     } graphs[2][2];
     int64_t use_graph = 1;
+    int64_t use_overlap = 1;  // row-partitioned runs: hide the halo exchange behind the interior rows
 
     // instrumentation
     int64_t launches = 0;
@@ -466,19 +470,35 @@ int download_stack(rsvdt_handle h, const DevBuf &src, double *host, int64_t rows
 }
 
 // ---- halo exchange of a block vector [row][nvec] (the VecScatter of PETSc's MPIAIJ mat-vec) ----------------------------
-int dist_exchange(rsvdt_handle h, cplx *buf, int nvec)
+// first half: send my boundary rows (push into the peers' mailboxes, publish the epoch) on stream `s`
+int dist_push(rsvdt_handle h, const cplx *buf, int nvec, cudaStream_t s)
 {
     auto &D = h->dist;
-    if (!D.on) return RSVDT_OK;
     if (!D.connected) return fail(h, RSVDT_ERR_STATE, "row-partitioned run: peers not connected (rsvdt_dist_ipc_import)");
     if (nvec > D.nvec_max) return fail(h, RSVDT_ERR_ARG, "halo exchange of %d vectors exceeds the mailbox (%d)", nvec, D.nvec_max);
     D.epoch++;
     const int parity = (int)(D.epoch & 1ull);
-    CU(launch_halo_push(buf, nvec, D.msgs_dev.p, (int)D.out.size(), D.max_out, parity, D.nvec_max, h->stream));
-    CU(launch_halo_signal(D.peer_flags_dev.p, (int)D.out.size(), D.epoch, h->stream));
-    CU(launch_halo_wait_unpack(buf, nvec, D.ins_dev.p, (int)D.in.size(), D.max_in, parity, D.nvec_max, D.epoch, h->stream));
-    h->launches += (D.out.empty() ? 0 : 2) + (D.in.empty() ? 0 : 1);
+    CU(launch_halo_push(buf, nvec, D.msgs_dev.p, (int)D.out.size(), D.max_out, parity, D.nvec_max, s));
+    CU(launch_halo_signal(D.peer_flags_dev.p, (int)D.out.size(), D.epoch, s));
+    h->launches += D.out.empty() ? 0 : 2;
     return RSVDT_OK;
+}
+
+// second half: wait for the peers' epoch and copy their rows into my ghost rows (main stream)
+int dist_wait_unpack(rsvdt_handle h, cplx *buf, int nvec)
+{
+    auto &D = h->dist;
+    const int parity = (int)(D.epoch & 1ull);
+    CU(launch_halo_wait_unpack(buf, nvec, D.ins_dev.p, (int)D.in.size(), D.max_in, parity, D.nvec_max, D.epoch, h->stream));
+    h->launches += D.in.empty() ? 0 : 1;
+    return RSVDT_OK;
+}
+
+int dist_exchange(rsvdt_handle h, cplx *buf, int nvec)
+{
+    if (!h->dist.on) return RSVDT_OK;
+    RS(dist_push(h, buf, nvec, h->stream));
+    return dist_wait_unpack(h, buf, nvec);
 }
 
 // ---- one RK4 step on a block of nv vectors (TSRK4.c:18-47 / TSTransRK4.c:15-36) ---------------------------
@@ -490,11 +510,51 @@ cudaError_t launch_stage_any(rsvdt_handle h, const CsrOwned &Op, int nv, int mod
     return launch_rk4_stage(Op.d, nv, mode, a, (int)h->stage_variant, h->stream);
 }
 
+// One stage of a row-partitioned run with the halo exchange hidden behind the interior rows (the overlap MPIAIJ's mat-vec
+// does between its VecScatter and the diagonal-block product): boundary rows first, their push to the peers on the side
+// stream while the interior rows are computed, then the unpack of the peers' rows.
+int stage_overlapped(rsvdt_handle h, const CsrOwned &Op, int nv, int mode, const StageArgs &a, cplx *out_buf)
+{
+    auto &D = h->dist;
+    const bool bc = h->use_bcsr && Op.bcsr_valid && bcsr_stage_supported(Op.bcsr.B, nv);
+    auto launch = [&](int64_t r0, int64_t cnt) -> cudaError_t {
+        if (cnt <= 0) return cudaSuccess;
+        return bc ? launch_rk4_stage_bcsr(Op.bcsr, nv, mode, a, (int)h->stage_variant, h->stream, r0, cnt)
+                  : launch_rk4_stage(Op.d, nv, mode, a, (int)h->stage_variant, h->stream, r0, cnt);
+    };
+    CU(launch(0, D.lo_end));
+    CU(launch(D.hi_begin, h->N - D.hi_begin));
+    CU(cudaEventRecord(h->ev_fork, h->stream));
+    CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    RS(dist_push(h, out_buf, nv, h->side));
+    CU(cudaEventRecord(h->ev_join, h->side));
+    CU(launch(D.lo_end, D.hi_begin - D.lo_end));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    return dist_wait_unpack(h, out_buf, nv);
+}
+
 int rk4_step(rsvdt_handle h, const CsrOwned &Op, int nv, cplx *y, cplx *xa, cplx *xb, cplx *acc, const cplx *f_prev,
              const cplx *f_half, const cplx *f_next, cplx *snap)
 {
     const double dt = h->g.dt;
     StageArgs a;
+    if (h->dist.on && h->dist.overlap && h->use_overlap) {
+        Bracket br(h, &h->ev_stage);
+        a = StageArgs();
+        a.xin = y; a.ybase = y; a.f = f_prev; a.xout = xa; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6;
+        RS(stage_overlapped(h, Op, nv, 0, a, xa));
+        a = StageArgs();
+        a.xin = xa; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xb; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6 * 2;
+        RS(stage_overlapped(h, Op, nv, 1, a, xb));
+        a = StageArgs();
+        a.xin = xb; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xa; a.acc_out = acc; a.cx = dt; a.ca = dt / 6 * 2;
+        RS(stage_overlapped(h, Op, nv, 1, a, xa));
+        a = StageArgs();
+        a.xin = xa; a.f = f_next; a.acc_in = acc; a.acc_out = y; a.snap = snap; a.ca = dt / 6;
+        RS(stage_overlapped(h, Op, nv, 2, a, y));
+        h->launches += 12;
+        return RSVDT_OK;
+    }
     {   // k1 = Op y + F3(prev) ; x2 = y + dt/2 k1 ; acc = y + dt/6 k1            TSRK4.c:18,30,44
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
@@ -1555,6 +1615,23 @@ int rsvdt_dist_set_messages(rsvdt_handle h, int nout, const int *out_peer, const
         D.max_in = std::max(D.max_in, m.count);
         D.in.push_back(m);
     }
+    // interior / boundary split (layout 0): the rows sent to peers sit at the two ends of the owned range for slab partitions
+    D.overlap = false;
+    if (D.layout == 0 && nout > 0) {
+        int64_t lo_end = 0, hi_begin = h->N, o2 = 0;
+        for (int i = 0; i < nout; o2 += out_count[i], i++)
+            for (int j = 0; j < out_count[i]; j++) {
+                const int64_t r = out_rows[o2 + j];
+                if (r < h->N / 2) lo_end = std::max(lo_end, r + 1); else hi_begin = std::min(hi_begin, r);
+            }
+        lo_end = std::min(h->N, (lo_end + 59) / 60 * 60);   // whole block rows for every supported block size (3, 4, 5)
+        hi_begin = hi_begin / 60 * 60;
+        if (hi_begin > lo_end && 2 * (lo_end + h->N - hi_begin) <= h->N) {
+            D.overlap = true;
+            D.lo_end = lo_end;
+            D.hi_begin = hi_begin;
+        }
+    }
     // mailbox: two epoch-parity slots per incoming message; flags: one counter per rank
     CU(D.mailbox.alloc(std::max<size_t>((size_t)2 * D.in_rows_total * D.nvec_max * sizeof(cplx), 256)));
     CU(D.flags.alloc((size_t)D.nranks * sizeof(unsigned long long)));
@@ -1716,6 +1793,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "use_bcsr")) h->use_bcsr = value;
     else if (!strcmp(name, "use_small")) h->use_small = value;
     else if (!strcmp(name, "use_graph")) h->use_graph = value;
+    else if (!strcmp(name, "use_overlap")) h->use_overlap = value;
     else return fail(h, RSVDT_ERR_ARG, "unknown option '%s'", name);
     return RSVDT_OK;
 }

@@ -37,10 +37,10 @@ DEVFN cplx ldg(const cplx *p) { return __ldg(p); }
 template <int MODE, bool HAS_F>
 __global__ void __launch_bounds__(256)
 rk4_stage_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const cplx *__restrict__ val,
-                     int nv, int64_t n_units, StageArgs a)
+                     int nv, int64_t u_begin, int64_t n_units, StageArgs a)
 {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_units) return;
+    const int64_t u = u_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_begin, row_begin + count)
+    if (u >= u_begin + n_units) return;
     const int64_t row = u / nv;
     const int iv = (int)(u - row * nv);
     cplx s = make_double2(0.0, 0.0);
@@ -107,13 +107,13 @@ DEVFN cplx axpy1(double c, const cplx s, const cplx y) { return make_double2(fma
 template <int B, int CV, int MODE, bool HAS_F>
 __global__ void __launch_bounds__(128, 4)
 rk4_stage_bcsr_kernel(const int64_t *__restrict__ browptr, const int32_t *__restrict__ bcol, const cplx *__restrict__ bval,
-                      int nv, int nvp, int64_t n_threads, StageArgs a)
+                      int nv, int nvp, int64_t br_begin, int64_t n_threads, StageArgs a)
 {
     constexpr int BS = (B * B + 1) & ~1;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
-    const int64_t br = t / nvp;
-    const int iv0 = (int)(t - br * nvp) * CV;
+    const int64_t br = br_begin + t / nvp;
+    const int iv0 = (int)(t % nvp) * CV;
     const int64_t u0 = br * B * nv + iv0;   // unit of (first row of the block row, iv0); next row: + nv
     cplx s[B][CV];
 #pragma unroll
@@ -202,15 +202,16 @@ rk4_stage_bcsr_kernel(const int64_t *__restrict__ browptr, const int32_t *__rest
 }
 
 template <int B, int CV>
-static cudaError_t bcsr_launch(const BcsrDev &Op, int nv, int mode, const StageArgs &a, cudaStream_t s)
+static cudaError_t bcsr_launch(const BcsrDev &Op, int nv, int mode, const StageArgs &a, cudaStream_t s, int64_t br_begin,
+                               int64_t br_count)
 {
     const int nvp = nv / CV;
-    const int64_t n_threads = Op.nbrows * nvp;
-    if (n_threads == 0) return cudaSuccess;
+    const int64_t n_threads = br_count * nvp;
+    if (n_threads <= 0) return cudaSuccess;
     const int threads = 128;
     const unsigned blocks = (unsigned)((n_threads + threads - 1) / threads);
     const bool hf = a.f != nullptr;
-#define LAUNCH(M, F) rk4_stage_bcsr_kernel<B, CV, M, F><<<blocks, threads, 0, s>>>(Op.browptr, Op.bcol, Op.bval, nv, nvp, n_threads, a)
+#define LAUNCH(M, F) rk4_stage_bcsr_kernel<B, CV, M, F><<<blocks, threads, 0, s>>>(Op.browptr, Op.bcol, Op.bval, nv, nvp, br_begin, n_threads, a)
     if (mode == 0) { if (hf) LAUNCH(0, true); else LAUNCH(0, false); }
     else if (mode == 1) { if (hf) LAUNCH(1, true); else LAUNCH(1, false); }
     else { if (hf) LAUNCH(2, true); else LAUNCH(2, false); }
@@ -220,26 +221,32 @@ static cudaError_t bcsr_launch(const BcsrDev &Op, int nv, int mode, const StageA
 
 bool bcsr_stage_supported(int B, int nv) { return (B == 3 || B == 4 || B == 5) && nv >= 1; }
 
-cudaError_t launch_rk4_stage_bcsr(const BcsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s)
+cudaError_t launch_rk4_stage_bcsr(const BcsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s,
+                                  int64_t row_begin, int64_t row_count)
 {
     const bool two = (nv % 2 == 0) && variant != 1;
+    if (row_count < 0) row_count = Op.nbrows * Op.B - row_begin;
+    if (row_begin % Op.B || row_count % Op.B) return cudaErrorInvalidValue;   // ranges must be whole block rows
+    const int64_t b0 = row_begin / Op.B, bn = row_count / Op.B;
     switch (Op.B) {
-        case 3: return two ? bcsr_launch<3, 2>(Op, nv, mode, a, s) : bcsr_launch<3, 1>(Op, nv, mode, a, s);
-        case 4: return two ? bcsr_launch<4, 2>(Op, nv, mode, a, s) : bcsr_launch<4, 1>(Op, nv, mode, a, s);
-        case 5: return two ? bcsr_launch<5, 2>(Op, nv, mode, a, s) : bcsr_launch<5, 1>(Op, nv, mode, a, s);
+        case 3: return two ? bcsr_launch<3, 2>(Op, nv, mode, a, s, b0, bn) : bcsr_launch<3, 1>(Op, nv, mode, a, s, b0, bn);
+        case 4: return two ? bcsr_launch<4, 2>(Op, nv, mode, a, s, b0, bn) : bcsr_launch<4, 1>(Op, nv, mode, a, s, b0, bn);
+        case 5: return two ? bcsr_launch<5, 2>(Op, nv, mode, a, s, b0, bn) : bcsr_launch<5, 1>(Op, nv, mode, a, s, b0, bn);
         default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s)
+cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s,
+                             int64_t row_begin, int64_t row_count)
 {
     (void)variant;
-    const int64_t n_units = Op.nrows * (int64_t)nv;
-    if (n_units == 0) return cudaSuccess;
+    if (row_count < 0) row_count = Op.nrows - row_begin;
+    const int64_t n_units = row_count * (int64_t)nv, u_begin = row_begin * (int64_t)nv;
+    if (n_units <= 0) return cudaSuccess;
     const int threads = 256;
     const int64_t blocks = (n_units + threads - 1) / threads;
     const bool hf = a.f != nullptr;
-#define LAUNCH(M, F) rk4_stage_csr_kernel<M, F><<<(unsigned)blocks, threads, 0, s>>>(Op.rowptr, Op.col, Op.val, nv, n_units, a)
+#define LAUNCH(M, F) rk4_stage_csr_kernel<M, F><<<(unsigned)blocks, threads, 0, s>>>(Op.rowptr, Op.col, Op.val, nv, u_begin, n_units, a)
     if (mode == 0) { if (hf) LAUNCH(0, true); else LAUNCH(0, false); }
     else if (mode == 1) { if (hf) LAUNCH(1, true); else LAUNCH(1, false); }
     else { if (hf) LAUNCH(2, true); else LAUNCH(2, false); }

@@ -38,7 +38,10 @@ struct StageArgs {
     double cx = 0, ca = 0;
 };
 
-cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s);
+// rows [row_begin, row_begin + row_count) only (row_count < 0: to the end): the interior / boundary split that overlaps
+// the halo exchange of a row-partitioned run with the interior rows
+cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s,
+                             int64_t row_begin = 0, int64_t row_count = -1);
 
 // Block-CSR form (dense B x B blocks, e.g. the 5 flow variables of an LNS operator): browptr[nbrows+1], bcol[nblocks]
 // (block column), bval[nblocks][BS] with the B*B entries column-major ([j][r]) and BS = B*B rounded up to even (32-byte aligned
@@ -52,7 +55,8 @@ struct BcsrDev {
 };
 bool bcsr_stage_supported(int B, int nv);
 // variant 1 forces one test vector per thread (default: two when nv is even)
-cudaError_t launch_rk4_stage_bcsr(const BcsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s);
+cudaError_t launch_rk4_stage_bcsr(const BcsrDev &Op, int nv, int mode, const StageArgs &a, int variant, cudaStream_t s,
+                                  int64_t row_begin = 0, int64_t row_count = -1);
 
 // Whole RK4 step in one kernel for narrow-band operators (all 4 stages, halo recomputation in shared memory).
 //   f_prev / f_half / f_next : forcing slices at t_n, t_n + dt/2, t_n + dt (nullptr -> unforced)
