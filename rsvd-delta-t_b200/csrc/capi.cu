@@ -103,7 +103,6 @@ struct rsvdt_context {
 
     // Weight_matrices (Variables.h:69-80): 0=W_f_sqrt_inv 1=B 2=W_q_sqrt_inv 3=W_q_sqrt 4=C, and their conj-transposes
     CsrOwned W[5], WH[5];
-    int64_t Nb = 0, Nc = 0;
 
     // RSVD_vars + TS_vars
     rsvdt_grid g{};
@@ -140,7 +139,6 @@ struct rsvdt_context {
     int64_t launches = 0;
     bool profile = false;
     std::vector<EventPair> ev_stage, ev_idft, ev_dft;
-    std::vector<EventPair> ev_pool;
     float last_ms_stage = 0, last_ms_idft = 0, last_ms_dft = 0, last_ms_all = 0;
     int64_t last_n_stage = 0, last_n_idft = 0, last_n_dft = 0;
 };
@@ -1340,16 +1338,33 @@ int rsvdt_qr_all_freqs(rsvdt_handle h)
     std::vector<int> st((size_t)g.Nw_eff);
     int64_t srows, roff;
     stack_geom(h, h->yhat_rows, &srows, &roff);
-    for (int pass = 0; pass < 2; pass++) {  // CholeskyQR2 (QRAllFreqs.c:22-32 semantics: Q with diag(R) > 0)
-        RS(gram_all(h, h->Yhat.as<cplx>(), h->yhat_rows, srows, roff));
-        CU(launch_chol_inverse(h->small.as<cplx>(), (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->status.as<int>(), h->stream));
+    // CholeskyQR2 (QRAllFreqs.c:22-32 semantics: thin Q with diag(R) > 0).  If a Cholesky factorisation breaks down (a block
+    // with condition number beyond ~1e8) the pass is redone with the shift of shifted CholeskyQR3 and two more passes follow.
+    int npass = 2;
+    bool shifted = false;
+    for (int pass = 0; pass < npass; pass++) {
+        double shift = 0.0;
+        for (int attempt = 0;; attempt++) {
+            RS(gram_all(h, h->Yhat.as<cplx>(), h->yhat_rows, srows, roff));
+            CU(launch_chol_inverse_big(h->small.as<cplx>(), (int)g.k, (int)g.Nw_eff, shift, h->smallM.as<cplx>(), h->status.as<int>(), h->stream));
+            h->launches += 1;
+            CU(cudaMemcpyAsync(st.data(), h->status.p, st.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            int64_t badw = -1;
+            for (int64_t w = 0; w < g.Nw_eff && badw < 0; w++)
+                if (st[(size_t)w] != 0) badw = w;
+            if (badw < 0) break;
+            if (attempt > 0 || shifted)
+                return fail(h, RSVDT_ERR_NUMERIC, "QR breakdown at frequency %lld (column %d, pass %d): numerically rank-deficient block",
+                            (long long)badw, st[(size_t)badw] - 1, pass);
+            shifted = true;
+            npass = pass + 3;
+            shift = 11.0 * ((double)h->N_global * g.k + (double)g.k * (g.k + 1)) * 1.1e-16;
+        }
         CU(launch_apply_right(h->Yhat.as<cplx>(), srows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
-        h->launches += 2;
-        CU(cudaMemcpyAsync(st.data(), h->status.p, st.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        for (int64_t w = 0; w < g.Nw_eff; w++)
-            if (st[(size_t)w] != 0) return fail(h, RSVDT_ERR_NUMERIC, "QR breakdown at frequency %lld (column %d, pass %d)", (long long)w, st[(size_t)w] - 1, pass);
+        h->launches += 1;
     }
+    CU(cudaStreamSynchronize(h->stream));
     return RSVDT_OK;
 }
 

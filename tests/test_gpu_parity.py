@@ -469,3 +469,26 @@ def test_cuda_graph_replay_is_bit_identical(pkg, O, A_GL, opts):
     for a, b in zip(res[0], res[1]):
         assert np.array_equal(a, b)
     assert rel_err(res[1][0], _oracle_action(O, A, v, F, True)) < ACTION_TOL
+
+
+def test_qr_ill_conditioned_block_falls_back_to_shifted_cholqr3(pkg, O):
+    # a block with condition number ~1e11 breaks plain CholeskyQR2; the shifted restart must still return the thin-QR factor
+    rng = np.random.default_rng(51)
+    N, k, Nw = 4000, 6, 3
+    Y = np.asfortranarray(rng.standard_normal((N, k * Nw)) + 1j * rng.standard_normal((N, k * Nw)))
+    Y[:, k + 2] = Y[:, k + 1] + 1e-11 * Y[:, k + 2]
+    n, rp, ci, va = pkg.synthetic.ginzburg_landau(N)
+    v = make_vars(O, pkg, N, k, Nw, 3.0, 0.004, 0.3)
+    r = _handle(pkg, O.Csr(N, N, rp, ci, va), v)
+    r.set_Y_hat(Y)
+    r.QRAllFreqs()
+    Q = r.get_Y_hat()
+    for iw in range(Nw):
+        blk = slice(iw * k, (iw + 1) * k)
+        assert np.abs(Q[:, blk].conj().T @ Q[:, blk] - np.eye(k)).max() < 1e-12
+        # same column space: Y = Q (Q^H Y)
+        P = Q[:, blk] @ (Q[:, blk].conj().T @ Y[:, blk])
+        assert rel_err(P, Y[:, blk]) < 1e-10
+    Qref = O.qr_all_freqs(N, k, Nw, Y)
+    assert rel_err(Q[:, :k], Qref[:, :k]) < 1e-10       # well-conditioned blocks agree with Gram-Schmidt
+    r.close()
