@@ -71,6 +71,8 @@ struct rsvdt_context {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // runs the few irregular tiles of a fused step next to the main kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t synth_stream = nullptr;  // low priority: forcing synthesis of the next chunk, overlapped with the RK4 steps
+    cudaEvent_t ev_step0 = nullptr, ev_synth = nullptr;
     std::string err;
 
     // LNS_vars (Variables.h:59-62).  N = rows owned by this rank (all rows on one GPU); the local arrays hold n_ext rows:
@@ -134,6 +136,7 @@ struct rsvdt_context {
     } graphs[2][2];
     int64_t use_graph = 1;
     int64_t use_overlap = 1;  // row-partitioned runs: hide the halo exchange behind the interior rows
+    int64_t use_pipeline = 0; // (measured: no gain, the two kernels compete for SM residency) synthesise the next chunk's forcing on a low-priority stream while the current chunk steps
 
     // instrumentation
     int64_t launches = 0;
@@ -183,17 +186,18 @@ struct Bracket {
     std::vector<EventPair> *list;
     EventPair ep{};
     bool on = false;
-    Bracket(rsvdt_handle h_, std::vector<EventPair> *l) : h(h_), list(l)
+    cudaStream_t st;
+    Bracket(rsvdt_handle h_, std::vector<EventPair> *l, cudaStream_t s = nullptr) : h(h_), list(l), st(s ? s : h_->stream)
     {
         if (h->profile && list->size() < 8192) {
             on = cudaEventCreate(&ep.a) == cudaSuccess && cudaEventCreate(&ep.b) == cudaSuccess;
-            if (on) cudaEventRecord(ep.a, h->stream);
+            if (on) cudaEventRecord(ep.a, st);
         }
     }
     ~Bracket()
     {
         if (on) {
-            cudaEventRecord(ep.b, h->stream);
+            cudaEventRecord(ep.b, st);
             list->push_back(ep);
         }
     }
@@ -682,31 +686,33 @@ int64_t max_harmonic(const rsvdt_grid &g)
 // forcing slices s = 0..Sc-1 at half-step indices j_start + dir*s  (TSRK4.c:21-27, CreateForcingOnFly.c:17-19)
 // prev (optional): also produce the slice at j_start - dir (the forcing at t_n of the chunk's first step, i.e. the F3
 // carried over from the previous step, TSRK4.c:18 / TSActionRK4.c:103) into *prev
-int synth_forcing(rsvdt_handle h, const cplx *Fhat, cplx *slices, int Sc, int64_t j_start, int dir, cplx *prev)
+int synth_forcing(rsvdt_handle h, const cplx *Fhat, cplx *slices, int Sc, int64_t j_start, int dir, cplx *prev,
+                  cudaStream_t st = nullptr)
 {
     const rsvdt_grid &g = h->g;
     const int64_t U = h->n_ext * g.k;
-    Bracket br(h, &h->ev_idft);
+    if (!st) st = h->stream;
+    Bracket br(h, &h->ev_idft, st);
     const double PI = 3.14159265358979323846;
     const double hh = 0.5 * (double)Sc;
     const double x = (double)max_harmonic(g) * (PI / (double)g.Ns) * (hh + 1.0);   // |tau| <= 1 + 1/hh with the extra slice
     const int P = (h->idft_variant >= 10 || Sc < 4) ? -1 : idft_taylor_terms(x);
     if (P > 0 && P < Sc) {
         const int64_t J2 = 2 * j_start + (int64_t)dir * (Sc - 1);
-        CU(launch_idft_taylor_coef(h->coef.as<cplx>(), P, (int)g.Nw_eff, J2, dir, g.Ns, hh, g.RealOperator, h->stream));
-        CU(launch_idft_taylor(slices, U, h->coef.as<cplx>(), Fhat, U, Sc, P, (int)g.Nw_eff, U, prev, h->stream));
+        CU(launch_idft_taylor_coef(h->coef.as<cplx>(), P, (int)g.Nw_eff, J2, dir, g.Ns, hh, g.RealOperator, st));
+        CU(launch_idft_taylor(slices, U, h->coef.as<cplx>(), Fhat, U, Sc, P, (int)g.Nw_eff, U, prev, st));
     } else {
         if (prev) {
-            CU(launch_idft_coef(h->coef.as<cplx>(), 1, (int)g.Nw_eff, j_start - dir, 1, g.Ns, g.RealOperator, h->stream));
-            CU(launch_small_cgemm(prev, U, h->coef.as<cplx>(), Fhat, U, 1, (int)g.Nw_eff, U, 2, h->stream));
+            CU(launch_idft_coef(h->coef.as<cplx>(), 1, (int)g.Nw_eff, j_start - dir, 1, g.Ns, g.RealOperator, st));
+            CU(launch_small_cgemm(prev, U, h->coef.as<cplx>(), Fhat, U, 1, (int)g.Nw_eff, U, 2, st));
             h->launches += 2;
         }
         // direct contraction in tiles of at most 32 slices
         for (int s0 = 0; s0 < Sc; s0 += 32) {
             const int Sb = std::min(32, Sc - s0);
-            CU(launch_idft_coef(h->coef.as<cplx>() + (int64_t)s0 * g.Nw_eff, Sb, (int)g.Nw_eff, j_start + (int64_t)dir * s0, dir, g.Ns, g.RealOperator, h->stream));
+            CU(launch_idft_coef(h->coef.as<cplx>() + (int64_t)s0 * g.Nw_eff, Sb, (int)g.Nw_eff, j_start + (int64_t)dir * s0, dir, g.Ns, g.RealOperator, st));
             CU(launch_small_cgemm(slices + (int64_t)s0 * U, U, h->coef.as<cplx>() + (int64_t)s0 * g.Nw_eff, Fhat, U, Sb, (int)g.Nw_eff, U,
-                                  (int)(h->idft_variant % 10), h->stream));
+                                  (int)(h->idft_variant % 10), st));
             h->launches += 2;
         }
         h->launches -= 2;
@@ -765,6 +771,11 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
     // forcing at t_n of the first step of the chunk (F3 carried over, TSRK4.c:18); for the very first chunk it is the
     // initial forcing of TSActionRK4.c:103, produced together with the chunk's slices
     const cplx *f_carry = nullptr;
+    // Pipelining: the synthesis of chunk c+1 (HBM- and FP64-bound) runs on a low-priority stream while chunk c steps (the
+    // step kernel is bound by the shared-memory pipe and leaves HBM half idle).  It may start once step 0 of chunk c has
+    // read the carried slice that lives in the buffer it overwrites.
+    const bool pipe = h->use_pipeline && !small && U > 262144;
+    bool next_ready = false;
     for (int64_t i0 = i_begin; i0 <= i_end; i0 += Tc) {
         const int64_t nsteps = std::min(Tc, i_end - i0 + 1);
         const int Sc = (int)(2 * nsteps);
@@ -775,7 +786,9 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
             first_prev = h->slices[1].as<cplx>() + (int64_t)(S - 1) * U;   // a slot of the other buffer, free until chunk 2
             f_carry = first_prev;
         }
-        RS(synth_forcing(h, Fhat, sl, Sc, j_start, direct ? 1 : -1, first_prev));
+        if (next_ready) CU(cudaStreamWaitEvent(h->stream, h->ev_synth, 0));
+        else RS(synth_forcing(h, Fhat, sl, Sc, j_start, direct ? 1 : -1, first_prev));
+        next_ready = false;
         if (small) {   // the whole chunk in one launch of the persistent single-CTA kernel
             Bracket br(h, &h->ev_stage);
             SmallStepArgs sa;
@@ -843,6 +856,16 @@ int forced_steps(rsvdt_handle h, bool direct, const cplx *Fhat, cplx *y, cplx *s
                 if (slot >= 0) snap = snaps + slot * U;
             }
             RS(rk4_step_any(h, Op, nv, path, &ycur, &ynext, f_prev, f_half, f_next, snap));
+            if (c == 0 && pipe && i0 + Tc <= i_end) {
+                const int64_t i0n = i0 + Tc;
+                const int Scn = (int)(2 * std::min(Tc, i_end - i0n + 1));
+                const int64_t j_next = direct ? 2 * (i0n - 1) + 1 : -1 - 2 * (i0n - 1);
+                CU(cudaEventRecord(h->ev_step0, h->stream));
+                CU(cudaStreamWaitEvent(h->synth_stream, h->ev_step0, 0));
+                RS(synth_forcing(h, Fhat, h->slices[cur ^ 1].as<cplx>(), Scn, j_next, direct ? 1 : -1, nullptr, h->synth_stream));
+                CU(cudaEventRecord(h->ev_synth, h->synth_stream));
+                next_ready = true;
+            }
         }
         f_carry = sl + (int64_t)(Sc - 1) * U;
         cur ^= 1;
@@ -1183,9 +1206,19 @@ int rsvdt_create(int device, rsvdt_handle *hout)
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_step0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_synth, cudaEventDisableTiming) != cudaSuccess) {
         delete h;
         return RSVDT_ERR_CUDA;
+    }
+    {
+        int lo = 0, hi = 0;   // numerically lower = higher priority; the synthesis stream gets the lowest
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->synth_stream, cudaStreamNonBlocking, lo) != cudaSuccess) {
+            delete h;
+            return RSVDT_ERR_CUDA;
+        }
     }
     *hout = h;
     return RSVDT_OK;
@@ -1216,6 +1249,9 @@ int rsvdt_destroy(rsvdt_handle h)
             if (h->graphs[a][b].exec) cudaGraphExecDestroy(h->graphs[a][b].exec);
     cudaEventDestroy(h->ev_fork);
     cudaEventDestroy(h->ev_join);
+    cudaEventDestroy(h->ev_step0);
+    cudaEventDestroy(h->ev_synth);
+    cudaStreamDestroy(h->synth_stream);
     cudaStreamDestroy(h->side);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -1809,6 +1845,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "use_small")) h->use_small = value;
     else if (!strcmp(name, "use_graph")) h->use_graph = value;
     else if (!strcmp(name, "use_overlap")) h->use_overlap = value;
+    else if (!strcmp(name, "use_pipeline")) h->use_pipeline = value;
     else return fail(h, RSVDT_ERR_ARG, "unknown option '%s'", name);
     return RSVDT_OK;
 }

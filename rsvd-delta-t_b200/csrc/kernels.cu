@@ -601,7 +601,7 @@ DEVFN void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n"
 //   R*nv congruent to nv modulo the 8 16-byte slots of a shared-memory wavefront: conflict-free sliding-window accesses.
 // =====================================================================================================
 template <int LO, int HI, int R, int MINB, bool FORCED>
-__global__ void __launch_bounds__(MINB >= 3 ? 160 : 320) __maxnreg__(MINB >= 3 ? 112 : 96)
+__global__ void __launch_bounds__(MINB >= 4 ? 128 : (MINB == 3 ? 160 : 320)) __maxnreg__(MINB >= 4 ? 120 : (MINB == 3 ? 112 : 96))
 rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict__ tile_ok, int64_t N, int nv, int nq,
                    int TR, BandedStepArgs a)
 {
@@ -763,10 +763,10 @@ inline int tma_R(int nv)
 inline int tma_nq(int nv, int R, int nd, bool forced, int minb)
 {
     // shared memory per CTA = ((nbuf*nv + nd) * E0) * 16 + 16, E0 = R*nq; threads = nq*nv <= 160 (3 CTAs/SM) or 320 (2)
-    const int budget = (minb >= 3 ? 74 : 112) * 1024;
+    const int budget = (minb >= 4 ? 55 : (minb == 3 ? 74 : 112)) * 1024;
     const int per_row = ((forced ? 5 : 2) * nv + nd) * 16;
     int nq = (budget - 64) / (per_row * R);
-    const int tmax = (minb >= 3 ? 160 : 320) / nv;
+    const int tmax = (minb >= 4 ? 128 : (minb == 3 ? 160 : 320)) / nv;
     return nq < tmax ? nq : tmax;
 }
 
@@ -814,25 +814,26 @@ bool dia_tma_supported(int lo, int hi, int nv, int variant)
     const bool combo = (lo == 1 && hi == 1) || (lo == 2 && hi == 1) || (lo == 1 && hi == 2) || (lo == 2 && hi == 2);
     const int R = tma_R(nv);
     if (!combo || R == 0 || nv > 64) return false;
-    const int nq = tma_nq(nv, R, lo + hi + 1, true, variant == 1 ? 2 : 3);
+    const int nq = tma_nq(nv, R, lo + hi + 1, true, variant == 1 ? 2 : (variant == 2 ? 4 : 3));
     return nq >= 2 && 4 * (lo + hi) * 4 <= nq * R;
 }
 
 int dia_tma_tile_rows(int lo, int hi, int nv, int variant)
 {
     const int R = tma_R(nv);
-    return tma_nq(nv, R, lo + hi + 1, true, variant == 1 ? 2 : 3) * R - 4 * (lo + hi);
+    return tma_nq(nv, R, lo + hi + 1, true, variant == 1 ? 2 : (variant == 2 ? 4 : 3)) * R - 4 * (lo + hi);
 }
 
 cudaError_t launch_rk4_dia_tma_step(const cplx *dia, int lo, int hi, const unsigned char *tile_ok, int ntiles, int64_t N,
                                     int nv, int variant, const BandedStepArgs &a, cudaStream_t s)
 {
     const int R = tma_R(nv);
-    const int minb = variant == 1 ? 2 : 3;
+    const int minb = variant == 1 ? 2 : (variant == 2 ? 4 : 3);
     const int nq = tma_nq(nv, R, lo + hi + 1, true, minb);
 #define DISPATCH(L, H)                                                                                    \
     if (lo == L && hi == H)                                                                               \
         return minb == 2 ? dia_tma_dispatch_R<L, H, 2>(R, dia, tile_ok, ntiles, N, nv, nq, a, s)          \
+             : minb == 4 ? dia_tma_dispatch_R<L, H, 4>(R, dia, tile_ok, ntiles, N, nv, nq, a, s)          \
                          : dia_tma_dispatch_R<L, H, 3>(R, dia, tile_ok, ntiles, N, nv, nq, a, s);
     DISPATCH(1, 1)
     DISPATCH(2, 1)

@@ -492,3 +492,25 @@ def test_qr_ill_conditioned_block_falls_back_to_shifted_cholqr3(pkg, O):
     Qref = O.qr_all_freqs(N, k, Nw, Y)
     assert rel_err(Q[:, :k], Qref[:, :k]) < 1e-10       # well-conditioned blocks agree with Gram-Schmidt
     r.close()
+
+
+def test_pipelined_forcing_synthesis(pkg, O):
+    # block vectors above the launch-bound threshold: the forcing of chunk c+1 is synthesised on a low-priority stream
+    # while chunk c steps; the result must be bit-identical to the serial order and equal to the oracle
+    N, k, Nw = 30011, 10, 8
+    n, rp, ci, va = pkg.synthetic.ginzburg_landau(N)
+    A = O.Csr(N, N, rp, ci, va)
+    v = make_vars(O, pkg, N, k, Nw, 8.0, 0.003, 0.2)
+    F = _forcing(N, k * Nw, 61)
+    res = {}
+    for pipe in (1, 0):
+        r = _handle(pkg, A, v)
+        r.set_option("use_pipeline", pipe)
+        r.set_option("chunk_steps", 16)
+        r.keep_snapshots(True)
+        res[pipe] = (r.TSActionRK4(F, direct=True), r.TSActionRK4(F, direct=False), r.get_snapshots())
+        r.close()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert rel_err(res[1][0], _oracle_action(O, A, v, F, True)) < ACTION_TOL
+    assert rel_err(res[1][1], _oracle_action(O, A, v, F, False)) < ACTION_TOL
