@@ -27,6 +27,19 @@ DEVFN void cfma_conj(cplx &s, const cplx a, const cplx b)
 }
 DEVFN cplx cmul(const cplx a, const cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 DEVFN cplx ldg(const cplx *p) { return __ldg(p); }
+// read-once data (operator entries, forcing): do not allocate in L1, the gathered stage-vector rows live there
+DEVFN cplx ldg_stream(const cplx *p)
+{
+    cplx v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+DEVFN int32_t ldg_stream_i32(const int32_t *p)
+{
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
 // =====================================================================================================
 // K1: one RK4 stage = CSR SpMM over nv columns + forcing add + stage AXPYs   (TSRK4.c:18-47, TSTransRK4.c:15-36)
@@ -94,6 +107,13 @@ DEVFN cplx2 ldg2(const cplx *p)
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a.x), "=d"(v.a.y), "=d"(v.b.x), "=d"(v.b.y) : "l"(p));
     return v;
 }
+// streaming variant for the operator entries (read exactly once): keep them out of L1 so the gathered x rows stay there
+DEVFN cplx2 ldg2_stream(const cplx *p)
+{
+    cplx2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a.x), "=d"(v.a.y), "=d"(v.b.x), "=d"(v.b.y) : "l"(p));
+    return v;
+}
 DEVFN void st2(cplx *p, const cplx v0, const cplx v1)
 {
     cplx2 v;
@@ -121,7 +141,7 @@ rk4_stage_bcsr_kernel(const int64_t *__restrict__ browptr, const int32_t *__rest
         if (CV == 2) {
             cplx2 v;
             v.a = v.b = make_double2(0.0, 0.0);
-            if (HAS_F) v = ldg2(a.f + u0 + r * nv);
+            if (HAS_F) v = ldg2_stream(a.f + u0 + r * nv);
             s[r][0] = v.a;
             s[r][CV - 1] = v.b;
         } else {
@@ -141,7 +161,7 @@ rk4_stage_bcsr_kernel(const int64_t *__restrict__ browptr, const int32_t *__rest
         if (CV == 2) { const cplx2 v = ldg2(xb); xn[0] = v.a; xn[CV - 1] = v.b; } else { xn[0] = ldg(xb); }
 #pragma unroll
         for (int e = 0; e < B * B; e += 2) {
-            const cplx2 aa = ldg2(av + e);
+            const cplx2 aa = ldg2_stream(av + e);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int ee = e + h;
@@ -167,11 +187,11 @@ rk4_stage_bcsr_kernel(const int64_t *__restrict__ browptr, const int32_t *__rest
         if (CV == 2) {
             const cplx s0 = s[r][0], s1 = s[r][CV - 1];
             if (MODE == 0) {
-                const cplx2 y = ldg2(a.ybase + u);
+                const cplx2 y = ldg2_stream(a.ybase + u);
                 st2(a.xout + u, axpy1(a.cx, s0, y.a), axpy1(a.cx, s1, y.b));
                 st2(a.acc_out + u, axpy1(a.ca, s0, y.a), axpy1(a.ca, s1, y.b));
             } else if (MODE == 1) {
-                const cplx2 y = ldg2(a.ybase + u);
+                const cplx2 y = ldg2_stream(a.ybase + u);
                 const cplx2 ac = *reinterpret_cast<const cplx2 *>(a.acc_in + u);
                 st2(a.xout + u, axpy1(a.cx, s0, y.a), axpy1(a.cx, s1, y.b));
                 st2(a.acc_out + u, axpy1(a.ca, s0, ac.a), axpy1(a.ca, s1, ac.b));
