@@ -221,6 +221,52 @@ rk4_stage_bcsr_kernel(const int64_t *__restrict__ browptr, const int32_t *__rest
     }
 }
 
+// CSR stage with two test vectors per thread (nv even): one operator entry and one 256-bit gather feed two complex FMAs,
+// halving the load instructions per unit for operators with long rows and no block structure.
+template <int MODE, bool HAS_F>
+__global__ void __launch_bounds__(256)
+rk4_stage_csr2_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const cplx *__restrict__ val,
+                      int nv, int nvp, int64_t t_begin, int64_t n_threads, StageArgs a)
+{
+    const int64_t t = t_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_begin + n_threads) return;
+    const int64_t row = t / nvp;
+    const int iv0 = (int)(t - row * nvp) * 2;
+    const int64_t u = row * nv + iv0;
+    cplx s0 = make_double2(0.0, 0.0), s1 = s0;
+    if (HAS_F) { const cplx2 f = ldg2(a.f + u); s0 = f.a; s1 = f.b; }
+    int64_t p = __ldg(rowptr + row);
+    const int64_t p1 = __ldg(rowptr + row + 1);
+    const cplx *__restrict__ xin = a.xin + iv0;
+    for (; p + 2 <= p1; p += 2) {
+        const int32_t c0 = __ldg(col + p), c1 = __ldg(col + p + 1);
+        const cplx a0 = ldg(val + p), a1 = ldg(val + p + 1);
+        const cplx2 x0 = ldg2(xin + (int64_t)c0 * nv), x1 = ldg2(xin + (int64_t)c1 * nv);
+        cfma(s0, a0, x0.a); cfma(s1, a0, x0.b);
+        cfma(s0, a1, x1.a); cfma(s1, a1, x1.b);
+    }
+    if (p < p1) {
+        const cplx a0 = ldg(val + p);
+        const cplx2 x0 = ldg2(xin + (int64_t)__ldg(col + p) * nv);
+        cfma(s0, a0, x0.a); cfma(s1, a0, x0.b);
+    }
+    if (MODE == 0) {
+        const cplx2 y = ldg2(a.ybase + u);
+        st2(a.xout + u, axpy1(a.cx, s0, y.a), axpy1(a.cx, s1, y.b));
+        st2(a.acc_out + u, axpy1(a.ca, s0, y.a), axpy1(a.ca, s1, y.b));
+    } else if (MODE == 1) {
+        const cplx2 y = ldg2(a.ybase + u);
+        const cplx2 ac = *reinterpret_cast<const cplx2 *>(a.acc_in + u);
+        st2(a.xout + u, axpy1(a.cx, s0, y.a), axpy1(a.cx, s1, y.b));
+        st2(a.acc_out + u, axpy1(a.ca, s0, ac.a), axpy1(a.ca, s1, ac.b));
+    } else {
+        const cplx2 ac = *reinterpret_cast<const cplx2 *>(a.acc_in + u);
+        const cplx y0 = axpy1(a.ca, s0, ac.a), y1 = axpy1(a.ca, s1, ac.b);
+        st2(a.acc_out + u, y0, y1);
+        if (a.snap) st2(a.snap + u, y0, y1);
+    }
+}
+
 template <int B, int CV>
 static cudaError_t bcsr_launch(const BcsrDev &Op, int nv, int mode, const StageArgs &a, cudaStream_t s, int64_t br_begin,
                                int64_t br_count)
@@ -264,8 +310,19 @@ cudaError_t launch_rk4_stage(const CsrDev &Op, int nv, int mode, const StageArgs
     const int64_t n_units = row_count * (int64_t)nv, u_begin = row_begin * (int64_t)nv;
     if (n_units <= 0) return cudaSuccess;
     const int threads = 256;
-    const int64_t blocks = (n_units + threads - 1) / threads;
     const bool hf = a.f != nullptr;
+    if (variant != 1 && nv % 2 == 0 && Op.max_row_nnz >= 8) {   // long rows: two test vectors per thread, 256-bit gathers
+        const int nvp = nv / 2;
+        const int64_t n_thr = row_count * nvp, t_begin = row_begin * nvp;
+        const int64_t blk2 = (n_thr + threads - 1) / threads;
+#define LAUNCH2(M, F) rk4_stage_csr2_kernel<M, F><<<(unsigned)blk2, threads, 0, s>>>(Op.rowptr, Op.col, Op.val, nv, nvp, t_begin, n_thr, a)
+        if (mode == 0) { if (hf) LAUNCH2(0, true); else LAUNCH2(0, false); }
+        else if (mode == 1) { if (hf) LAUNCH2(1, true); else LAUNCH2(1, false); }
+        else { if (hf) LAUNCH2(2, true); else LAUNCH2(2, false); }
+#undef LAUNCH2
+        return cudaGetLastError();
+    }
+    const int64_t blocks = (n_units + threads - 1) / threads;
 #define LAUNCH(M, F) rk4_stage_csr_kernel<M, F><<<(unsigned)blocks, threads, 0, s>>>(Op.rowptr, Op.col, Op.val, nv, u_begin, n_units, a)
     if (mode == 0) { if (hf) LAUNCH(0, true); else LAUNCH(0, false); }
     else if (mode == 1) { if (hf) LAUNCH(1, true); else LAUNCH(1, false); }

@@ -77,6 +77,8 @@ def test_action_faithful_twiddles_within_reference_tolerance(pkg, O, A_GL):
                                                       ((4, 5, 6), True, 5, 4, {}), ((9, 11), True, 5, 3, {}),
                                                       ((9, 11), True, 5, 4, dict(use_bcsr=0)),
                                                       ((9, 11), True, 5, 4, dict(stage_variant=1)),
+                                                      ((9, 11), True, 5, 4, dict(use_bcsr=0, stage_variant=1)),
+                                                      ((9, 11), True, 5, 3, dict(use_bcsr=0)),
                                                       ((6, 7), True, 4, 6, {}), ((5, 6), True, 3, 2, {})])
 def test_action_lns_stencil(pkg, O, shape, cplx, nvar, k, opts):
     # block-stencil operators: the block-CSR stage kernel (B = 5, 4, 3; one or two test vectors per thread) and the
