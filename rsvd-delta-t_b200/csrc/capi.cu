@@ -135,7 +135,8 @@ struct rsvdt_context {
         int64_t nsteps = 0, launches = 0;
     } graphs[2][2];
     int64_t use_graph = 1;
-    int64_t use_overlap = 1;  // row-partitioned runs: hide the halo exchange behind the interior rows
+    int64_t use_overlap = 0;  // row-partitioned runs: hide the halo exchange behind the interior rows (measured: the three
+                              // launches per stage cost more than the exchange they hide at plane-sized halos; off by default)
     int64_t use_pipeline = 0; // (measured: no gain, the two kernels compete for SM residency) synthesise the next chunk's forcing on a low-priority stream while the current chunk steps
 
     // instrumentation

@@ -27,6 +27,7 @@ ap.add_argument("--k", type=int, default=8)
 ap.add_argument("--Nw", type=int, default=32)
 ap.add_argument("--steps", type=int, default=16)
 ap.add_argument("--passes", type=int, default=2)
+ap.add_argument("--option", action="append", default=[])
 ap.add_argument("--no-adjoint", action="store_true", help="do not build A^H (direct-only timing, halves the setup memory)")
 args = ap.parse_args()
 
@@ -64,6 +65,9 @@ else:
     r, plan = pkg.dist.setup_rank(pkg, lrank, N, gen_rows, bw, 0, None, grid, with_adjoint=not args.no_adjoint)
     n_own = plan.n_own
     nnz_own = None
+for opt in args.option:
+    name, value = opt.split("=")
+    r.set_option(name, int(value))
 setup_s = time.time() - t0
 rng = np.random.default_rng(14 + rank)
 F = np.empty((n_own, args.k * args.Nw), np.complex128, order="F")

@@ -26,10 +26,12 @@ def gather_rows(local, plan_ranges, world):
     return np.concatenate(parts, axis=0)
 
 
-def run_case(pkg, name, N, gen_rows, full_csr, max_bw, layout, band, k, Nw, w, dt_in, TL, rank, world, dev, TR=False):
+def run_case(pkg, name, N, gen_rows, full_csr, max_bw, layout, band, k, Nw, w, dt_in, TL, rank, world, dev, TR=False, options=None):
     dt, Ns, Nt, RR = pkg.capi.setup_time_freq_grid(w, Nw, dt_in, TL)
     grid = dict(k=k, Nw=Nw, Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=w, TransientRemoval=TR)
     r, plan = pkg.dist.setup_rank(pkg, dev, N, gen_rows, max_bw, layout, band, grid)
+    for oname, oval in (options or {}).items():
+        r.set_option(oname, oval)
     Nw_eff = r.grid.Nw_eff
     rng = np.random.default_rng(21)
     F = np.asfortranarray(rng.random((N, k * Nw_eff)) + 1j * rng.random((N, k * Nw_eff)))
@@ -103,6 +105,7 @@ def main():
         return rpp[a - a5: b - a5 + 1] - s, cc[s:e], vv[s:e]
 
     ok &= run_case(pkg, "lns-2d", NL, lns, fullL, 5 * (20 + 2), 0, None, 4, 4, 3.0, 0.003, 0.3, rank, world, lrank)
+    ok &= run_case(pkg, "lns-2d overlap", NL, lns, fullL, 5 * (20 + 2), 0, None, 4, 4, 3.0, 0.003, 0.3, rank, world, lrank, options={"use_overlap": 1})
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
