@@ -13,8 +13,10 @@ Contract (see the task statement): `python bench.py --gpus N --steps K --warmup 
   roofline    dominant kernel = the RK4 stage kernel; achieved = algorithmic bytes per launch divided by
               its average launch duration measured with CUDA events inside the timed region.
   cpu_baseline / --impl reference
-              the CPU oracle (a PETSc-free restatement of the reference's operation sequence; the reference itself
-              needs PETSc/SLEPc/MPI and cannot be built here) timed on the host cores on a bounded sample.
+              the reference's own RK4 step (SourceCode/TSRK4.c + CreateForcingOnFly.c, compiled unmodified into
+              oracle/_ref/ against the one-rank PETSc API shim oracle/petsc_shim/, whose primitives are threaded with
+              OpenMP in place of MPI ranks) timed on the host cores on a bounded sample: kind "reference".  If
+              oracle/_ref/ is absent, the oracle port (oracle/rsvdt_oracle.c) is timed instead: kind "port".
 """
 from __future__ import annotations
 
@@ -124,14 +126,53 @@ class CpuPort:
         self.F = pkg.synthetic.random_forcing(N, ncols, c["Nw"], seed=14)
         O.time_forced_steps(self.A, self.v, self.idft, self.F, 1, 1)  # warm-up (page faults, thread pool)
 
+    kind = "port"
+    what = "oracle port rsvdt_oracle.c (TSActionRK4.c:116-122 one vector at a time)"
+
     def sample(self, nsteps):
         secs = self.O.time_forced_steps(self.A, self.v, self.idft, self.F, self.ncols, nsteps)
         return self.N * self.ncols * nsteps / secs, secs, self.O.num_threads()
 
 
+class CpuReference:
+    """the reference's own TSRK4.c / CreateForcingOnFly.c (oracle/_ref/librsvdt_ref.so: reference sources on the PETSc API
+    shim, OpenMP threads in place of MPI ranks) on the bench workload, one test vector at a time as TSActionRK4.c runs"""
+
+    kind = "reference"
+    what = ("reference sources TSRK4.c + CreateForcingOnFly.c compiled unmodified against the PETSc API shim "
+            "(oracle/_ref, OpenMP threads in place of MPI ranks)")
+
+    def __init__(self, pkg, N, rowptr, col, val, dt, Ns, Nt, RR, ncols):
+        if "LOCAL_RANK" in os.environ or "OMP_NUM_THREADS" not in os.environ:
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        from oracle import oracle as O
+        from oracle import ref as R
+        c = WORKLOAD
+        self.R, self.N, self.ncols = R, N, ncols
+        self.A = O.Csr(N, N, rowptr, col, val)
+        self.v = O.Vars(N=N, k=ncols, Nw=c["Nw"], Nw_eff=c["Nw"], Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=c["w"])
+        self.F = pkg.synthetic.random_forcing(N, 1, c["Nw"], seed=14)
+        R.time_forced_steps(self.A, self.v, self.F, 1, 0, 1)  # warm-up (page faults, thread pool)
+
+    def sample(self, nsteps):
+        secs = self.R.time_forced_steps(self.A, self.v, self.F, self.ncols, 1, nsteps)
+        return self.N * self.ncols * nsteps / secs, secs, self.R.num_threads()
+
+
+def cpu_arm(pkg, *a):
+    """oracle/_ref (the reference's own code) when it was built, else the oracle port"""
+    try:
+        from oracle import ref as R
+        if R.available():
+            return CpuReference(pkg, *a)
+    except Exception as e:  # a stale or foreign-CPU binary: fall back to the port, say so
+        print(f"bench: oracle/_ref not usable ({e}); timing the oracle port", file=sys.stderr)
+    return CpuPort(pkg, *a)
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port, all host threads.
-    (The reference itself needs PETSc/SLEPc/MPI and cannot be built here)"""
+    """--impl reference: the reference's CPU implementation of the path on all host threads: oracle/_ref (the reference's
+    own sources on the PETSc API shim) when built, else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -139,7 +180,7 @@ def run_reference(args):
     entry.build()
     N, rowptr, col, val, dt, Ns, Nt, RR = build_workload(pkg)
     ncols, nsteps = 1, 8
-    port = CpuPort(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, ncols)
+    port = cpu_arm(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, ncols)
     for _ in range(max(args.warmup, 0)):
         port.sample(1)
     vals, tot_s, cores = [], 0.0, 1
@@ -148,13 +189,13 @@ def run_reference(args):
         vals.append(v)
         tot_s += secs
     value = float(N * ncols * nsteps * len(vals) / tot_s) if tot_s > 0 else 0.0
-    sample = (f"{ncols} test vector x {nsteps} forced RK4 steps of the N=1e6 workload per bench step "
-              f"(TSActionRK4.c:116-122 one vector at a time), {cores} OpenMP threads")
+    sample = (f"{ncols} test vector x {nsteps} forced RK4 steps of the N=1e6 workload per bench step, {cores} OpenMP threads; "
+              f"{port.what}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
             "config": {k: WORKLOAD[k] for k in ("workload", "N", "k", "Nw", "w")},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": port.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -307,9 +348,10 @@ def main():
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) -------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, secs, cores = CpuPort(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, 1).sample(400)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 test vector x 400 forced RK4 steps of the same N=1e6 workload ({secs:.1f} s of CPU work)"}
+        arm = cpu_arm(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, 1)
+        v, secs, cores = arm.sample(100)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": arm.kind,
+               "sample": f"1 test vector x 100 forced RK4 steps of the same N=1e6 workload ({secs:.1f} s of CPU work); {arm.what}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -179,9 +179,11 @@ def time_forced_steps(A: Csr, v: Vars, F_hat_k, ncols, warm, nsteps):
     return sec.value
 
 
-def run_executable(workdir, yaml_name="variables.yaml", timeout=3600, threads=None):
-    """`RSVDt_ref -inputs variables.yaml` in workdir (README.md:221) -> CompletedProcess"""
+def run_executable(workdir, yaml_name="variables.yaml", timeout=3600, threads=None, autoinit=False):
+    """`RSVDt_ref -inputs variables.yaml` in workdir (README.md:221) -> CompletedProcess.
+    autoinit=True runs the build with -ftrivial-auto-var-init=pattern (see Makefile.ref: main.c never initialises
+    RSVDt.TS.DirAdj on the TransRun path, so which of A / A^H the transient run integrates is undefined behaviour)."""
     env = dict(os.environ)
     if threads is not None:
         env["OMP_NUM_THREADS"] = str(threads)
-    return subprocess.run([EXE_PATH, "-inputs", yaml_name], cwd=workdir, capture_output=True, text=True, timeout=timeout, env=env)
+    return subprocess.run([EXE_PATH + ("_autoinit" if autoinit else ""), "-inputs", yaml_name], cwd=workdir, capture_output=True, text=True, timeout=timeout, env=env)

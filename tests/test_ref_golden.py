@@ -1,0 +1,434 @@
+"""Parity against OUTPUTS OF THE REFERENCE'S OWN CODE.
+
+tests/golden/ref_*.npz were produced by tests/golden/make_ref_golden.py from oracle/_ref/: the reference's SourceCode/*.c
+compiled unmodified against the PETSc/SLEPc API shim (oracle/petsc_shim/), run as the executable
+`RSVDt_ref -inputs variables.yaml` and function by function.  The CPU tests pin the oracle restatement
+(oracle/rsvdt_oracle.c) to those outputs; the `gpu` tests compare the CUDA path -- through the C ABI and through the host
+driver `RSVDt`, the drop-in for the reference executable -- with the same committed outputs (no oracle call, and nothing
+under /root/reference is read at test time).
+
+Tolerances: the oracle in its "faithful" mode (the reference's un-reduced exp() twiddle tables, CreateDFTiDFTMats.c:52-53)
+must agree to rounding (1e-12); with exactly reduced twiddles -- what the CUDA path uses -- actions agree to 1e-9, gains
+to 1e-8 and mode subspaces to a principal angle of 1e-6 (BASELINE.json north_star)."""
+import hashlib
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, principal_angle, rel_err
+from ref_cases import SMALL_YAML, TUTORIAL_YAML, csr_of, real_operator, weight_mats, write_case_files
+
+EXE = os.path.join(ROOT, "rsvd-delta-t_b200", "RSVDt")
+ROUND = 1e-12        # oracle (faithful twiddles) vs reference code
+ACTION_TOL = 1e-9    # exact-twiddle implementations vs reference code
+GAIN_TOL = 1e-8
+ANGLE_TOL = 1e-6
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def _vars(O, g, key="grid", **kw):
+    dt, Ns, Nt, RR = g[key]
+    return O.Vars(dt=float(dt), Ns=int(Ns), Nt=int(Nt), ResRatio=int(RR), **kw)
+
+
+def _phase_aligned_err(U, Uref):
+    """max over columns of || u e^{i phi} - uref || (singular vectors are defined up to a unit phase)"""
+    worst = 0.0
+    for c in range(Uref.shape[1]):
+        ip = np.vdot(U[:, c], Uref[:, c])
+        worst = max(worst, float(np.linalg.norm(U[:, c] * ip / abs(ip) - Uref[:, c])))
+    return worst
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ====================================================================================================== CPU: the oracle
+def test_oracle_grid_and_twiddles_match_reference(O):
+    g = _load("ref_gl_functions.npz")
+    k, Nw, w = int(g["k"]), int(g["Nw"]), float(g["w"])
+    assert np.array_equal(O.setup_time_freq_grid(w, Nw, float(g["dt_in"]), float(g["TransientLength"])), g["grid"])
+    Ns = int(g["grid"][1])
+    dft, idft = O.create_dft_idft_mats(Nw, Nw, Ns, False, True)
+    assert np.array_equal(dft, g["dft"])                                # bit-identical tables
+    assert np.array_equal(idft[:, ::997], g["idft_cols"]) and _sha(idft) == str(g["idft_sha256"])
+    dft, idft = O.create_dft_idft_mats(Nw, Nw, Ns, False, False)        # exactly reduced phases
+    assert np.abs(dft - g["dft"]).max() < 1e-14 and np.abs(idft[:, ::997] - g["idft_cols"]).max() < 1e-13
+    # the shipped tutorial's grid: the reference code itself gives these numbers
+    assert O.setup_time_freq_grid(0.05, 42, 0.003, 10.0)[1:] == (41916, 3336, 998)
+
+
+@pytest.mark.parametrize("TR", [False, True])
+@pytest.mark.parametrize("direct", [True, False])
+def test_oracle_action_matches_reference(O, A_GL, TR, direct):
+    g = _load("ref_gl_functions.npz")
+    k, Nw = int(g["k"]), int(g["Nw"])
+    A = A_GL.shifted(float(g["beta"]))
+    v = _vars(O, g, N=500, k=k, Nw=Nw, Nw_eff=Nw, w=float(g["w"]), TransientRemoval=TR, DirAdj=direct)
+    ref = g[f"Y_{'direct' if direct else 'adjoint'}_{'tr' if TR else 'notr'}"]
+    Op = A if direct else A.hermitian_transpose()
+    dft, idft = O.create_dft_idft_mats(Nw, Nw, v.Ns, False, True)
+    assert rel_err(O.ts_action_rk4(Op, v, dft, idft, g["F_hat"]), ref) < ROUND
+    dft, idft = O.create_dft_idft_mats(Nw, Nw, v.Ns, False, False)
+    assert rel_err(O.ts_action_rk4(Op, v, dft, idft, g["F_hat"]), ref) < ACTION_TOL
+
+
+def test_oracle_dense_phases_match_reference(O, A_GL):
+    g = _load("ref_gl_functions.npz")
+    k, Nw = int(g["k"]), int(g["Nw"])
+    A = A_GL.shifted(float(g["beta"]))
+    Y = g["Y_direct_notr"]
+    assert rel_err(O.qr_all_freqs(500, k, Nw, Y), g["Q"]) < ROUND                       # QRAllFreqs.c
+    U, S = O.svd_all_freqs(500, k, Nw, Y)                                                # SVDAllFreqs.c
+    assert np.abs(S / g["S_svd"] - 1).max() < ROUND and _phase_aligned_err(U, g["U_svd"]) < 1e-10
+    v = _vars(O, g, N=500, k=k, Nw=Nw, Nw_eff=Nw, w=float(g["w"]))
+    assert rel_err(O.ts_exp_a_deltat(A, v, g["F_hat"][:, :4]), g["expAdT"]) < ROUND     # TSExpADeltaT.c
+    q, _, steps, _ = O.transient_run_rk4(A, v.dt, 300, 300, 1e30, 0.0, g["F_hat"][:, 0])  # TSTransRK4.c x 300
+    assert steps == 300 and rel_err(q, g["q_trans_300"]) < ROUND
+
+
+@pytest.mark.parametrize("TR", [False, True])
+def test_oracle_real_operator_matches_reference(O, A_GL, TR):
+    # real-valued A: Nw_eff = Nw/2 and different twiddle tables (LNSStructure.c:40-44, CreateDFTiDFTMats.c:35-36,61)
+    g = _load("ref_gl_functions.npz")
+    Ar = real_operator(O, A_GL)
+    for direct in (True, False):
+        v = _vars(O, g, "real_grid", N=500, k=2, Nw=8, Nw_eff=4, w=0.8, RealOperator=True, TransientRemoval=TR, DirAdj=direct)
+        dft, idft = O.create_dft_idft_mats(8, 4, v.Ns, True, True)
+        got = O.ts_action_rk4(Ar if direct else Ar.hermitian_transpose(), v, dft, idft, g["real_F_hat"])
+        assert rel_err(got, g[f"real_Y_{'direct' if direct else 'adjoint'}_{'tr' if TR else 'notr'}"]) < ROUND
+
+
+@pytest.mark.parametrize("k,Nw", [(1, 2), (2, 5)])
+def test_oracle_edge_shapes_match_reference(O, A_GL, k, Nw):
+    g = _load("ref_gl_functions.npz")
+    A = A_GL.shifted(float(g["beta"]))
+    v = _vars(O, g, f"edge_{k}_{Nw}_grid", N=500, k=k, Nw=Nw, Nw_eff=Nw, w=1.1)
+    dft, idft = O.create_dft_idft_mats(Nw, Nw, v.Ns, False, True)
+    assert rel_err(O.ts_action_rk4(A, v, dft, idft, g[f"edge_{k}_{Nw}_F"]), g[f"edge_{k}_{Nw}_Y"]) < ROUND
+
+
+def test_oracle_weighted_actions_match_reference(O, A_GL):
+    # DirectActionRK4.c / AdjointActionRK4.c with ApplyWeightMats.c on both sides, B: N x Nb, C: Nc x N, Nb, Nc < N
+    g = _load("ref_gl_weighted.npz")
+    k, Nw = int(g["k"]), int(g["Nw"])
+    mats, shapes = weight_mats(500)
+    Oc = {n: csr_of(O, shapes[n], mats[n]) for n in mats}
+    v = _vars(O, g, N=500, k=k, Nw=Nw, Nw_eff=Nw, w=float(g["w"]))
+    dft, idft = O.create_dft_idft_mats(Nw, Nw, v.Ns, False, True)
+    X = O.mat_mat_mult(Oc["B"], O.mat_mat_mult(Oc["W_f_sqrt_inv"], g["F"]))
+    Y = O.ts_action_rk4(A_GL, v, dft, idft, X)
+    assert rel_err(O.mat_mat_mult(Oc["W_q_sqrt"], O.mat_mat_mult(Oc["C"], Y)), g["Y_direct"]) < ROUND
+    X = O.mat_mat_mult(Oc["C"], O.mat_mat_mult(Oc["W_q_sqrt"], g["G"], True), True)
+    va = O.Vars(**{**v.__dict__, "DirAdj": False})
+    Y = O.ts_action_rk4(A_GL.hermitian_transpose(), va, dft, idft, X)
+    assert rel_err(O.mat_mat_mult(Oc["W_f_sqrt_inv"], O.mat_mat_mult(Oc["B"], Y, True), True), g["Y_adjoint"]) < ROUND
+
+
+@pytest.mark.parametrize("tag,opt", [("tr", 1), ("notr", 2)])
+def test_oracle_full_solve_matches_reference_executable(O, pkg, A_GL, tag, opt):
+    # what `RSVDt_ref -inputs variables.yaml` wrote (S_hat, U_hat_*, V_hat_*) vs the oracle's main.c sequence
+    g = _load("ref_gl_executable.npz")
+    k, Nw, w = 3, 8, 0.6
+    F = pkg.synthetic.random_forcing(500, k, Nw, seed=3)
+    assert _sha(F) == str(g["small_F_sha256"])
+    dt, Ns, Nt, RR = O.setup_time_freq_grid(w, Nw, 0.003, 1.0)
+    v = O.Vars(N=500, k=k, Nw=Nw, Nw_eff=Nw, Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=w, TransientRemoval=(tag == "tr"))
+    S, U, V = O.full_solve(A_GL.shifted(0.3), v, 1, F, faithful_twiddles=True)
+    Sg, Ug, Vg = g[f"small_S_{tag}"], g[f"small_U_{tag}"], g[f"small_V_{tag}"]      # U: [N, Nw, k]
+    assert np.abs(Sg.imag).max() == 0 and np.abs(S / Sg.real - 1).max() < 1e-11
+    for iw in range(Nw):
+        for j in range(k):
+            assert principal_angle(Ug[:, iw, j:j + 1], U[:, iw * k + j:iw * k + j + 1]) <= ANGLE_TOL
+            assert principal_angle(Vg[:, iw, j:j + 1], V[:, iw * k + j:iw * k + j + 1]) <= ANGLE_TOL
+    files = set(str(f) for f in g[f"small_files_{tag}"])
+    want = {"S_hat", "variables.yaml"} | ({f"{m}_hat_k{j + 1}_allFreqs" for m in "UV" for j in range(k)} if opt == 1 else
+                                          {f"{m}_hat_Freq{iw}_allK" for m in "UV" for iw in range(Nw)})
+    assert files == want                                                             # SaveResults.c:32-84
+
+
+def test_oracle_transient_run_matches_reference_executable(O, A_GL):
+    # TransientRunRK4.c through the executable.  main.c never sets RSVDt.TS.DirAdj on this path (an uninitialised stack
+    # variable TSTransRK4.c:15 branches on): the fixture holds the run with the flag reading true (direct, A) and the
+    # plain build's run, whose stack held zero (A^H).  The oracle reproduces both; the drop-in integrates A.
+    g = _load("ref_gl_executable.npz")
+    dt, Ns, Nt, RR = O.setup_time_freq_grid(0.6, 8, 0.003, 1.0)
+    A = A_GL.shifted(0.3)
+    for tag, Op in (("", A), ("plain_", A.hermitian_transpose())):
+        q, norms, steps, reason = O.transient_run_rk4(Op, dt, Ns, 400, 1e3, 1e-12, g["trans_q0"])
+        assert g[f"trans_{tag}norms"].size == Ns // 400 + 1 and np.allclose(norms, g[f"trans_{tag}norms"], rtol=1e-12)
+        assert rel_err(q, g[f"trans_{tag}last"]) < ROUND
+        q2, _, _, _ = O.transient_run_rk4(Op, dt, 800, 400, 1e3, 1e-12, g["trans_q0"])
+        assert rel_err(q2, g[f"trans_{tag}q2"]) < ROUND
+    assert abs(g["trans_norms"][1] / g["trans_plain_norms"][1] - 1) > 0.01      # the two runs really differ
+
+
+def test_reference_tutorial_output_is_consistent_with_exact_resolvent(pkg, A_GL):
+    # The shipped tutorial (variables.yaml as shipped) through the reference executable: its gains against a dense SVD of
+    # the exact resolvent of A_GL.  RSVD with k = 10, q = 1 recovers the leading gain to ~1e-3 around the peak.
+    g = _load("ref_gl_tutorial.npz")
+    S = g["S_hat"].real
+    assert S.shape == (10, 42) and np.abs(g["S_hat"].imag).max() == 0
+    assert (np.diff(S, axis=0) <= 0).all()                      # sorted gains per frequency
+    A = A_GL.to_dense()
+    for iw in (0, 5, 42 - 13, 41):
+        m = iw if iw <= 20 else iw - 42                          # FFT ordering of the frequency slots
+        exact = np.linalg.svd(np.linalg.inv(1j * m * 0.05 * np.eye(500) - A), compute_uv=False)[0]
+        assert S[0, iw] == pytest.approx(exact, rel=5e-3)
+    assert S[0, 42 - 13] == pytest.approx(1672.0219, rel=2e-3)   # the tutorial's peak
+
+
+@pytest.mark.skipif(not os.environ.get("RSVDT_SLOW"), reason="about 2 minutes of oracle time; set RSVDT_SLOW=1")
+def test_oracle_tutorial_matches_reference_executable(O, pkg, A_GL):
+    g = _load("ref_gl_tutorial.npz")
+    k, Nw = 10, 42
+    F = pkg.synthetic.random_forcing(500, k, Nw, seed=14)
+    assert _sha(F) == str(g["F_sha256"])
+    dt, Ns, Nt, RR = O.setup_time_freq_grid(0.05, Nw, 0.003, 10.0)
+    v = O.Vars(N=500, k=k, Nw=Nw, Nw_eff=Nw, Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=0.05, TransientRemoval=True)
+    S, U, V = O.full_solve(A_GL, v, 1, F, faithful_twiddles=True)
+    assert np.abs(S[0] / g["S_hat"].real[0] - 1).max() < GAIN_TOL
+    for iw in range(Nw):
+        assert principal_angle(g["U_lead"][:, iw:iw + 1], U[:, iw * k:iw * k + 1]) <= ANGLE_TOL
+        assert principal_angle(g["V_lead"][:, iw:iw + 1], V[:, iw * k:iw * k + 1]) <= ANGLE_TOL
+
+
+# ========================================================================= CPU, live: oracle vs reference code if built
+def _ref():
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return R
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_live_oracle_vs_reference_code_on_lns_stencil(O, pkg, seed):
+    # an operator the fixtures do not cover: 2-D block stencil (5 variables x 9 points), TR on and off, both directions
+    R = _ref()
+    n, rowptr, col, val = pkg.synthetic.lns_stencil((6, 5), nvar=5, complex_coupling=True, seed=seed)
+    A = O.Csr(n, n, rowptr, col, val)
+    k, Nw, w = 2, 4, 2.0
+    assert O.setup_time_freq_grid(w, Nw, 0.01, 0.4) == R.setup_time_freq_grid(w, Nw, 0.01, 0.4)
+    dt, Ns, Nt, RR = O.setup_time_freq_grid(w, Nw, 0.01, 0.4)
+    F = pkg.synthetic.random_forcing(n, k, Nw, seed=seed + 10)
+    for TR in (False, True):
+        for direct in (True, False):
+            v = O.Vars(N=n, k=k, Nw=Nw, Nw_eff=Nw, Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=w, TransientRemoval=TR, DirAdj=direct)
+            dft, idft = O.create_dft_idft_mats(Nw, Nw, Ns, False, True)
+            got = O.ts_action_rk4(A if direct else A.hermitian_transpose(), v, dft, idft, F)
+            assert rel_err(got, R.ts_action_rk4(A, v, F)) < (1e-9 if TR else ROUND)
+    Y = pkg.synthetic.random_forcing(n, 3, 5, seed=seed + 20)
+    assert rel_err(O.qr_all_freqs(n, 3, 5, Y), R.qr_all_freqs(n, 3, 5, Y)) < ROUND
+    assert np.allclose(O.svd_all_freqs(n, 3, 5, Y)[1], R.svd_all_freqs(n, 3, 5, Y)[1], rtol=1e-12)
+    P = R.permute_mat(Y, 3)                                     # PermuteMat.c: col iw*k+ik -> ik*Nw+iw
+    assert np.array_equal(P, Y.reshape(n, 3, 5, order="F").transpose(0, 2, 1).reshape(n, 15, order="F"))
+    assert np.array_equal(R.permute_mat(P, 3, reverse=True), Y)
+
+
+# ========================================================================================================= GPU: CUDA path
+gpu = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests (there is no CPU fallback)")
+
+
+def _handle(pkg, A, v, DiscFlg=False, beta=0.0):
+    r = pkg.capi.RSVDt(0)
+    real = r.LNSStructure(A.nrows, A.rowptr, A.col, A.val, DiscFlg, beta)
+    assert real == v.RealOperator
+    r.set_grid(v.k, v.Nw, v.Ns, v.Nt, v.ResRatio, v.dt, v.w, v.TransientRemoval)
+    return r
+
+
+@gpu
+@pytest.mark.parametrize("TR", [False, True])
+def test_cuda_actions_match_reference_code(pkg, O, A_GL, TR):
+    _need_gpu()
+    g = _load("ref_gl_functions.npz")
+    k, Nw, w = int(g["k"]), int(g["Nw"]), float(g["w"])
+    assert np.array_equal(pkg.capi.setup_time_freq_grid(w, Nw, float(g["dt_in"]), float(g["TransientLength"])), g["grid"])
+    v = _vars(O, g, N=500, k=k, Nw=Nw, Nw_eff=Nw, w=w, TransientRemoval=TR)
+    tag = "tr" if TR else "notr"
+    for small in (0, 2):                      # tiled kernels / the single-CTA latency path
+        r = _handle(pkg, A_GL, v, True, float(g["beta"]))
+        r.set_option("use_small", small)
+        assert rel_err(r.TSActionRK4(g["F_hat"], direct=True), g[f"Y_direct_{tag}"]) < ACTION_TOL
+        assert rel_err(r.TSActionRK4(g["F_hat"], direct=False), g[f"Y_adjoint_{tag}"]) < ACTION_TOL
+        r.close()
+
+
+@gpu
+def test_cuda_dense_phases_match_reference_code(pkg, O, A_GL):
+    _need_gpu()
+    g = _load("ref_gl_functions.npz")
+    k, Nw = int(g["k"]), int(g["Nw"])
+    v = _vars(O, g, N=500, k=k, Nw=Nw, Nw_eff=Nw, w=float(g["w"]))
+    r = _handle(pkg, A_GL, v, True, float(g["beta"]))
+    r.set_Y_hat(g["Y_direct_notr"])
+    r.QRAllFreqs()
+    assert rel_err(r.get_Y_hat(), g["Q"]) < 1e-10
+    r.set_Y_hat(g["Y_direct_notr"])
+    r.SVDAllFreqs()
+    assert np.abs(r.get_S_hat() / g["S_svd"] - 1).max() < 1e-10
+    assert _phase_aligned_err(r.get_V_hat(), g["U_svd"]) < 1e-8
+    assert rel_err(r.TSExpADeltaT(g["F_hat"][:, :4]), g["expAdT"]) < 1e-11
+    q, norms, steps, reason = r.TransientRunRK4(g["F_hat"][:, 0].copy(), 300, 300, 1e30, 0.0)
+    assert rel_err(q, g["q_trans_300"]) < 1e-11
+    r.close()
+
+
+@gpu
+def test_cuda_real_operator_and_edge_shapes_match_reference_code(pkg, O, A_GL):
+    _need_gpu()
+    g = _load("ref_gl_functions.npz")
+    Ar = real_operator(O, A_GL)
+    for TR in (False, True):
+        v = _vars(O, g, "real_grid", N=500, k=2, Nw=8, Nw_eff=4, w=0.8, RealOperator=True, TransientRemoval=TR)
+        r = _handle(pkg, Ar, v)
+        tag = "tr" if TR else "notr"
+        assert rel_err(r.TSActionRK4(g["real_F_hat"], direct=True), g[f"real_Y_direct_{tag}"]) < ACTION_TOL
+        assert rel_err(r.TSActionRK4(g["real_F_hat"], direct=False), g[f"real_Y_adjoint_{tag}"]) < ACTION_TOL
+        r.close()
+    for k, Nw in ((1, 2), (2, 5)):
+        v = _vars(O, g, f"edge_{k}_{Nw}_grid", N=500, k=k, Nw=Nw, Nw_eff=Nw, w=1.1)
+        r = _handle(pkg, A_GL, v, True, float(g["beta"]))
+        assert rel_err(r.TSActionRK4(g[f"edge_{k}_{Nw}_F"], direct=True), g[f"edge_{k}_{Nw}_Y"]) < ACTION_TOL
+        r.close()
+
+
+@gpu
+def test_cuda_weighted_actions_match_reference_code(pkg, O, A_GL):
+    _need_gpu()
+    g = _load("ref_gl_weighted.npz")
+    k, Nw = int(g["k"]), int(g["Nw"])
+    mats, shapes = weight_mats(500)
+    v = _vars(O, g, N=500, k=k, Nw=Nw, Nw_eff=Nw, w=float(g["w"]))
+    r = _handle(pkg, A_GL, v)
+    for n in mats:
+        r.ReadWeightMats(n, shapes[n][0], shapes[n][1], *mats[n])
+    r.set_Y_hat(g["F"])
+    r.DirectActionRK4()
+    assert rel_err(r.get_Y_hat(), g["Y_direct"]) < ACTION_TOL
+    r.set_Y_hat(g["G"])
+    r.AdjointActionRK4()
+    assert rel_err(r.get_Y_hat(), g["Y_adjoint"]) < ACTION_TOL
+    r.close()
+
+
+# ------------------------------------------------------------------------------- GPU: the drop-in executable `RSVDt`
+def _run_driver(tmp, yaml_text, files, pkg, **fmt):
+    os.makedirs(os.path.join(tmp, "results"), exist_ok=True)
+    write_case_files(pkg.petsc_io, tmp, files)
+    with open(os.path.join(tmp, "variables.yaml"), "w") as f:
+        f.write(yaml_text.format(root=tmp, **fmt))
+    out = subprocess.run([EXE, "-inputs", "variables.yaml"], cwd=tmp, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    return out.stdout
+
+
+def _read_modes(io, res, k, Nw_eff, opt):
+    if opt == 1:
+        U = np.stack([io.read_mat_dense(f"{res}/U_hat_k{j + 1}_allFreqs") for j in range(k)], axis=2)
+        V = np.stack([io.read_mat_dense(f"{res}/V_hat_k{j + 1}_allFreqs") for j in range(k)], axis=2)
+    else:
+        U = np.stack([io.read_mat_dense(f"{res}/U_hat_Freq{iw}_allK") for iw in range(Nw_eff)], axis=1)
+        V = np.stack([io.read_mat_dense(f"{res}/V_hat_Freq{iw}_allK") for iw in range(Nw_eff)], axis=1)
+    return U, V
+
+
+@gpu
+@pytest.mark.parametrize("tag,opt", [("tr", 1), ("notr", 2)])
+def test_driver_results_match_reference_executable(pkg, tmp_path, tag, opt):
+    # same variables.yaml, same PETSc-binary inputs -> same result files as `RSVDt_ref` wrote (names, shapes, values)
+    _need_gpu()
+    g = _load("ref_gl_executable.npz")
+    k, Nw = 3, 8
+    F = pkg.synthetic.random_forcing(500, k, Nw, seed=3)
+    assert _sha(F) == str(g["small_F_sha256"])
+    tmp = str(tmp_path)
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", F)}
+    _run_driver(tmp, SMALL_YAML, files, pkg, Nw=Nw, w=0.6, TL=1.0, TR="true" if tag == "tr" else "false", opt=opt,
+                transrun="false", q=1, disc="true", weights="false")
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g[f"small_files_{tag}"])
+    S = pkg.petsc_io.read_mat_dense(f"{res}/S_hat")
+    Sg = g[f"small_S_{tag}"]
+    assert S.shape == Sg.shape and np.abs(S.imag).max() == 0 and np.abs(S.real / Sg.real - 1).max() <= GAIN_TOL
+    U, V = _read_modes(pkg.petsc_io, res, k, Nw, opt)
+    Ug, Vg = g[f"small_U_{tag}"], g[f"small_V_{tag}"]
+    assert U.shape == Ug.shape and V.shape == Vg.shape
+    for iw in range(Nw):
+        for j in range(k):
+            assert principal_angle(U[:, iw, j:j + 1], Ug[:, iw, j:j + 1]) <= ANGLE_TOL
+            assert principal_angle(V[:, iw, j:j + 1], Vg[:, iw, j:j + 1]) <= ANGLE_TOL
+
+
+@gpu
+def test_driver_weighted_solve_matches_reference_executable(pkg, tmp_path):
+    _need_gpu()
+    g = _load("ref_gl_weighted.npz")
+    k, Nw = int(g["k"]), int(g["Nw"])
+    mats, shapes = weight_mats(500)
+    tmp = str(tmp_path)
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", g["F"])}
+    for n in mats:
+        files[n] = ("csr", shapes[n], mats[n])
+    _run_driver(tmp, SMALL_YAML, files, pkg, Nw=Nw, w=1.0, TL=1.0, TR="false", opt=2, transrun="false", q=1, disc="false",
+                weights="true")
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    S = pkg.petsc_io.read_mat_dense(f"{res}/S_hat")
+    assert np.abs(S.real / g["S_hat"].real - 1).max() <= GAIN_TOL
+    U, V = _read_modes(pkg.petsc_io, res, k, Nw, 2)
+    assert U.shape == g["U_hat"].shape and V.shape == g["V_hat"].shape          # Nc x Nw x k, Nb x Nw x k
+    for iw in range(Nw):
+        assert principal_angle(U[:, iw, :1], g["U_hat"][:, iw, :1]) <= ANGLE_TOL
+        assert principal_angle(V[:, iw, :1], g["V_hat"][:, iw, :1]) <= ANGLE_TOL
+
+
+@gpu
+def test_driver_transient_run_matches_reference_executable(pkg, tmp_path):
+    _need_gpu()
+    g = _load("ref_gl_executable.npz")
+    tmp = str(tmp_path)
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", np.zeros((500, 8), complex)),
+             "results/q0": ("vec", g["trans_q0"])}
+    _run_driver(tmp, SMALL_YAML, files, pkg, Nw=8, w=0.6, TL=1.0, TR="false", opt=1, transrun="true", q=1, disc="true",
+                weights="false")
+    res = os.path.join(tmp, "results", "TransientSnapshots_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g["trans_files"])
+    assert np.allclose(pkg.petsc_io.read_vec(f"{res}/q_transient_norms").real, g["trans_norms"], rtol=1e-11)
+    assert rel_err(pkg.petsc_io.read_vec(f"{res}/q_transient_last_snapshot"), g["trans_last"]) < 1e-11
+    assert rel_err(pkg.petsc_io.read_vec(f"{res}/q_transient_2"), g["trans_q2"]) < 1e-11
+
+
+@gpu
+def test_driver_tutorial_as_shipped_matches_reference_executable(pkg, tmp_path):
+    # BASELINE.json configs[0]: Tutorial/Ginzburg-Landau with variables.yaml as shipped, reference executable vs drop-in
+    _need_gpu()
+    g = _load("ref_gl_tutorial.npz")
+    k, Nw = 10, 42
+    F = pkg.synthetic.random_forcing(500, k, Nw, seed=14)
+    assert _sha(F) == str(g["F_sha256"])
+    tmp = str(tmp_path)
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", F)}
+    _run_driver(tmp, TUTORIAL_YAML, files, pkg)
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    S = pkg.petsc_io.read_mat_dense(f"{res}/S_hat")
+    gerr = np.abs(S.real / g["S_hat"].real - 1)
+    print("tutorial as shipped vs reference executable: gain rel err leading", gerr[0].max(), "all", gerr.max())
+    assert S.shape == (k, Nw) and gerr[0].max() <= GAIN_TOL
+    U, V = _read_modes(pkg.petsc_io, res, k, Nw, 1)
+    ang = max(principal_angle(U[:, iw, :1], g["U_lead"][:, iw:iw + 1]) for iw in range(Nw))
+    angv = max(principal_angle(V[:, iw, :1], g["V_lead"][:, iw:iw + 1]) for iw in range(Nw))
+    print("tutorial as shipped vs reference executable: principal angles U, V", ang, angv)
+    assert ang <= ANGLE_TOL and angv <= ANGLE_TOL
