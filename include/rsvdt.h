@@ -78,6 +78,15 @@ int rsvdt_set_grid(rsvdt_handle h, const rsvdt_grid *g);
 int rsvdt_set_weight_csr(rsvdt_handle h, int which, int64_t nrows, int64_t ncols, const int64_t *rowptr,
                          const int64_t *col, const double *val_re_im);
 
+/* The same for row-partitioned runs (after rsvdt_dist_init): every rank passes the rows of M it owns in M's row space and
+ * the rows of M^H it owns in M's column space -- both PETSC_DECIDE splits, as MatLoad gives a MATMPIAIJ
+ * (ReadWeightMats.c:28-31) -- with GLOBAL column indices.  Applying a weight all-gathers the owned rows of Y_hat one
+ * frequency block at a time through the callback of rsvdt_set_allgather and forms the local rows of the product
+ * (ApplyWeightMats.c:16-80 on MPI matrices: MatMatMult of an MPIAIJ with an MPIDENSE matrix). */
+int rsvdt_set_weight_csr_local(rsvdt_handle h, int which, int64_t nrows_global, int64_t ncols_global, int64_t n_local,
+                               const int64_t *rowptr, const int64_t *col_global, const double *val_re_im, int64_t nH_local,
+                               const int64_t *rowptr_H, const int64_t *col_global_H, const double *val_H_re_im);
+
 /* ---- RSVD_mat->Y_hat ----------------------------------------------------------------------------- */
 /* CreateRandomMat.c:23-31 (the InputForcingFlg path): uploads Y_hat, nrows x (k*Nw_eff), reference layout. */
 int rsvdt_set_yhat(rsvdt_handle h, const double *Y_host, int64_t nrows);
@@ -157,6 +166,11 @@ int rsvdt_dist_get_in_offsets(rsvdt_handle h, int64_t *in_mailbox_row_offset);
  * the caller supplies it (torch.distributed all_reduce over NCCL in the Python host); stream-ordered on `stream`. */
 typedef int (*rsvdt_allreduce_fn)(void *device_ptr, int64_t n_doubles, void *cuda_stream, void *user);
 int rsvdt_set_allreduce(rsvdt_handle h, rsvdt_allreduce_fn fn, void *user);
+/* all-gather across ranks of n doubles per rank resident on the device (send: n doubles, recv: nranks*n doubles in rank
+ * order), used by the row-partitioned weight / input / output matrices; stream-ordered on `stream`. */
+typedef int (*rsvdt_allgather_fn)(const void *send_device_ptr, void *recv_device_ptr, int64_t n_doubles_per_rank,
+                                  void *cuda_stream, void *user);
+int rsvdt_set_allgather(rsvdt_handle h, rsvdt_allgather_fn fn, void *user);
 void *rsvdt_cuda_stream(rsvdt_handle h);
 
 /* ---- test / measurement hooks (no reference counterpart) ------------------------------------------ */

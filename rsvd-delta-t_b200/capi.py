@@ -37,6 +37,7 @@ class Grid(C.Structure):
 
 SNAPSHOT_CB = C.CFUNCTYPE(C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int64, _vp)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -166,6 +167,16 @@ class RSVDt:
         val = np.ascontiguousarray(val, c128)
         self._ck(lib().rsvdt_set_weight_csr(self._h, C.c_int(idx), C.c_int64(nrows), C.c_int64(ncols), _p(rowptr),
                                             _p(col), _p(val)))
+
+    def ReadWeightMats_local(self, which, nrows_global, ncols_global, M_rows, MH_rows):
+        """row-partitioned ReadWeightMats: M_rows / MH_rows = (rowptr, col_global, val) of the rows of M / M^H this rank owns
+        (PETSC_DECIDE splits of M's row and column spaces); see dist.local_weight"""
+        idx = {"W_f_sqrt_inv": 0, "B": 1, "W_q_sqrt_inv": 2, "W_q_sqrt": 3, "C": 4}[which]
+        a = [np.ascontiguousarray(M_rows[0], np.int64), np.ascontiguousarray(M_rows[1], np.int64), np.ascontiguousarray(M_rows[2], c128),
+             np.ascontiguousarray(MH_rows[0], np.int64), np.ascontiguousarray(MH_rows[1], np.int64), np.ascontiguousarray(MH_rows[2], c128)]
+        self._ck(lib().rsvdt_set_weight_csr_local(self._h, C.c_int(idx), C.c_int64(nrows_global), C.c_int64(ncols_global),
+                                                  C.c_int64(a[0].size - 1), _p(a[0]), _p(a[1]), _p(a[2]),
+                                                  C.c_int64(a[3].size - 1), _p(a[3]), _p(a[4]), _p(a[5])))
 
     # ---- Y_hat ---------------------------------------------------------------------------------------
     def set_Y_hat(self, Y):

@@ -43,6 +43,9 @@ struct CsrOwned {
     DevBuf rowptr, col, val;
     int64_t lo_bw = 0, hi_bw = 0;  // max (row - col), max (col - row)
     bool set = false;
+    // row-partitioned weight matrices: global sizes; the stored columns index the all-gathered input block
+    // [rank][gather_rows][k] (gather_rows = rows of rank 0 = the largest PETSC_DECIDE share of the column space)
+    int64_t g_nrows = 0, g_ncols = 0, gather_rows = 0, in_rows_local = 0;
     // diagonal (DIA) form for the fused sliding-window step kernel: dia[row][dia_lo+dia_hi+1]
     DevBuf dia, tile_ok, slow_ranges;
     int dia_lo = 0, dia_hi = 0;
@@ -101,6 +104,9 @@ struct rsvdt_context {
         int64_t lo_end = 0, hi_begin = 0;
         rsvdt_allreduce_fn allreduce = nullptr;
         void *allreduce_user = nullptr;
+        rsvdt_allgather_fn allgather = nullptr;
+        void *allgather_user = nullptr;
+        DevBuf gather_send, gather_recv;
     } dist;
 
     // Weight_matrices (Variables.h:69-80): 0=W_f_sqrt_inv 1=B 2=W_q_sqrt_inv 3=W_q_sqrt 4=C, and their conj-transposes
@@ -1100,21 +1106,56 @@ int ts_action(rsvdt_handle h, bool direct)
     return rc;
 }
 
-// ApplyWeightMats.c:16-80 : Y_hat <- M * Y_hat for sparse M (rows may change)
-int apply_sparse(rsvdt_handle h, const CsrOwned &M)
+// ApplyWeightMats.c:16-80 : X <- M * X for sparse M on a device stack [iw][row][ik] (rows may change).
+// Row-partitioned runs: M holds this rank's rows with columns indexing the all-gathered input; one frequency block at a time
+// the owned rows of X are all-gathered (NCCL through the registered callback) and the local rows of the product formed.
+// The weights are applied once per action, so this costs one pass over X per matrix against ~1e4 RK4 steps in between.
+void stack_geom(rsvdt_handle h, int64_t rows, int64_t *srows, int64_t *roff);
+int apply_sparse_to(rsvdt_handle h, const CsrOwned &M, DevBuf &X, int64_t &xrows)
 {
     const rsvdt_grid &g = h->g;
-    if (h->yhat_rows != M.d.ncols) return fail(h, RSVDT_ERR_ARG, "weight matrix has %lld columns, Y_hat has %lld rows", (long long)M.d.ncols, (long long)h->yhat_rows);
+    const bool part = h->dist.on;
+    const int64_t want = part ? M.in_rows_local : M.d.ncols;
+    if (xrows != want) return fail(h, RSVDT_ERR_ARG, "weight matrix expects %lld rows, the matrix it multiplies has %lld", (long long)want, (long long)xrows);
     DevBuf out;
-    CU(out.alloc(stack_bytes(g.Nw_eff, M.d.nrows, g.k)));
-    CU(launch_spmm_stack(M.d, h->Yhat.as<cplx>(), out.as<cplx>(), (int)g.Nw_eff, (int)g.k, h->stream));
-    h->launches++;
+    if (!part) {
+        CU(out.alloc(stack_bytes(g.Nw_eff, M.d.nrows, g.k)));
+        CU(launch_spmm_stack(M.d, X.as<cplx>(), out.as<cplx>(), (int)g.Nw_eff, (int)g.k, h->stream));
+        h->launches++;
+    } else {
+        if (h->dist.nranks > 1 && !h->dist.allgather) return fail(h, RSVDT_ERR_STATE, "row-partitioned run: no all-gather registered (rsvdt_set_allgather)");
+        int64_t srows_in, roff_in, srows_out, roff_out;
+        stack_geom(h, xrows, &srows_in, &roff_in);
+        stack_geom(h, M.d.nrows, &srows_out, &roff_out);
+        CU(out.alloc(stack_bytes(g.Nw_eff, srows_out, g.k)));
+        if (srows_out != M.d.nrows) CU(cudaMemsetAsync(out.p, 0, stack_bytes(g.Nw_eff, srows_out, g.k), h->stream));
+        const size_t blk = (size_t)M.gather_rows * g.k * sizeof(cplx);
+        RS(ensure(h, h->dist.gather_send, blk));
+        RS(ensure(h, h->dist.gather_recv, blk * (size_t)h->dist.nranks));
+        CU(cudaMemsetAsync(h->dist.gather_send.p, 0, blk, h->stream));
+        for (int64_t a = 0; a < g.Nw_eff; a++) {
+            const cplx *src = X.as<cplx>() + ((size_t)a * srows_in + roff_in) * g.k;
+            CU(cudaMemcpyAsync(h->dist.gather_send.p, src, (size_t)xrows * g.k * sizeof(cplx), cudaMemcpyDeviceToDevice, h->stream));
+            if (h->dist.nranks > 1) {
+                const int rc = h->dist.allgather(h->dist.gather_send.p, h->dist.gather_recv.p, (int64_t)(blk / sizeof(double)), (void *)h->stream,
+                                                 h->dist.allgather_user);
+                if (rc) return fail(h, RSVDT_ERR_CUDA, "all-gather callback failed (%d)", rc);
+            } else {
+                CU(cudaMemcpyAsync(h->dist.gather_recv.p, h->dist.gather_send.p, blk, cudaMemcpyDeviceToDevice, h->stream));
+            }
+            cplx *dst = out.as<cplx>() + ((size_t)a * srows_out + roff_out) * g.k;
+            CU(launch_spmm_stack(M.d, h->dist.gather_recv.as<cplx>(), dst, 1, (int)g.k, h->stream));
+            h->launches++;
+        }
+    }
     CU(cudaStreamSynchronize(h->stream));
-    h->Yhat.swap(out);
-    h->yhat_rows = M.d.nrows;
+    X.swap(out);
+    xrows = M.d.nrows;
     out.release();
     return RSVDT_OK;
 }
+
+int apply_sparse(rsvdt_handle h, const CsrOwned &M) { return apply_sparse_to(h, M, h->Yhat, h->yhat_rows); }
 
 int action_with_weights(rsvdt_handle h, bool direct)
 {
@@ -1317,7 +1358,7 @@ int rsvdt_set_weight_csr(rsvdt_handle h, int which, int64_t nrows, int64_t ncols
     RS(bind(h));
     if (which < 0 || which > 4 || !rowptr || !col || !val) return fail(h, RSVDT_ERR_ARG, "bad weight arguments");
     if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "set the operator before the weights");
-    if (h->dist.on) return fail(h, RSVDT_ERR_ARG, "weight / input / output matrices are not supported in row-partitioned runs yet");
+    if (h->dist.on) return fail(h, RSVDT_ERR_ARG, "row-partitioned run: pass the owned rows with rsvdt_set_weight_csr_local");
     static const char *names[5] = {"W_f_sqrt_inv", "B", "W_q_sqrt_inv", "W_q_sqrt", "C"};
     if ((which == 0 || which == 2 || which == 3) && nrows != ncols)   // ReadWeightMats.c:34,64,75
         return fail(h, RSVDT_ERR_USER, "weight matrix (%s) must be square, current size = %lld x %lld", names[which], (long long)nrows, (long long)ncols);
@@ -1326,6 +1367,63 @@ int rsvdt_set_weight_csr(rsvdt_handle h, int which, int64_t nrows, int64_t ncols
     const cplx *v = reinterpret_cast<const cplx *>(val);
     RS(upload_csr(h, h->W[which], nrows, ncols, rowptr, col, v, false, 0.0));
     RS(upload_csr(h, h->WH[which], nrows, ncols, rowptr, col, v, true, 0.0));
+    return RSVDT_OK;
+}
+
+// PETSC_DECIDE split of n rows over nranks: first row of `rank`
+static int64_t split_begin(int64_t n, int nranks, int rank) { return (int64_t)rank * (n / nranks) + std::min<int64_t>(rank, n % nranks); }
+
+// columns of a row-partitioned weight matrix: global column -> position in the all-gathered block [rank][gather_rows]
+static int remap_gathered(rsvdt_handle h, int64_t ncols_g, int64_t nnz, const int64_t *col, std::vector<int64_t> &out, int64_t *gather_rows)
+{
+    const int P = h->dist.nranks;
+    const int64_t q = ncols_g / P, r = ncols_g % P, big = q + (r ? 1 : 0);
+    *gather_rows = std::max<int64_t>(big, 1);
+    out.resize((size_t)std::max<int64_t>(nnz, 1));
+    for (int64_t p = 0; p < nnz; p++) {
+        const int64_t c = col[p];
+        if (c < 0 || c >= ncols_g) return fail(h, RSVDT_ERR_ARG, "weight matrix: column index %lld out of range", (long long)c);
+        const int64_t owner = (c < r * (q + 1)) ? c / (q + 1) : r + (q ? (c - r * (q + 1)) / q : 0);
+        out[(size_t)p] = owner * (*gather_rows) + (c - split_begin(ncols_g, P, (int)owner));
+    }
+    return RSVDT_OK;
+}
+
+int rsvdt_set_weight_csr_local(rsvdt_handle h, int which, int64_t nrows_global, int64_t ncols_global, int64_t n_local,
+                               const int64_t *rowptr, const int64_t *col_global, const double *val, int64_t nH_local,
+                               const int64_t *rowptr_H, const int64_t *col_global_H, const double *val_H)
+{
+    RS(bind(h));
+    if (which < 0 || which > 4 || !rowptr || !col_global || !val || !rowptr_H || !col_global_H || !val_H) return fail(h, RSVDT_ERR_ARG, "bad weight arguments");
+    if (!h->dist.on) return fail(h, RSVDT_ERR_STATE, "rsvdt_set_weight_csr_local needs rsvdt_dist_init; use rsvdt_set_weight_csr otherwise");
+    if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "set the operator before the weights");
+    static const char *names[5] = {"W_f_sqrt_inv", "B", "W_q_sqrt_inv", "W_q_sqrt", "C"};
+    if ((which == 0 || which == 2 || which == 3) && nrows_global != ncols_global)   // ReadWeightMats.c:34,64,75
+        return fail(h, RSVDT_ERR_USER, "weight matrix (%s) must be square, current size = %lld x %lld", names[which], (long long)nrows_global, (long long)ncols_global);
+    if (which == 1 && nrows_global != h->N_global) return fail(h, RSVDT_ERR_USER, "Input matrix (B) must have %lld rows", (long long)h->N_global);        // :49
+    if (which == 4 && ncols_global != h->N_global) return fail(h, RSVDT_ERR_USER, "Output matrix (C) must have %lld columns", (long long)h->N_global);   // :89
+    const int P = h->dist.nranks, me = h->dist.rank;
+    const int64_t own_r = split_begin(nrows_global, P, me + 1) - split_begin(nrows_global, P, me);
+    const int64_t own_c = split_begin(ncols_global, P, me + 1) - split_begin(ncols_global, P, me);
+    if (n_local != own_r || nH_local != own_c)
+        return fail(h, RSVDT_ERR_ARG, "%s: rank %d must pass %lld rows of M and %lld rows of M^H (PETSC_DECIDE split), got %lld and %lld", names[which], me,
+                    (long long)own_r, (long long)own_c, (long long)n_local, (long long)nH_local);
+    std::vector<int64_t> cm;
+    int64_t gr = 0;
+    RS(remap_gathered(h, ncols_global, rowptr[n_local], col_global, cm, &gr));
+    RS(upload_csr(h, h->W[which], n_local, gr * P, rowptr, cm.data(), reinterpret_cast<const cplx *>(val), false, 0.0));
+    h->W[which].g_nrows = nrows_global; h->W[which].g_ncols = ncols_global; h->W[which].gather_rows = gr; h->W[which].in_rows_local = own_c;
+    RS(remap_gathered(h, nrows_global, rowptr_H[nH_local], col_global_H, cm, &gr));
+    RS(upload_csr(h, h->WH[which], nH_local, gr * P, rowptr_H, cm.data(), reinterpret_cast<const cplx *>(val_H), false, 0.0));
+    h->WH[which].g_nrows = ncols_global; h->WH[which].g_ncols = nrows_global; h->WH[which].gather_rows = gr; h->WH[which].in_rows_local = own_r;
+    return RSVDT_OK;
+}
+
+int rsvdt_set_allgather(rsvdt_handle h, rsvdt_allgather_fn fn, void *user)
+{
+    RS(bind(h));
+    h->dist.allgather = fn;
+    h->dist.allgather_user = user;
     return RSVDT_OK;
 }
 
@@ -1338,7 +1436,8 @@ int rsvdt_set_yhat(rsvdt_handle h, const double *Y_host, int64_t nrows)
     if (!Y_host || nrows <= 0) return fail(h, RSVDT_ERR_ARG, "bad Y_hat arguments");
     int64_t srows, roff;
     stack_geom(h, nrows, &srows, &roff);
-    if (h->dist.on && nrows != h->N) return fail(h, RSVDT_ERR_ARG, "row-partitioned runs take Y_hat with the %lld owned rows", (long long)h->N);
+    const bool weighted = h->W[0].set || h->W[1].set || h->W[3].set || h->W[4].set;   // then Y_hat lives in the N_b / N_c row space
+    if (h->dist.on && nrows != h->N && !weighted) return fail(h, RSVDT_ERR_ARG, "row-partitioned runs take Y_hat with the %lld owned rows", (long long)h->N);
     RS(upload_stack(h, h->Yhat, Y_host, nrows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1, srows, roff));
     h->yhat_rows = nrows;
     return RSVDT_OK;
@@ -1452,24 +1551,8 @@ int rsvdt_svd_all_freqs(rsvdt_handle h)
     h->vhat_rows = h->yhat_rows;
     h->yhat_rows = 0;
     // SVDAllFreqs.c:63-64 optional W^{-1/2} scalings
-    if (h->W[2].set && h->Uhat.p) {
-        DevBuf out;
-        if (h->uhat_rows != h->W[2].d.ncols) return fail(h, RSVDT_ERR_ARG, "W_q_sqrt_inv size mismatch");
-        CU(out.alloc(stack_bytes(g.Nw_eff, h->W[2].d.nrows, g.k)));
-        CU(launch_spmm_stack(h->W[2].d, h->Uhat.as<cplx>(), out.as<cplx>(), (int)g.Nw_eff, (int)g.k, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        h->Uhat.swap(out);
-        out.release();
-    }
-    if (h->W[0].set) {
-        DevBuf out;
-        if (h->vhat_rows != h->W[0].d.ncols) return fail(h, RSVDT_ERR_ARG, "W_f_sqrt_inv size mismatch");
-        CU(out.alloc(stack_bytes(g.Nw_eff, h->W[0].d.nrows, g.k)));
-        CU(launch_spmm_stack(h->W[0].d, h->Vhat.as<cplx>(), out.as<cplx>(), (int)g.Nw_eff, (int)g.k, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        h->Vhat.swap(out);
-        out.release();
-    }
+    if (h->W[2].set && h->Uhat.p) RS(apply_sparse_to(h, h->W[2], h->Uhat, h->uhat_rows));
+    if (h->W[0].set) RS(apply_sparse_to(h, h->W[0], h->Vhat, h->vhat_rows));
     return RSVDT_OK;
 }
 

@@ -129,6 +129,22 @@ def transpose_slab(rowptr, col, val, row_offset: int, c_lo: int, c_hi: int):
     return rp, r, v
 
 
+def local_weight(nrows, ncols, rowptr, col, val, nranks, rank):
+    """Rows of a weight / input / output matrix M (nrows x ncols, global CSR) that `rank` owns, and the rows of M^H it owns:
+    PETSC_DECIDE splits of M's row space and column space (what MatLoad gives a MATMPIAIJ, ReadWeightMats.c:28-31, and what
+    the in-place MatHermitianTranspose of ApplyWeightMats.c:44-74 produces).  Column indices stay global.
+    -> ((rowptr, col, val) of M[r0:r1, :], (rowptr, col, val) of M^H[c0:c1, :])"""
+    rowptr = np.asarray(rowptr, np.int64)
+    col = np.asarray(col, np.int64)
+    val = np.asarray(val)
+    r0, r1 = split_ownership(nrows, nranks, rank)
+    c0, c1 = split_ownership(ncols, nranks, rank)
+    p0, p1 = rowptr[r0], rowptr[r1]
+    M_rows = (rowptr[r0:r1 + 1] - p0, col[p0:p1], val[p0:p1])
+    MH_rows = transpose_slab(rowptr, col, val, 0, c0, c1)
+    return M_rows, MH_rows
+
+
 def build_messages(plan: Plan, all_requests):
     """all_requests[p][q] = (rows p needs from q, first ghost row on p).  -> my outgoing / incoming message lists"""
     out = []
@@ -207,6 +223,24 @@ def connect(r, plan: Plan, group=None):
     cb = capi.ALLREDUCE_FN(_allreduce)
     _KEEPALIVE.append(cb)
     r._ck(L.rsvdt_set_allreduce(r._h, cb, None))
+
+    def _allgather(send, recv, n, stream, user):
+        try:
+            ts = torch.as_tensor(_Dev(send, n), device="cuda")
+            tr = torch.as_tensor(_Dev(recv, n * world), device="cuda")
+            ext = torch.cuda.ExternalStream(stream)
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(ext)                       # the packing copy ran on the library's stream
+            dist.all_gather_into_tensor(tr, ts, group=group)
+            ext.wait_stream(cur)
+            return 0
+        except Exception as e:  # pragma: no cover
+            print("all-gather callback failed:", e)
+            return 1
+
+    cbg = capi.ALLGATHER_FN(_allgather)
+    _KEEPALIVE.append(cbg)
+    r._ck(L.rsvdt_set_allgather(r._h, cbg, None))
     dist.barrier(group=group)
     return out, inc
 

@@ -131,3 +131,139 @@ def write_vec(path: str, v, int64: bool = True) -> None:
 
 def file_exists(path: str) -> bool:
     return os.path.exists(path)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Partitioned I/O: every rank reads / writes only its rows of a record ("next" row 4 of SURVEY.md section 8f: MatLoad of a
+# MATMPIAIJ gives each rank its PETSC_DECIDE row range, LNSStructure.c:22-27; MatView / VecView collect them in row order).
+# ----------------------------------------------------------------------------------------------------------------------
+class MatRowReader:
+    """Row-range reader of a binary Mat record.  Reads the header and the M row lengths once (8*M bytes), then any
+    row range [r0, r1) costs two seeks and reads only its own columns and values."""
+
+    def __init__(self, path: str):
+        self.path = path
+        with open(path, "rb") as f:
+            head = f.read(8)
+            self.it, self.isz = _detect_int(head, MAT_FILE_CLASSID)
+            f.seek(0)
+            hdr = np.frombuffer(f.read(4 * self.isz), self.it).astype(np.int64)
+            self.M, self.N, self.nnz = int(hdr[1]), int(hdr[2]), int(hdr[3])
+            self.native_dense = self.nnz == -1
+            size = os.fstat(f.fileno()).st_size
+            if self.native_dense:
+                self.rowptr = np.arange(self.M + 1, dtype=np.int64) * self.N
+                self.off_val = 4 * self.isz
+                self.cplx = size - self.off_val >= self.M * self.N * 16
+            else:
+                rl = np.frombuffer(f.read(self.M * self.isz), self.it).astype(np.int64)
+                self.rowptr = np.zeros(self.M + 1, np.int64)
+                np.cumsum(rl, out=self.rowptr[1:])
+                if self.rowptr[-1] != self.nnz:
+                    raise ValueError("row lengths do not sum to nnz")
+                self.off_col = (4 + self.M) * self.isz
+                self.off_val = self.off_col + self.nnz * self.isz
+                self.cplx = size - self.off_val >= self.nnz * 16
+
+    def _scalars(self, f, first, count):
+        w = 16 if self.cplx else 8
+        f.seek(self.off_val + first * w)
+        raw = np.frombuffer(f.read(count * w), ">f8")
+        if self.cplx:
+            raw = raw.reshape(-1, 2)
+            return raw[:, 0] + 1j * raw[:, 1]
+        return raw.astype(np.complex128)
+
+    def rows(self, r0: int, r1: int):
+        """-> (rowptr [r1-r0+1, starting at 0], global columns, values) of rows [r0, r1)"""
+        r0, r1 = max(0, int(r0)), min(self.M, int(r1))
+        p0, p1 = int(self.rowptr[r0]), int(self.rowptr[r1])
+        rp = (self.rowptr[r0:r1 + 1] - p0).astype(np.int64)
+        with open(self.path, "rb") as f:
+            if self.native_dense:   # column-major values: gather the rows column by column
+                out = np.empty((r1 - r0, self.N), np.complex128)
+                for c in range(self.N):
+                    out[:, c] = self._scalars(f, c * self.M + r0, r1 - r0)
+                return rp, np.tile(np.arange(self.N, dtype=np.int64), r1 - r0), out.reshape(-1)
+            f.seek(self.off_col + p0 * self.isz)
+            col = np.frombuffer(f.read((p1 - p0) * self.isz), self.it).astype(np.int64)
+            val = self._scalars(f, p0, p1 - p0)
+        return rp, col, np.ascontiguousarray(val, dtype=np.complex128)
+
+    def dense_rows(self, r0: int, r1: int) -> np.ndarray:
+        """rows [r0, r1) as a dense (r1-r0, N) complex128 Fortran array (for F_hat files, CreateRandomMat.c:23-31)"""
+        rp, col, val = self.rows(r0, r1)
+        D = np.zeros((r1 - r0, self.N), np.complex128, order="F")
+        D[np.repeat(np.arange(r1 - r0), np.diff(rp)), col] = val
+        return D
+
+
+def read_vec_rows(path: str, r0: int, r1: int):
+    """-> (n_global, entries [r0, r1)) of a binary Vec record"""
+    with open(path, "rb") as f:
+        it, isz = _detect_int(f.read(8), VEC_FILE_CLASSID)
+        f.seek(isz)
+        n = int(np.frombuffer(f.read(isz), it)[0])
+        size = os.fstat(f.fileno()).st_size
+        cplx = size - 2 * isz >= n * 16
+        w = 16 if cplx else 8
+        f.seek(2 * isz + r0 * w)
+        raw = np.frombuffer(f.read((r1 - r0) * w), ">f8")
+    if cplx:
+        raw = raw.reshape(-1, 2)
+        return n, raw[:, 0] + 1j * raw[:, 1]
+    return n, raw.astype(np.complex128)
+
+
+class DenseMatWriter:
+    """Collective writer of the record MatView(dense) produces (an AIJ record holding every entry, row by row).
+    Rank 0 calls create() (header + file size), then -- after a barrier -- every rank calls write_rows() with its own
+    row block; the three sections of a row block (row lengths, column indices, values) are contiguous slabs."""
+
+    def __init__(self, path: str, M: int, N: int, int64: bool = True):
+        self.path, self.M, self.N = path, int(M), int(N)
+        self.it, self.isz = (">i8", 8) if int64 else (">i4", 4)
+        self.off_rl = 4 * self.isz
+        self.off_col = self.off_rl + self.M * self.isz
+        self.off_val = self.off_col + self.M * self.N * self.isz
+        self.size = self.off_val + self.M * self.N * 16
+
+    def create(self):
+        with open(self.path, "wb") as f:
+            f.write(np.asarray([MAT_FILE_CLASSID, self.M, self.N, self.M * self.N]).astype(self.it).tobytes())
+            f.truncate(self.size)
+
+    def write_rows(self, r0: int, block) -> None:
+        block = np.asarray(block, dtype=np.complex128)
+        n = block.shape[0]
+        assert block.ndim == 2 and block.shape[1] == self.N and 0 <= r0 and r0 + n <= self.M
+        if n == 0:
+            return
+        with open(self.path, "r+b") as f:
+            f.seek(self.off_rl + r0 * self.isz)
+            f.write(np.full(n, self.N).astype(self.it).tobytes())
+            f.seek(self.off_col + r0 * self.N * self.isz)
+            f.write(np.tile(np.arange(self.N), n).astype(self.it).tobytes())
+            f.seek(self.off_val + r0 * self.N * 16)
+            f.write(_scalars(np.ascontiguousarray(block).reshape(-1)))
+
+
+class VecWriter:
+    """Collective VecView: rank 0 create(), barrier, every rank write_rows(r0, values)."""
+
+    def __init__(self, path: str, n: int, int64: bool = True):
+        self.path, self.n = path, int(n)
+        self.it, self.isz = (">i8", 8) if int64 else (">i4", 4)
+
+    def create(self):
+        with open(self.path, "wb") as f:
+            f.write(np.asarray([VEC_FILE_CLASSID, self.n]).astype(self.it).tobytes())
+            f.truncate(2 * self.isz + self.n * 16)
+
+    def write_rows(self, r0: int, v) -> None:
+        v = np.asarray(v, dtype=np.complex128).reshape(-1)
+        if v.size == 0:
+            return
+        with open(self.path, "r+b") as f:
+            f.seek(2 * self.isz + r0 * 16)
+            f.write(_scalars(v))
