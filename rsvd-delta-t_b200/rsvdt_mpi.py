@@ -256,6 +256,8 @@ class Run:
         max_bw = max(lo, hi, 1)
         min_rows = N // self.world
         layout = 1 if (max_bw <= 8 and 8 * max_bw < min_rows) else 0
+        if os.environ.get("RSVDT_LAYOUT") in ("0", "1"):          # testing hook: force the local layout
+            layout = int(os.environ["RSVDT_LAYOUT"])
         self.layout, self.band = layout, (lo, hi)
         grid = dict(k=v["k"], Nw=v["Nw"], Ns=v["Ns"], Nt=v["Nt"], ResRatio=v["ResRatio"], dt=v["dt"], w=v["w"],
                     TransientRemoval=v["TransientRemoval"])
@@ -347,7 +349,8 @@ class Run:
         else:
             self.log("Generating a random forcing matrix")
             F = random_rows(v["RandSeed"], b0, b1, v["k"] * v["Nw_eff"])
-        self.set_grid(v)
+        if int(self.r.grid.k) != v["k"]:
+            raise UserError(f"internal: the ranks were connected for k = {int(self.r.grid.k)} test vectors, the forcing has {v['k']}")
         self.r.set_Y_hat(F)
 
     def create_results_dir(self, v, name):

@@ -1,0 +1,275 @@
+"""The multi-GPU drop-in `rsvd-delta-t_b200/rsvdt_mpi.py` (stands for `mpiexec -n P RSVDt -inputs variables.yaml`).
+
+CPU tests (gloo, world_size 2): the host logic -- YAML rules of ReadUserInput.c, partitioned PETSc-binary readers and the
+collective writers (every rank its own PETSC_DECIDE rows), rank-count-independent random forcing, row/column splitting of
+the weight matrices and the gathered-index product the CUDA library forms.
+GPU test (2 GPUs): the driver under torchrun against the committed outputs of the reference executable
+(tests/golden/ref_gl_executable.npz, ref_gl_weighted.npz) -- same variables.yaml, same input files."""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN, ROOT, principal_angle, rel_err
+from ref_cases import SMALL_YAML, weight_mats, write_case_files
+
+
+@pytest.fixture(scope="module")
+def drv(pkg):
+    return importlib.import_module("rsvdt_b200.rsvdt_mpi")
+
+
+# ------------------------------------------------------------------------------------------------ YAML / input rules
+def _yaml(tmp_path, text):
+    p = tmp_path / "variables.yaml"
+    p.write_text(text)
+    return ["RSVDt", "-inputs", str(p)]
+
+
+BASE = """RootDir: /data/   # trailing comment
+ResultsDir: 'res/'
+OperatorDir: "A"
+Nw: 8
+w: 0.5
+dt: 0.003
+TransientLength: 10
+"""
+
+
+def test_read_user_input_defaults_and_required_keys(drv, tmp_path):
+    logs = []
+    v = drv.read_user_input(_yaml(tmp_path, BASE), logs.append)
+    # defaults of ReadUserInput.c:32-170 and their warnings
+    assert (v["k"], v["q"], v["RandSeed"], v["Display"], v["SaveResultsOpt"]) == (3, 0, 1373, 2, 1)
+    assert not any(v[f] for f in ("InputForcingFlg", "TwoPI", "TransRun", "TransientRemoval", "DiscFlg"))
+    assert (v["RootDir"], v["ResultsDir"], v["OperatorDir"]) == ("/data/", "res/", "A")      # comment / quotes stripped
+    assert "Warning: 'k' variable not found. Setting 'k' to default value: 3" in logs
+    assert "Warning: 'InvInputWeightFlg' variable not found. Setting 'InputWeightFlg' to default value: 0" in logs  # sic
+    assert not any("TransSaveMod" in m for m in logs)                 # transient-run warnings only when TransRun (:146-170)
+    for key, msg in (("TransientLength", "Must specify 'TransientLength'"), ("dt", "Must specify 'dt'"),
+                     ("w", "Must specify 'dt'"), ("Nw", "Must specify 'Nw'"), ("RootDir", "Must specify 'RootDir'")):
+        text = "\n".join(line for line in BASE.splitlines() if not line.startswith(key + ":")) + "\n"
+        with pytest.raises(drv.UserError, match=msg):
+            drv.read_user_input(_yaml(tmp_path, text), lambda m: None)
+    with pytest.raises(drv.UserError, match="-inputs"):
+        drv.read_user_input(["RSVDt"], lambda m: None)
+
+
+def test_read_user_input_conditionals(drv, tmp_path):
+    quiet = lambda m: None  # noqa: E731
+    with pytest.raises(drv.UserError, match="Must specify 'InputForcingDir'"):
+        drv.read_user_input(_yaml(tmp_path, BASE + "InputForcingFlg: true\n"), quiet)
+    with pytest.raises(drv.UserError, match="Discounting flag is on"):
+        drv.read_user_input(_yaml(tmp_path, BASE + "DiscFlg: true\n"), quiet)
+    with pytest.raises(drv.UserError, match="'beta' must be positive"):
+        drv.read_user_input(_yaml(tmp_path, BASE + "DiscFlg: true\nbeta: -1\n"), quiet)
+    with pytest.raises(drv.UserError, match="Unknown logical value"):
+        drv.read_user_input(_yaml(tmp_path, BASE + "TwoPI: maybe\n"), quiet)
+    v = drv.read_user_input(_yaml(tmp_path, BASE + "TwoPI: yes\nTransRun: on\nTransICFlg: false\n"), quiet)
+    assert v["w"] == pytest.approx(0.5 * 2 * np.pi) and v["TransRun"] and v["TransSaveMod"] == 100 and v["TransConVal"] == 1e-8
+    with pytest.raises(drv.UserError, match="Must specify 'TransICDir'"):
+        drv.read_user_input(_yaml(tmp_path, BASE + "TransRun: true\nTransICFlg: true\n"), quiet)
+
+
+def test_random_rows_do_not_depend_on_the_partition(drv):
+    full = drv.random_rows(14, 0, 1000, 3, block=128)
+    parts = [drv.random_rows(14, a, b, 3, block=128) for a, b in ((0, 77), (77, 640), (640, 1000))]
+    assert np.array_equal(np.vstack(parts), full)
+    assert 0 <= full.real.min() and full.real.max() < 1 and 0 <= full.imag.min() and full.imag.max() < 1
+    assert not np.array_equal(full[:, 0], full[:, 1]) and not np.array_equal(full, drv.random_rows(15, 0, 1000, 3, block=128))
+
+
+# ------------------------------------------------------------------------------------- partitioned I/O, gloo world-2
+def _io_worker(rank, world, port, tmp, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    io, D = pkg.petsc_io, pkg.dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # MatLoad of a MATMPIAIJ: every rank its PETSC_DECIDE rows of the tutorial operator (64-bit file) and of a 32-bit copy
+        M, N, rp, ci, va = io.read_mat(os.path.join(GOLDEN, "A_GL"))
+        r0, r1 = D.split_ownership(N, world, rank)
+        for path in (os.path.join(GOLDEN, "A_GL"), os.path.join(tmp, "A32")):
+            a, b, c = io.MatRowReader(path).rows(r0, r1)
+            assert np.array_equal(a, rp[r0:r1 + 1] - rp[r0]) and np.array_equal(b, ci[rp[r0]:rp[r1]])
+            assert np.array_equal(c, va[rp[r0]:rp[r1]])
+        # the operator as dist.local_operator consumes it (both layouts) == rows of the global matrix
+        rd = io.MatRowReader(os.path.join(GOLDEN, "A_GL"))
+        plan, A, AH, im2 = D.local_operator(N, world, rank, rd.rows, 2, 0)
+        assert plan.n_own == r1 - r0 and A[0][-1] == rp[r1] - rp[r0]
+        # F_hat rows (dense record) and the initial vector
+        F = np.load(os.path.join(tmp, "F.npy"))
+        assert np.array_equal(io.MatRowReader(os.path.join(tmp, "F_hat")).dense_rows(r0, r1), F[r0:r1])
+        n, qv = io.read_vec_rows(os.path.join(tmp, "q0"), r0, r1)
+        assert n == N and np.array_equal(qv, F[r0:r1, 0])
+        # collective MatView / VecView: byte-identical to the one-rank writers
+        w = io.DenseMatWriter(os.path.join(tmp, "F_out"), N, F.shape[1])
+        if rank == 0:
+            w.create()
+        dist.barrier()
+        w.write_rows(r0, F[r0:r1])
+        vw = io.VecWriter(os.path.join(tmp, "q_out"), N)
+        if rank == 0:
+            vw.create()
+        dist.barrier()
+        vw.write_rows(r0, F[r0:r1, 0])
+        dist.barrier()
+        if rank == 0:
+            assert open(os.path.join(tmp, "F_out"), "rb").read() == open(os.path.join(tmp, "F_hat"), "rb").read()
+            assert open(os.path.join(tmp, "q_out"), "rb").read() == open(os.path.join(tmp, "q0"), "rb").read()
+        # weight matrices: local rows of M and of M^H; the product the library forms on the all-gathered block
+        from ref_cases import weight_mats
+        mats, shapes = weight_mats(N)
+        rng = np.random.default_rng(3)
+        for name, (m, n_) in shapes.items():
+            Mr, MHr = D.local_weight(m, n_, *mats[name], world, rank)
+            X = rng.standard_normal((n_, 2)) + 1j * rng.standard_normal((n_, 2))      # same on both ranks (same seed)
+            c0, c1 = D.split_ownership(n_, world, rank)
+            big = -(-n_ // world)
+            send = np.zeros((big, 2), complex)
+            send[: c1 - c0] = X[c0:c1]
+            parts = [None] * world
+            dist.all_gather_object(parts, send)
+            G = np.vstack(parts)                                                       # [rank][gather_rows] x k
+            owner = D.owner_of(Mr[1], D.all_ranges(n_, world))
+            starts = np.array([a for a, _ in D.all_ranges(n_, world)])
+            idx = owner * big + (Mr[1] - starts[owner])                                # remap_gathered of csrc/capi.cu
+            y = np.zeros((Mr[0].size - 1, 2), complex)
+            rows = np.repeat(np.arange(Mr[0].size - 1), np.diff(Mr[0]))
+            np.add.at(y, rows, Mr[2][:, None] * G[idx])
+            full = np.zeros((m, n_), complex)
+            frp, fci, fva = mats[name]
+            full[np.repeat(np.arange(m), np.diff(frp)), fci] = fva
+            a0, a1 = D.split_ownership(m, world, rank)
+            assert np.allclose(y, (full @ X)[a0:a1])
+            dH = np.zeros((MHr[0].size - 1, m), complex)
+            dH[np.repeat(np.arange(MHr[0].size - 1), np.diff(MHr[0])), MHr[1]] = MHr[2]
+            assert np.allclose(dH, full.conj().T[c0:c1])
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL " + repr(e) + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_io_and_weight_split_world2(pkg, tmp_path):
+    io = pkg.petsc_io
+    M, N, rp, ci, va = io.read_mat(os.path.join(GOLDEN, "A_GL"))
+    tmp = str(tmp_path)
+    io.write_mat_aij(os.path.join(tmp, "A32"), M, N, rp, ci, va, int64=False)
+    rng = np.random.default_rng(1)
+    F = np.asfortranarray(rng.random((N, 6)) + 1j * rng.random((N, 6)))
+    np.save(os.path.join(tmp, "F.npy"), F)
+    io.write_mat_dense(os.path.join(tmp, "F_hat"), F)
+    io.write_vec(os.path.join(tmp, "q0"), F[:, 0])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_io_worker, args=(r, 2, port, tmp, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+# ------------------------------------------------------------------------------------------------------ GPU, 2 ranks
+def _torchrun(tmp, nproc=2, port=29541, layout=None):
+    env = dict(os.environ)
+    if layout is not None:
+        env["RSVDT_LAYOUT"] = str(layout)
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+                           "--master-addr", "127.0.0.1", "--master-port", str(port),
+                           os.path.join(ROOT, "rsvd-delta-t_b200", "rsvdt_mpi.py"), "-inputs", "variables.yaml"],
+                          cwd=tmp, capture_output=True, text=True, timeout=900, env=env)
+
+
+def _read_modes(io, res, k, Nw_eff, opt):
+    if opt == 1:
+        U = np.stack([io.read_mat_dense(f"{res}/U_hat_k{j + 1}_allFreqs") for j in range(k)], axis=2)
+        V = np.stack([io.read_mat_dense(f"{res}/V_hat_k{j + 1}_allFreqs") for j in range(k)], axis=2)
+    else:
+        U = np.stack([io.read_mat_dense(f"{res}/U_hat_Freq{iw}_allK") for iw in range(Nw_eff)], axis=1)
+        V = np.stack([io.read_mat_dense(f"{res}/V_hat_Freq{iw}_allK") for iw in range(Nw_eff)], axis=1)
+    return U, V
+
+
+@pytest.mark.gpu
+def test_mpi_driver_two_gpus_matches_reference_executable(pkg, tmp_path):
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    io = pkg.petsc_io
+    g = np.load(os.path.join(GOLDEN, "ref_gl_executable.npz"))
+    k, Nw = 3, 8
+    F = pkg.synthetic.random_forcing(500, k, Nw, seed=3)
+    # ---- whole solves, TR on (SaveResultsOpt 1) and off (2)
+    for tag, opt in (("tr", 1), ("notr", 2)):
+        tmp = str(tmp_path / tag)
+        os.makedirs(os.path.join(tmp, "results"))
+        write_case_files(io, tmp, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", F)})
+        open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(
+            root=tmp, Nw=Nw, w=0.6, TL=1.0, TR="true" if tag == "tr" else "false", opt=opt, transrun="false", q=1,
+            disc="true", weights="false"))
+        out = _torchrun(tmp, layout=1 if tag == "tr" else 0)      # both local layouts (banded halo / general ghosts)
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+        assert "Based on the input forcing: k = 3" in out.stdout and "Rows partitioned over 2 GPUs" in out.stdout
+        assert f"local layout {1 if tag == 'tr' else 0}" in out.stdout
+        res = os.path.join(tmp, "results", "ResolventModes_0")
+        assert set(os.listdir(res)) == set(str(f) for f in g[f"small_files_{tag}"])
+        S = io.read_mat_dense(f"{res}/S_hat")
+        assert np.abs(S.imag).max() == 0 and np.abs(S.real / g[f"small_S_{tag}"].real - 1).max() <= 1e-8
+        U, V = _read_modes(io, res, k, Nw, opt)
+        for iw in range(Nw):
+            for j in range(k):
+                assert principal_angle(U[:, iw, j:j + 1], g[f"small_U_{tag}"][:, iw, j:j + 1]) <= 1e-6
+                assert principal_angle(V[:, iw, j:j + 1], g[f"small_V_{tag}"][:, iw, j:j + 1]) <= 1e-6
+    # ---- transient run
+    tmp = str(tmp_path / "trans")
+    os.makedirs(os.path.join(tmp, "results"))
+    write_case_files(io, tmp, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", np.zeros((500, 8), complex)),
+                               "results/q0": ("vec", g["trans_q0"])})
+    open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(
+        root=tmp, Nw=8, w=0.6, TL=1.0, TR="false", opt=1, transrun="true", q=1, disc="true", weights="false"))
+    out = _torchrun(tmp, port=29542)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    res = os.path.join(tmp, "results", "TransientSnapshots_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g["trans_files"])
+    assert np.allclose(io.read_vec(f"{res}/q_transient_norms").real, g["trans_norms"], rtol=1e-11)
+    assert rel_err(io.read_vec(f"{res}/q_transient_last_snapshot"), g["trans_last"]) < 1e-11
+    assert rel_err(io.read_vec(f"{res}/q_transient_2"), g["trans_q2"]) < 1e-11
+    # ---- weighted solve: B, C, W_f^{-1/2}, W_q^{1/2}, W_q^{-1/2} row-partitioned
+    gw = np.load(os.path.join(GOLDEN, "ref_gl_weighted.npz"))
+    kw, Nww = int(gw["k"]), int(gw["Nw"])
+    mats, shapes = weight_mats(500)
+    tmp = str(tmp_path / "weighted")
+    os.makedirs(os.path.join(tmp, "results"))
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", gw["F"])}
+    for n in mats:
+        files[n] = ("csr", shapes[n], mats[n])
+    write_case_files(io, tmp, files)
+    open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(
+        root=tmp, Nw=Nww, w=1.0, TL=1.0, TR="false", opt=2, transrun="false", q=1, disc="false", weights="true"))
+    out = _torchrun(tmp, port=29543)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    S = io.read_mat_dense(f"{res}/S_hat")
+    assert np.abs(S.real / gw["S_hat"].real - 1).max() <= 1e-8
+    U, V = _read_modes(io, res, kw, Nww, 2)
+    assert U.shape == gw["U_hat"].shape and V.shape == gw["V_hat"].shape
+    for iw in range(Nww):
+        assert principal_angle(U[:, iw, :1], gw["U_hat"][:, iw, :1]) <= 1e-6
+        assert principal_angle(V[:, iw, :1], gw["V_hat"][:, iw, :1]) <= 1e-6
