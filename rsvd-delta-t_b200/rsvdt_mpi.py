@@ -205,11 +205,19 @@ class Run:
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-        if not torch.cuda.is_available():
-            raise UserError("no usable CUDA device (this build has no CPU fallback)")
-        torch.cuda.set_device(self.local_rank)
+        # RSVDT_MPI_HOSTONLY=1 is a dry run of the host logic for the CPU tests (gloo): inputs are parsed and partitioned, and
+        # the run stops where the first CUDA handle would be created -- there is no CPU fallback for the numerics.
+        self.hostonly = os.environ.get("RSVDT_MPI_HOSTONLY") == "1"
+        self.dev = "cpu" if self.hostonly else "cuda"
+        if not self.hostonly:
+            if not torch.cuda.is_available():
+                raise UserError("no usable CUDA device (this build has no CPU fallback)")
+            torch.cuda.set_device(self.local_rank)
         if not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            if self.hostonly:
+                dist.init_process_group("gloo")
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         self.pkg = entry.load_package()
         self.io = self.pkg.petsc_io
         self.argv = argv
@@ -238,12 +246,12 @@ class Run:
         rp, cg, va = rd.rows(r0, r1)
         rows = np.repeat(np.arange(r0, r1, dtype=np.int64), np.diff(rp))
         d = cg - rows
-        ext = torch.tensor([int(-d.min()) if d.size else 0, int(d.max()) if d.size else 0], dtype=torch.int64, device="cuda")
+        ext = torch.tensor([int(-d.min()) if d.size else 0, int(d.max()) if d.size else 0], dtype=torch.int64, device=self.dev)
         dist.all_reduce(ext, op=dist.ReduceOp.MAX)
         lo, hi = max(int(ext[0].item()), 0), max(int(ext[1].item()), 0)
         # the halo mailboxes are sized for k test vectors when the ranks connect, and k comes from the forcing file when
         # there is one (CreateRandomMat.c:30) divided by Nw_eff, which depends on whether A is real (LNSStructure.c:37-44)
-        im2 = torch.tensor([float(np.sum(va.imag ** 2))], dtype=torch.float64, device="cuda")
+        im2 = torch.tensor([float(np.sum(va.imag ** 2))], dtype=torch.float64, device=self.dev)
         dist.all_reduce(im2)
         real = float(im2.item()) ** 0.5 < 1e-12
         if v["InputForcingFlg"] and not v["TransRun"]:
@@ -261,6 +269,10 @@ class Run:
         self.layout, self.band = layout, (lo, hi)
         grid = dict(k=v["k"], Nw=v["Nw"], Ns=v["Ns"], Nt=v["Nt"], ResRatio=v["ResRatio"], dt=v["dt"], w=v["w"],
                     TransientRemoval=v["TransientRemoval"])
+        if self.hostonly:
+            self.log(f"host-only dry run: N = {N}, rows [{r0}, {r1}) on rank {self.rank}, band {lo}/{hi}, layout {layout}, "
+                     f"real = {real}, k = {v['k']}")
+            raise UserError("host-only dry run stops before rsvdt_create (no CPU fallback)")
         self.r, self.plan = pkg.dist.setup_rank(pkg, self.local_rank, N, rd.rows, max_bw, layout, (lo, hi) if layout == 1 else None,
                                                grid, DiscFlg=v["DiscFlg"], beta=v["beta"])
         v["N"] = N
@@ -422,7 +434,7 @@ class Run:
         else:
             self.log("Random vector is generated\n")
             q0 = random_rows(v["RandSeed"], r0, r1, 1)[:, 0]
-            t = self.torch.tensor([float(np.vdot(q0, q0).real)], dtype=self.torch.float64, device="cuda")
+            t = self.torch.tensor([float(np.vdot(q0, q0).real)], dtype=self.torch.float64, device=self.dev)
             self.dist.all_reduce(t)
             q0 = q0 / math.sqrt(float(t.item()))                                      # VecNormalize, :93
         folder = v["FolderDir"]

@@ -196,6 +196,13 @@ def _torchrun(tmp, nproc=2, port=29541, layout=None):
                           cwd=tmp, capture_output=True, text=True, timeout=900, env=env)
 
 
+def _diag(out):
+    """the part of a failed torchrun's output that matters: the first Python traceback of a rank + the driver's own log"""
+    err = out.stderr
+    i = err.find("Traceback")
+    return "\n--- stdout tail ---\n" + out.stdout[-1500:] + "\n--- first traceback ---\n" + (err[i:i + 4000] if i >= 0 else err[-4000:])
+
+
 def _read_modes(io, res, k, Nw_eff, opt):
     if opt == 1:
         U = np.stack([io.read_mat_dense(f"{res}/U_hat_k{j + 1}_allFreqs") for j in range(k)], axis=2)
@@ -206,56 +213,72 @@ def _read_modes(io, res, k, Nw_eff, opt):
     return U, V
 
 
-@pytest.mark.gpu
-def test_mpi_driver_two_gpus_matches_reference_executable(pkg, tmp_path):
+def _need_two_gpus():
     if not torch.cuda.is_available():
         pytest.fail("CUDA device required")
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,opt,layout", [("tr", 1, 1), ("notr", 2, 0)])
+def test_mpi_driver_two_gpus_full_solve_matches_reference_executable(pkg, tmp_path, tag, opt, layout):
+    # whole solves, TR on (SaveResultsOpt 1, banded halo layout) and off (SaveResultsOpt 2, general ghost layout)
+    _need_two_gpus()
     io = pkg.petsc_io
     g = np.load(os.path.join(GOLDEN, "ref_gl_executable.npz"))
     k, Nw = 3, 8
     F = pkg.synthetic.random_forcing(500, k, Nw, seed=3)
-    # ---- whole solves, TR on (SaveResultsOpt 1) and off (2)
-    for tag, opt in (("tr", 1), ("notr", 2)):
-        tmp = str(tmp_path / tag)
-        os.makedirs(os.path.join(tmp, "results"))
-        write_case_files(io, tmp, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", F)})
-        open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(
-            root=tmp, Nw=Nw, w=0.6, TL=1.0, TR="true" if tag == "tr" else "false", opt=opt, transrun="false", q=1,
-            disc="true", weights="false"))
-        out = _torchrun(tmp, layout=1 if tag == "tr" else 0)      # both local layouts (banded halo / general ghosts)
-        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-        assert "Based on the input forcing: k = 3" in out.stdout and "Rows partitioned over 2 GPUs" in out.stdout
-        assert f"local layout {1 if tag == 'tr' else 0}" in out.stdout
-        res = os.path.join(tmp, "results", "ResolventModes_0")
-        assert set(os.listdir(res)) == set(str(f) for f in g[f"small_files_{tag}"])
-        S = io.read_mat_dense(f"{res}/S_hat")
-        assert np.abs(S.imag).max() == 0 and np.abs(S.real / g[f"small_S_{tag}"].real - 1).max() <= 1e-8
-        U, V = _read_modes(io, res, k, Nw, opt)
-        for iw in range(Nw):
-            for j in range(k):
-                assert principal_angle(U[:, iw, j:j + 1], g[f"small_U_{tag}"][:, iw, j:j + 1]) <= 1e-6
-                assert principal_angle(V[:, iw, j:j + 1], g[f"small_V_{tag}"][:, iw, j:j + 1]) <= 1e-6
-    # ---- transient run
-    tmp = str(tmp_path / "trans")
+    tmp = str(tmp_path)
+    os.makedirs(os.path.join(tmp, "results"))
+    write_case_files(io, tmp, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", F)})
+    open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(
+        root=tmp, Nw=Nw, w=0.6, TL=1.0, TR="true" if tag == "tr" else "false", opt=opt, transrun="false", q=1,
+        disc="true", weights="false"))
+    out = _torchrun(tmp, layout=layout, port=29541 + layout)
+    assert out.returncode == 0, _diag(out)
+    assert "Based on the input forcing: k = 3" in out.stdout and "Rows partitioned over 2 GPUs" in out.stdout
+    assert f"local layout {layout}" in out.stdout
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g[f"small_files_{tag}"])
+    S = io.read_mat_dense(f"{res}/S_hat")
+    assert np.abs(S.imag).max() == 0 and np.abs(S.real / g[f"small_S_{tag}"].real - 1).max() <= 1e-8
+    U, V = _read_modes(io, res, k, Nw, opt)
+    for iw in range(Nw):
+        for j in range(k):
+            assert principal_angle(U[:, iw, j:j + 1], g[f"small_U_{tag}"][:, iw, j:j + 1]) <= 1e-6
+            assert principal_angle(V[:, iw, j:j + 1], g[f"small_V_{tag}"][:, iw, j:j + 1]) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_mpi_driver_two_gpus_transient_run_matches_reference_executable(pkg, tmp_path):
+    _need_two_gpus()
+    io = pkg.petsc_io
+    g = np.load(os.path.join(GOLDEN, "ref_gl_executable.npz"))
+    tmp = str(tmp_path)
     os.makedirs(os.path.join(tmp, "results"))
     write_case_files(io, tmp, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", np.zeros((500, 8), complex)),
                                "results/q0": ("vec", g["trans_q0"])})
     open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(
         root=tmp, Nw=8, w=0.6, TL=1.0, TR="false", opt=1, transrun="true", q=1, disc="true", weights="false"))
-    out = _torchrun(tmp, port=29542)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    out = _torchrun(tmp, port=29544)
+    assert out.returncode == 0, _diag(out)
     res = os.path.join(tmp, "results", "TransientSnapshots_0")
     assert set(os.listdir(res)) == set(str(f) for f in g["trans_files"])
     assert np.allclose(io.read_vec(f"{res}/q_transient_norms").real, g["trans_norms"], rtol=1e-11)
     assert rel_err(io.read_vec(f"{res}/q_transient_last_snapshot"), g["trans_last"]) < 1e-11
     assert rel_err(io.read_vec(f"{res}/q_transient_2"), g["trans_q2"]) < 1e-11
-    # ---- weighted solve: B, C, W_f^{-1/2}, W_q^{1/2}, W_q^{-1/2} row-partitioned
+
+
+@pytest.mark.gpu
+def test_mpi_driver_two_gpus_weighted_solve_matches_reference_executable(pkg, tmp_path):
+    # B, C, W_f^{-1/2}, W_q^{1/2}, W_q^{-1/2} row-partitioned (rsvdt_set_weight_csr_local, all-gather per frequency block)
+    _need_two_gpus()
+    io = pkg.petsc_io
     gw = np.load(os.path.join(GOLDEN, "ref_gl_weighted.npz"))
     kw, Nww = int(gw["k"]), int(gw["Nw"])
     mats, shapes = weight_mats(500)
-    tmp = str(tmp_path / "weighted")
+    tmp = str(tmp_path)
     os.makedirs(os.path.join(tmp, "results"))
     files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", gw["F"])}
     for n in mats:
@@ -263,8 +286,8 @@ def test_mpi_driver_two_gpus_matches_reference_executable(pkg, tmp_path):
     write_case_files(io, tmp, files)
     open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(
         root=tmp, Nw=Nww, w=1.0, TL=1.0, TR="false", opt=2, transrun="false", q=1, disc="false", weights="true"))
-    out = _torchrun(tmp, port=29543)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    out = _torchrun(tmp, port=29545)
+    assert out.returncode == 0, _diag(out)
     res = os.path.join(tmp, "results", "ResolventModes_0")
     S = io.read_mat_dense(f"{res}/S_hat")
     assert np.abs(S.real / gw["S_hat"].real - 1).max() <= 1e-8
