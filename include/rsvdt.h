@@ -166,6 +166,9 @@ int rsvdt_dist_get_in_offsets(rsvdt_handle h, int64_t *in_mailbox_row_offset);
  * the caller supplies it (torch.distributed all_reduce over NCCL in the Python host); stream-ordered on `stream`. */
 typedef int (*rsvdt_allreduce_fn)(void *device_ptr, int64_t n_doubles, void *cuda_stream, void *user);
 int rsvdt_set_allreduce(rsvdt_handle h, rsvdt_allreduce_fn fn, void *user);
+/* local layout 1 only: *ok = 1 if this rank's rows of A and A^H can be advanced by the fused band kernel for `nvec` vectors
+ * (host-side check, no communication); the ranks all-reduce it and fall back to layout 0 together if any says 0. */
+int rsvdt_dist_layout_supported(rsvdt_handle h, int nvec, int *ok);
 /* all-gather across ranks of n doubles per rank resident on the device (send: n doubles, recv: nranks*n doubles in rank
  * order), used by the row-partitioned weight / input / output matrices; stream-ordered on `stream`. */
 typedef int (*rsvdt_allgather_fn)(const void *send_device_ptr, void *recv_device_ptr, int64_t n_doubles_per_rank,

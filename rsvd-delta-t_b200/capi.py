@@ -140,6 +140,11 @@ class RSVDt:
         """row partition over GPUs (MATMPIAIJ / VECMPI of the reference); see dist.py"""
         self._ck(lib().rsvdt_dist_init(self._h, C.c_int(rank), C.c_int(nranks), C.c_int(layout)))
 
+    def dist_layout_supported(self, nvec) -> bool:
+        ok = C.c_int()
+        self._ck(lib().rsvdt_dist_layout_supported(self._h, C.c_int(int(nvec)), C.byref(ok)))
+        return bool(ok.value)
+
     def LNSStructure_local(self, N_global, n_own, own0, n_ext, A, AH, real_operator, DiscFlg=False, beta=0.0):
         """LNSStructure.c:23-56 for one rank.  A, AH: (rowptr, col_local, val) of the stored local rows"""
         arrs = []

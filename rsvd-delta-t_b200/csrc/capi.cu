@@ -1419,6 +1419,23 @@ int rsvdt_set_weight_csr_local(rsvdt_handle h, int which, int64_t nrows_global, 
     return RSVDT_OK;
 }
 
+// Row-partitioned runs in local layout 1 advance with the fused band kernel on halo-extended rows; whether this rank's rows of
+// A and A^H qualify (diagonal pattern, tile regularity) is a purely local, host-side question -- answered here without
+// touching the exchange, so that the ranks can agree (all-reduce of *ok) BEFORE the first collective step.
+int rsvdt_dist_layout_supported(rsvdt_handle h, int nvec, int *ok)
+{
+    RS(bind(h));
+    if (!ok || nvec < 1) return fail(h, RSVDT_ERR_ARG, "bad arguments");
+    *ok = 1;
+    if (!h->dist.on || h->dist.layout != 1) return RSVDT_OK;
+    if (!h->A.set || !h->AH.set) return fail(h, RSVDT_ERR_STATE, "operator not set");
+    RS(plan_dia(h, h->A, nvec, 3));
+    const bool a = h->A.plan_ok;
+    RS(plan_dia(h, h->AH, nvec, 3));
+    *ok = (a && h->AH.plan_ok) ? 1 : 0;
+    return RSVDT_OK;
+}
+
 int rsvdt_set_allgather(rsvdt_handle h, rsvdt_allgather_fn fn, void *user)
 {
     RS(bind(h));

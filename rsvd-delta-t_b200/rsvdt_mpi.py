@@ -266,15 +266,28 @@ class Run:
         layout = 1 if (max_bw <= 8 and 8 * max_bw < min_rows) else 0
         if os.environ.get("RSVDT_LAYOUT") in ("0", "1"):          # testing hook: force the local layout
             layout = int(os.environ["RSVDT_LAYOUT"])
-        self.layout, self.band = layout, (lo, hi)
+        self.band = (lo, hi)
         grid = dict(k=v["k"], Nw=v["Nw"], Ns=v["Ns"], Nt=v["Nt"], ResRatio=v["ResRatio"], dt=v["dt"], w=v["w"],
                     TransientRemoval=v["TransientRemoval"])
         if self.hostonly:
             self.log(f"host-only dry run: N = {N}, rows [{r0}, {r1}) on rank {self.rank}, band {lo}/{hi}, layout {layout}, "
                      f"real = {real}, k = {v['k']}")
             raise UserError("host-only dry run stops before rsvdt_create (no CPU fallback)")
-        self.r, self.plan = pkg.dist.setup_rank(pkg, self.local_rank, N, rd.rows, max_bw, layout, (lo, hi) if layout == 1 else None,
-                                               grid, DiscFlg=v["DiscFlg"], beta=v["beta"])
+        band = (lo, hi)
+        while True:
+            self.r, self.plan = pkg.dist.setup_rank(pkg, self.local_rank, N, rd.rows, max_bw, layout, band if layout == 1 else None,
+                                                   grid, DiscFlg=v["DiscFlg"], beta=v["beta"])
+            if layout == 0:
+                break
+            # layout 1 needs rows the fused band kernel accepts on EVERY rank, for the number of vectors this run advances
+            ok = torch.tensor([int(self.r.dist_layout_supported(1 if v["TransRun"] else v["k"]))], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()):
+                break
+            self.log("Local layout 1 (fused band kernel on halo rows) is not available for this operator; using layout 0")
+            self.r.close()
+            layout = 0
+        self.layout = layout
         v["N"] = N
         v["RealOperator"] = bool(self.r.real_operator)
         v["Nw_eff"] = v["Nw"] // 2 if v["RealOperator"] else v["Nw"]
