@@ -349,9 +349,11 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         arm = cpu_arm(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, 1)
-        v, secs, cores = arm.sample(100)
+        _, probe_s, _ = arm.sample(10)                                  # size the sample for ~12 s of CPU work on this host
+        nsample = int(min(max(12.0 / max(probe_s / 10, 1e-6), 20), 2000))
+        v, secs, cores = arm.sample(nsample)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": arm.kind,
-               "sample": f"1 test vector x 100 forced RK4 steps of the same N=1e6 workload ({secs:.1f} s of CPU work); {arm.what}"}
+               "sample": f"1 test vector x {nsample} forced RK4 steps of the same N=1e6 workload ({secs:.1f} s of CPU work); {arm.what}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
