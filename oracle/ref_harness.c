@@ -382,3 +382,177 @@ EXPORT int ref_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Self-test entry points for the shim's primitives (tests/test_petsc_shim.py checks them against numpy / LAPACK and
+ * against the independent PETSc-binary reader/writer rsvd-delta-t_b200/petsc_io.py).  Not reference code.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* mode 0: y = A x, 1: y = add + A x, 2: y = A^H x, 3: y = add + A^H x; dense != 0 converts A to MATDENSE first */
+EXPORT int shim_mat_mult(PetscInt m, PetscInt n, const PetscInt *rowptr, const PetscInt *col, const PetscScalar *val, int dense, int mode,
+                         const PetscScalar *x, const PetscScalar *add, PetscScalar *y)
+{
+    PetscErrorCode ierr;
+    Mat A;
+    Vec vx, va = NULL, vy;
+    const PetscInt nx = (mode < 2) ? n : m, ny = (mode < 2) ? m : n;
+    if (dense) {
+        ierr = ShimMatCreateDenseFrom(m, n, NULL, &A);CHKERRQ(ierr);
+        PetscInt lda;
+        PetscScalar *a = ShimMatDenseArray(A, &lda);
+        for (PetscInt r = 0; r < m; r++)
+            for (PetscInt p = rowptr[r]; p < rowptr[r + 1]; p++) a[r + lda * col[p]] += val[p];
+    } else {
+        ierr = ShimMatCreateAIJFrom(m, n, rowptr, col, val, &A);CHKERRQ(ierr);
+    }
+    ierr = ShimVecCreateFrom(nx, x, &vx);CHKERRQ(ierr);
+    ierr = ShimVecCreateFrom(ny, NULL, &vy);CHKERRQ(ierr);
+    if (add) { ierr = ShimVecCreateFrom(ny, add, &va);CHKERRQ(ierr); }
+    switch (mode) {
+    case 0: ierr = MatMult(A, vx, vy); break;
+    case 1: ierr = MatMultAdd(A, vx, va, vy); break;
+    case 2: ierr = MatMultHermitianTranspose(A, vx, vy); break;
+    default: ierr = MatMultHermitianTransposeAdd(A, vx, va, vy); break;
+    }
+    CHKERRQ(ierr);
+    memcpy(y, ShimVecArray(vy), (size_t)ny * sizeof(PetscScalar));
+    VecDestroy(&vx); VecDestroy(&vy); VecDestroy(&va); MatDestroy(&A);
+    return 0;
+}
+
+/* op 0: C = A*B (A AIJ m x n, B dense n x c), 1: same with MAT_REUSE_MATRIX into a submatrix view of a wider matrix,
+ * 2: C = A^T * B with A dense (MatTransposeMatMult), 3: in-place MatHermitianTranspose of the AIJ matrix then C = A^H * B */
+EXPORT int shim_mat_mat(int op, PetscInt m, PetscInt n, const PetscInt *rowptr, const PetscInt *col, const PetscScalar *val, PetscInt c,
+                        const PetscScalar *B, PetscScalar *Cout)
+{
+    PetscErrorCode ierr;
+    Mat A, Bm, Cm = NULL, Wide = NULL, Sub = NULL;
+    ierr = ShimMatCreateAIJFrom(m, n, rowptr, col, val, &A);CHKERRQ(ierr);
+    if (op == 0 || op == 1) {
+        ierr = ShimMatCreateDenseFrom(n, c, B, &Bm);CHKERRQ(ierr);
+        if (op == 0) {
+            ierr = MatMatMult(A, Bm, MAT_INITIAL_MATRIX, PETSC_DEFAULT, &Cm);CHKERRQ(ierr);
+            copy_out(Cm, Cout);
+        } else {
+            ierr = ShimMatCreateDenseFrom(m, c + 3, NULL, &Wide);CHKERRQ(ierr);
+            ierr = MatDenseGetSubMatrix(Wide, PETSC_DECIDE, PETSC_DECIDE, 2, 2 + c, &Sub);CHKERRQ(ierr);
+            ierr = MatMatMult(A, Bm, MAT_REUSE_MATRIX, PETSC_DEFAULT, &Sub);CHKERRQ(ierr);
+            copy_out(Sub, Cout);
+            ierr = MatDenseRestoreSubMatrix(Wide, &Sub);CHKERRQ(ierr);
+        }
+    } else if (op == 2) {
+        Mat Ad;
+        ierr = ShimMatCreateDenseFrom(m, n, NULL, &Ad);CHKERRQ(ierr);
+        PetscInt lda;
+        PetscScalar *a = ShimMatDenseArray(Ad, &lda);
+        for (PetscInt r = 0; r < m; r++)
+            for (PetscInt p = rowptr[r]; p < rowptr[r + 1]; p++) a[r + lda * col[p]] += val[p];
+        ierr = ShimMatCreateDenseFrom(m, c, B, &Bm);CHKERRQ(ierr);
+        ierr = MatTransposeMatMult(Ad, Bm, MAT_INITIAL_MATRIX, PETSC_DEFAULT, &Cm);CHKERRQ(ierr);
+        copy_out(Cm, Cout);
+        MatDestroy(&Ad);
+    } else {
+        ierr = ShimMatCreateDenseFrom(m, c, B, &Bm);CHKERRQ(ierr);
+        ierr = MatHermitianTranspose(A, MAT_INPLACE_MATRIX, &A);CHKERRQ(ierr);
+        ierr = MatMatMult(A, Bm, MAT_INITIAL_MATRIX, PETSC_DEFAULT, &Cm);CHKERRQ(ierr);
+        copy_out(Cm, Cout);
+    }
+    MatDestroy(&A); MatDestroy(&Bm); MatDestroy(&Cm); MatDestroy(&Wide);
+    return 0;
+}
+
+/* KSPSolve on a dense n x n system, in place on b like GalerkinProj.c:61 */
+EXPORT int shim_ksp_solve(PetscInt n, const PetscScalar *A, PetscScalar *b)
+{
+    PetscErrorCode ierr;
+    Mat Am;
+    Vec vb;
+    KSP ksp;
+    ierr = ShimMatCreateDenseFrom(n, n, A, &Am);CHKERRQ(ierr);
+    ierr = ShimVecCreateFrom(n, b, &vb);CHKERRQ(ierr);
+    ierr = KSPCreate(PETSC_COMM_WORLD, &ksp);CHKERRQ(ierr);
+    ierr = KSPSetOperators(ksp, Am, Am);CHKERRQ(ierr);
+    ierr = KSPSetType(ksp, KSPPGMRES);CHKERRQ(ierr);
+    ierr = KSPSetTolerances(ksp, 1.e-15, PETSC_DEFAULT, PETSC_DEFAULT, PETSC_DEFAULT);CHKERRQ(ierr);
+    ierr = KSPSolve(ksp, vb, vb);CHKERRQ(ierr);
+    memcpy(b, ShimVecArray(vb), (size_t)n * sizeof(PetscScalar));
+    KSPDestroy(&ksp); VecDestroy(&vb); MatDestroy(&Am);
+    return 0;
+}
+
+/* w = alpha x + y (VecWAXPY), then y += beta w (VecAXPY), then w = x + gamma w (VecAYPX); norm2 of w returned */
+EXPORT int shim_vec_ops(PetscInt n, const PetscScalar *x, PetscScalar *y, PetscScalar *w, double ar, double ai, double br, double bi, double gr, double gi, double *nrm)
+{
+    PetscErrorCode ierr;
+    Vec vx, vy, vw;
+    ierr = ShimVecCreateFrom(n, x, &vx);CHKERRQ(ierr);
+    ierr = ShimVecCreateFrom(n, y, &vy);CHKERRQ(ierr);
+    ierr = ShimVecCreateFrom(n, NULL, &vw);CHKERRQ(ierr);
+    ierr = VecWAXPY(vw, ar + ai * PETSC_i, vx, vy);CHKERRQ(ierr);
+    ierr = VecAXPY(vy, br + bi * PETSC_i, vw);CHKERRQ(ierr);
+    ierr = VecAYPX(vw, gr + gi * PETSC_i, vx);CHKERRQ(ierr);
+    ierr = VecNorm(vw, NORM_2, nrm);CHKERRQ(ierr);
+    memcpy(y, ShimVecArray(vy), (size_t)n * sizeof(PetscScalar));
+    memcpy(w, ShimVecArray(vw), (size_t)n * sizeof(PetscScalar));
+    VecDestroy(&vx); VecDestroy(&vy); VecDestroy(&vw);
+    return 0;
+}
+
+/* MatLoad (as MATMPIAIJ or MATDENSE) + optional MatShift + MatView, and VecLoad + VecView: file round trips */
+EXPORT int shim_mat_roundtrip(const char *in, const char *out, int as_dense, double shift)
+{
+    PetscErrorCode ierr;
+    PetscViewer fi, fo;
+    Mat A;
+    ierr = PetscViewerBinaryOpen(PETSC_COMM_WORLD, in, FILE_MODE_READ, &fi);CHKERRQ(ierr);
+    ierr = MatCreate(PETSC_COMM_WORLD, &A);CHKERRQ(ierr);
+    ierr = MatSetType(A, as_dense ? MATDENSE : MATMPIAIJ);CHKERRQ(ierr);
+    ierr = MatLoad(A, fi);CHKERRQ(ierr);
+    if (shift != 0.0) { ierr = MatShift(A, shift);CHKERRQ(ierr); }
+    ierr = PetscViewerBinaryOpen(PETSC_COMM_WORLD, out, FILE_MODE_WRITE, &fo);CHKERRQ(ierr);
+    ierr = MatView(A, fo);CHKERRQ(ierr);
+    PetscViewerDestroy(&fi); PetscViewerDestroy(&fo); MatDestroy(&A);
+    return 0;
+}
+
+EXPORT int shim_vec_roundtrip(const char *in, const char *out)
+{
+    PetscErrorCode ierr;
+    PetscViewer fi, fo;
+    Vec v;
+    ierr = PetscViewerBinaryOpen(PETSC_COMM_WORLD, in, FILE_MODE_READ, &fi);CHKERRQ(ierr);
+    ierr = VecCreate(PETSC_COMM_WORLD, &v);CHKERRQ(ierr);
+    ierr = VecLoad(v, fi);CHKERRQ(ierr);
+    ierr = PetscViewerBinaryOpen(PETSC_COMM_WORLD, out, FILE_MODE_WRITE, &fo);CHKERRQ(ierr);
+    ierr = VecView(v, fo);CHKERRQ(ierr);
+    PetscViewerDestroy(&fi); PetscViewerDestroy(&fo); VecDestroy(&v);
+    return 0;
+}
+
+/* options database: insert a YAML file, then look one key up as string / bool / int / real (type 0..3).
+ * returns 0 and *set; value as text in buf */
+EXPORT int shim_option_lookup(const char *yaml, const char *key, int type, int *set, char *buf, PetscInt buflen)
+{
+    PetscErrorCode ierr;
+    PetscBool flg = PETSC_FALSE;
+    ierr = PetscOptionsClear(NULL);CHKERRQ(ierr);
+    ierr = PetscOptionsInsertFileYAML(PETSC_COMM_WORLD, NULL, yaml, PETSC_TRUE);CHKERRQ(ierr);
+    buf[0] = 0;
+    if (type == 0) {
+        ierr = PetscOptionsGetString(NULL, NULL, key, buf, (size_t)buflen, &flg);CHKERRQ(ierr);
+    } else if (type == 1) {
+        PetscBool v = PETSC_FALSE;
+        ierr = PetscOptionsGetBool(NULL, NULL, key, &v, &flg);CHKERRQ(ierr);
+        snprintf(buf, (size_t)buflen, "%d", (int)v);
+    } else if (type == 2) {
+        PetscInt v = 0;
+        ierr = PetscOptionsGetInt(NULL, NULL, key, &v, &flg);CHKERRQ(ierr);
+        snprintf(buf, (size_t)buflen, "%lld", (long long)v);
+    } else {
+        PetscReal v = 0;
+        ierr = PetscOptionsGetReal(NULL, NULL, key, &v, &flg);CHKERRQ(ierr);
+        snprintf(buf, (size_t)buflen, "%.17g", v);
+    }
+    *set = (int)flg;
+    ierr = PetscOptionsClear(NULL);CHKERRQ(ierr);
+    return 0;
+}
