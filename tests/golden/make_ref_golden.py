@@ -197,8 +197,47 @@ def tutorial():
     print("written ref_gl_tutorial.npz")
 
 
+# ---------------------------------------------------------------------------------------------- 5. LNS-type operators
+def lns():
+    """Block-stencil operators of the BASELINE.json configs[2..4] kind (5 variables per grid point, 9- / 27-point stencil, dense
+    5x5 coupling blocks; the operators the block-CSR stage kernel is for), small enough for the reference code: actions in
+    both directions, with and without transient removal, and a whole solve through the executable for the 3-D one."""
+    out = {}
+    for tag, shape in (("2d", (9, 11)), ("3d", (4, 5, 6))):
+        n, rp, ci, va = pkg.synthetic.lns_stencil(shape, nvar=5, complex_coupling=True)
+        A = O.Csr(n, n, rp, ci, va)
+        k, Nw, w = 4, 8, 2.0
+        dt, Ns, Nt, RR = R.setup_time_freq_grid(w, Nw, 0.003, 0.5)
+        F = pkg.synthetic.random_forcing(n, k, Nw, seed=3)
+        out[f"{tag}_shape"] = np.array(shape)
+        out[f"{tag}_val_sha256"] = sha(va)
+        out[f"{tag}_F_sha256"] = sha(F)
+        out[f"{tag}_grid"] = np.array([dt, Ns, Nt, RR])
+        for TR in (False, True):
+            for direct in (True, False):
+                v = O.Vars(N=n, k=k, Nw=Nw, Nw_eff=Nw, Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=w, TransientRemoval=TR, DirAdj=direct)
+                out[f"{tag}_Y_{'direct' if direct else 'adjoint'}_{'tr' if TR else 'notr'}"] = R.ts_action_rk4(A, v, F)
+        if tag == "3d":
+            tmp = tempfile.mkdtemp(prefix="refgold_")
+            os.makedirs(os.path.join(tmp, "results"))
+            io.write_mat_aij(os.path.join(tmp, "A_GL"), n, n, rp, ci, va)          # SMALL_YAML names the operator file A_GL
+            io.write_mat_dense(os.path.join(tmp, "F_hat"), F)
+            with open(os.path.join(tmp, "variables.yaml"), "w") as f:
+                f.write(SMALL_YAML.format(root=tmp, Nw=Nw, w=w, TL=0.5, TR="true", opt=2, transrun="false", q=1, disc="false",
+                                          weights="false"))
+            res = R.run_executable(tmp)
+            assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+            rd = os.path.join(tmp, "results", "ResolventModes_0")
+            out["3d_S_hat"] = io.read_mat_dense(f"{rd}/S_hat")
+            U, V = read_modes(rd, k, Nw, 2)
+            out["3d_U_lead"], out["3d_V_lead"] = U[:, :, 0].copy(), V[:, :, 0].copy()
+            shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(HERE, "ref_lns_functions.npz"), **out)
+    print("written ref_lns_functions.npz")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "weighted", "executable", "tutorial"]
+    which = sys.argv[1:] or ["functions", "weighted", "executable", "tutorial", "lns"]
     if "functions" in which:
         small_functions()
     if "weighted" in which:
@@ -207,3 +246,5 @@ if __name__ == "__main__":
         executable()
     if "tutorial" in which:
         tutorial()
+    if "lns" in which:
+        lns()

@@ -201,6 +201,36 @@ def test_oracle_tutorial_matches_reference_executable(O, pkg, A_GL):
         assert principal_angle(g["V_lead"][:, iw:iw + 1], V[:, iw * k:iw * k + 1]) <= ANGLE_TOL
 
 
+def _lns_case(pkg, O, g, tag):
+    shape = tuple(int(x) for x in g[f"{tag}_shape"])
+    n, rp, ci, va = pkg.synthetic.lns_stencil(shape, nvar=5, complex_coupling=True)
+    assert _sha(va) == str(g[f"{tag}_val_sha256"])                  # the generator still produces the operator of the fixture
+    F = pkg.synthetic.random_forcing(n, 4, 8, seed=3)
+    assert _sha(F) == str(g[f"{tag}_F_sha256"])
+    return O.Csr(n, n, rp, ci, va), F
+
+
+@pytest.mark.parametrize("tag", ["2d", "3d"])
+def test_oracle_lns_operators_match_reference(O, pkg, tag):
+    # block-stencil operators (5 variables x 9 / 27 points), the kind BASELINE.json configs[2..4] name
+    g = _load("ref_lns_functions.npz")
+    A, F = _lns_case(pkg, O, g, tag)
+    for TR in (False, True):
+        for direct in (True, False):
+            v = _vars(O, g, f"{tag}_grid", N=A.nrows, k=4, Nw=8, Nw_eff=8, w=2.0, TransientRemoval=TR, DirAdj=direct)
+            dft, idft = O.create_dft_idft_mats(8, 8, v.Ns, False, True)
+            got = O.ts_action_rk4(A if direct else A.hermitian_transpose(), v, dft, idft, F)
+            ref = g[f"{tag}_Y_{'direct' if direct else 'adjoint'}_{'tr' if TR else 'notr'}"]
+            assert rel_err(got, ref) < (1e-9 if TR else ROUND)
+    if tag == "3d":                                                  # the whole solve the reference executable wrote
+        v = _vars(O, g, "3d_grid", N=A.nrows, k=4, Nw=8, Nw_eff=8, w=2.0, TransientRemoval=True)
+        S, U, V = O.full_solve(A, v, 1, F, faithful_twiddles=True)
+        assert np.abs(S[0] / g["3d_S_hat"].real[0] - 1).max() < GAIN_TOL
+        for iw in range(8):
+            assert principal_angle(g["3d_U_lead"][:, iw:iw + 1], U[:, iw * 4:iw * 4 + 1]) <= ANGLE_TOL
+            assert principal_angle(g["3d_V_lead"][:, iw:iw + 1], V[:, iw * 4:iw * 4 + 1]) <= ANGLE_TOL
+
+
 # ========================================================================= CPU, live: oracle vs reference code if built
 def _ref():
     from oracle import ref as R
@@ -323,6 +353,44 @@ def test_cuda_weighted_actions_match_reference_code(pkg, O, A_GL):
     r.AdjointActionRK4()
     assert rel_err(r.get_Y_hat(), g["Y_adjoint"]) < ACTION_TOL
     r.close()
+
+
+@gpu
+@pytest.mark.parametrize("tag", ["2d", "3d"])
+@pytest.mark.parametrize("opts", [{}, dict(use_bcsr=0)])
+def test_cuda_lns_operators_match_reference_code(pkg, O, tag, opts):
+    # the block-CSR stage kernel (and the plain CSR one) on block-stencil operators against the reference's own code
+    _need_gpu()
+    g = _load("ref_lns_functions.npz")
+    A, F = _lns_case(pkg, O, g, tag)
+    for TR in (False, True):
+        v = _vars(O, g, f"{tag}_grid", N=A.nrows, k=4, Nw=8, Nw_eff=8, w=2.0, TransientRemoval=TR)
+        r = _handle(pkg, A, v)
+        r.set_option("use_small", 0)
+        for name, val in opts.items():
+            r.set_option(name, val)
+        t = "tr" if TR else "notr"
+        assert rel_err(r.TSActionRK4(F, direct=True), g[f"{tag}_Y_direct_{t}"]) < ACTION_TOL
+        assert rel_err(r.TSActionRK4(F, direct=False), g[f"{tag}_Y_adjoint_{t}"]) < ACTION_TOL
+        r.close()
+
+
+@gpu
+def test_driver_lns_3d_solve_matches_reference_executable(pkg, O, tmp_path):
+    _need_gpu()
+    g = _load("ref_lns_functions.npz")
+    A, F = _lns_case(pkg, O, g, "3d")
+    tmp = str(tmp_path)
+    files = {"A_GL": ("csr", (A.nrows, A.ncols), (A.rowptr, A.col, A.val)), "F_hat": ("dense", F)}
+    _run_driver(tmp, SMALL_YAML, files, pkg, Nw=8, w=2.0, TL=0.5, TR="true", opt=2, transrun="false", q=1, disc="false",
+                weights="false")
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    S = pkg.petsc_io.read_mat_dense(f"{res}/S_hat")
+    assert np.abs(S.real[0] / g["3d_S_hat"].real[0] - 1).max() <= GAIN_TOL
+    U, V = _read_modes(pkg.petsc_io, res, 4, 8, 2)
+    for iw in range(8):
+        assert principal_angle(U[:, iw, :1], g["3d_U_lead"][:, iw:iw + 1]) <= ANGLE_TOL
+        assert principal_angle(V[:, iw, :1], g["3d_V_lead"][:, iw:iw + 1]) <= ANGLE_TOL
 
 
 # ------------------------------------------------------------------------------- GPU: the drop-in executable `RSVDt`
