@@ -185,6 +185,28 @@ def test_partitioned_io_and_weight_split_world2(pkg, tmp_path):
     assert all(r[1] == "ok" for r in res), res
 
 
+def test_driver_host_logic_dry_run_world2(pkg, tmp_path):
+    # the executable itself under torchrun with 2 gloo ranks: inputs parsed, operator partitioned, band / layout / k decided
+    # collectively -- and a loud stop where the first CUDA handle would be created (there is no CPU fallback)
+    io = pkg.petsc_io
+    tmp = str(tmp_path)
+    os.makedirs(os.path.join(tmp, "results"))
+    F = pkg.synthetic.random_forcing(500, 3, 8, seed=3)
+    write_case_files(io, tmp, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", F)})
+    open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(
+        root=tmp, Nw=8, w=0.6, TL=1.0, TR="true", opt=1, transrun="false", q=1, disc="true", weights="false"))
+    env = dict(os.environ, RSVDT_MPI_HOSTONLY="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29700 + os.getpid() % 200),
+                          os.path.join(ROOT, "rsvd-delta-t_b200", "rsvdt_mpi.py"), "-inputs", "variables.yaml"],
+                         cwd=tmp, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode != 0
+    assert "@ Ns              = 3496" in out.stdout and "Transient removal strategy is requested" in out.stdout
+    assert "host-only dry run: N = 500, rows [0, 250) on rank 0, band 3/3, layout 1, real = False, k = 3" in out.stdout
+    assert "host-only dry run stops before rsvdt_create (no CPU fallback)" in out.stderr
+    assert not os.listdir(os.path.join(tmp, "results"))              # nothing was computed or written
+
+
 # ------------------------------------------------------------------------------------------------------ GPU, 2 ranks
 def _torchrun(tmp, nproc=2, port=29541, layout=None):
     env = dict(os.environ)
