@@ -267,3 +267,40 @@ class VecWriter:
         with open(self.path, "r+b") as f:
             f.seek(2 * self.isz + r0 * 16)
             f.write(_scalars(v))
+
+
+class AijStreamWriter:
+    """Writes a binary AIJ Mat record from row blocks that arrive in order, without holding the matrix: the three sections
+    (row lengths, column indices, values) are streamed to side files and concatenated behind the header on close()."""
+
+    def __init__(self, path: str, M: int, N: int, int64: bool = True):
+        self.path, self.M, self.N = path, int(M), int(N)
+        self.it = ">i8" if int64 else ">i4"
+        self.parts = [open(path + ext, "wb") for ext in (".rl", ".ci", ".va")]
+        self.rows = 0
+        self.nnz = 0
+
+    def append_rows(self, rowptr, col, val) -> None:
+        rowptr = np.asarray(rowptr, np.int64)
+        n = int(rowptr[-1] - rowptr[0])
+        self.parts[0].write(np.diff(rowptr).astype(self.it).tobytes())
+        self.parts[1].write(np.asarray(col)[:n].astype(self.it).tobytes())
+        self.parts[2].write(_scalars(np.asarray(val)[:n]))
+        self.rows += rowptr.size - 1
+        self.nnz += n
+
+    def close(self) -> None:
+        for f in self.parts:
+            f.close()
+        if self.rows != self.M:
+            raise ValueError(f"{self.rows} rows written, {self.M} announced")
+        with open(self.path, "wb") as out:
+            out.write(np.asarray([MAT_FILE_CLASSID, self.M, self.N, self.nnz]).astype(self.it).tobytes())
+            for ext in (".rl", ".ci", ".va"):
+                with open(self.path + ext, "rb") as f:
+                    while True:
+                        buf = f.read(1 << 26)
+                        if not buf:
+                            break
+                        out.write(buf)
+                os.remove(self.path + ext)

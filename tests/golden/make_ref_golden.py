@@ -236,8 +236,28 @@ def lns():
     print("written ref_lns_functions.npz")
 
 
+# ---------------------------------------------------------------------------------------------- 6. a generated case directory
+def case():
+    """tools/make_case.py (config 5 in miniature: 3-D block stencil, selection-type B and C, diagonal weights, transient
+    removal, q = 1) run by the reference executable exactly as written to disk."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_case
+    tmp = tempfile.mkdtemp(prefix="refgold_")
+    info = make_case.write_case(pkg, tmp, "lns3d", shape=(4, 5, 6), k=3, Nw=4, w=2.0, TL=0.5, TR=True, q=1, opt=2, weights=True,
+                                forcing=True)
+    res = R.run_executable(tmp)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    rd = os.path.join(tmp, "results", "ResolventModes_0")
+    U, V = read_modes(rd, 3, 4, 2)
+    out = {"S_hat": io.read_mat_dense(f"{rd}/S_hat"), "U_hat": U, "V_hat": V, "Nb": info["Nb"], "Nc": info["Nc"],
+           "A_sha256": hashlib.sha256(open(os.path.join(tmp, "A"), "rb").read()).hexdigest()}
+    shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(HERE, "ref_lns_case.npz"), **out)
+    print("written ref_lns_case.npz")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "weighted", "executable", "tutorial", "lns"]
+    which = sys.argv[1:] or ["functions", "weighted", "executable", "tutorial", "lns", "case"]
     if "functions" in which:
         small_functions()
     if "weighted" in which:
@@ -248,3 +268,5 @@ if __name__ == "__main__":
         tutorial()
     if "lns" in which:
         lns()
+    if "case" in which:
+        case()
