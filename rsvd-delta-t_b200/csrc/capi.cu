@@ -1118,6 +1118,7 @@ int apply_sparse_to(rsvdt_handle h, const CsrOwned &M, DevBuf &X, int64_t &xrows
     const int64_t want = part ? M.in_rows_local : M.d.ncols;
     if (xrows != want) return fail(h, RSVDT_ERR_ARG, "weight matrix expects %lld rows, the matrix it multiplies has %lld", (long long)want, (long long)xrows);
     DevBuf out;
+    struct Release { DevBuf &b; ~Release() { b.release(); } } release_out{out};   // the product on failure, the old X on success
     if (!part) {
         CU(out.alloc(stack_bytes(g.Nw_eff, M.d.nrows, g.k)));
         CU(launch_spmm_stack(M.d, X.as<cplx>(), out.as<cplx>(), (int)g.Nw_eff, (int)g.k, h->stream));
@@ -1151,7 +1152,6 @@ int apply_sparse_to(rsvdt_handle h, const CsrOwned &M, DevBuf &X, int64_t &xrows
     CU(cudaStreamSynchronize(h->stream));
     X.swap(out);
     xrows = M.d.nrows;
-    out.release();
     return RSVDT_OK;
 }
 
