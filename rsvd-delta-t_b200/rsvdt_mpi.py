@@ -195,6 +195,11 @@ def hms(sec):
 
 # ---------------------------------------------------------------------------------------------------------- the run
 class Run:
+    # Test seam: a factory standing in for dist.setup_rank.  tests/test_mpi_driver.py sets it (together with
+    # RSVDT_MPI_HOSTONLY=1, i.e. gloo and no CUDA) to drive this file's host logic -- input rules, partitioned I/O, result
+    # files -- on CPU with the oracle as the numerical engine.  The product never sets it.
+    backend = None
+
     def __init__(self, argv):
         import torch
         import torch.distributed as dist
@@ -272,11 +277,13 @@ class Run:
         if self.hostonly:
             self.log(f"host-only dry run: N = {N}, rows [{r0}, {r1}) on rank {self.rank}, band {lo}/{hi}, layout {layout}, "
                      f"real = {real}, k = {v['k']}")
-            raise UserError("host-only dry run stops before rsvdt_create (no CPU fallback)")
+            if Run.backend is None:
+                raise UserError("host-only dry run stops before rsvdt_create (no CPU fallback)")
+        setup_rank = Run.backend if (self.hostonly and Run.backend is not None) else pkg.dist.setup_rank
         band = (lo, hi)
         while True:
-            self.r, self.plan = pkg.dist.setup_rank(pkg, self.local_rank, N, rd.rows, max_bw, layout, band if layout == 1 else None,
-                                                   grid, DiscFlg=v["DiscFlg"], beta=v["beta"])
+            self.r, self.plan = setup_rank(pkg, self.local_rank, N, rd.rows, max_bw, layout, band if layout == 1 else None,
+                                           grid, DiscFlg=v["DiscFlg"], beta=v["beta"])
             if layout == 0:
                 break
             # layout 1 needs rows the fused band kernel accepts on EVERY rank, for the number of vectors this run advances

@@ -207,6 +207,120 @@ def test_driver_host_logic_dry_run_world2(pkg, tmp_path):
     assert not os.listdir(os.path.join(tmp, "results"))              # nothing was computed or written
 
 
+# ------------------------------------------------------------- the whole executable on CPU ranks, oracle as the engine
+def _flow_worker(rank, world, port, tmp, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), RSVDT_MPI_HOSTONLY="1")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import __graft_entry__ as entry
+        entry.load_package()
+        from oracle import oracle as O
+        import fake_backend
+        drv = importlib.import_module("rsvdt_b200.rsvdt_mpi")
+        drv.Run.backend = staticmethod(fake_backend.make_backend(O))
+        os.chdir(tmp)
+        if rank != 0:
+            sys.stdout = open(os.devnull, "w")
+        rc = drv.main(["rsvdt_mpi.py", "-inputs", "variables.yaml"])
+        q.put((rank, rc))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL " + repr(e) + traceback.format_exc()))
+
+
+def _run_flow(tmp, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() * 7 + world) % 150
+    procs = [ctx.Process(target=_flow_worker, args=(r, world, port, tmp, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == 0 for r in res), res
+
+
+def _case_dir(tmp_path, name, pkg, files, **fmt):
+    tmp = str(tmp_path / name)
+    os.makedirs(os.path.join(tmp, "results"))
+    write_case_files(pkg.petsc_io, tmp, files)
+    open(os.path.join(tmp, "variables.yaml"), "w").write(SMALL_YAML.format(root=tmp, **fmt))
+    return tmp
+
+
+@pytest.mark.parametrize("tag,opt,world", [("tr", 1, 3), ("notr", 2, 2)])
+def test_executable_flow_on_cpu_ranks_matches_reference_files(pkg, tmp_path, tag, opt, world):
+    # rsvdt_mpi.py end to end on gloo ranks (uneven PETSC_DECIDE splits for 3 ranks), the oracle standing in for the CUDA
+    # library: input rules, partitioned reads, layout agreement, collective writers -> the reference executable's files
+    io = pkg.petsc_io
+    g = np.load(os.path.join(GOLDEN, "ref_gl_executable.npz"))
+    k, Nw = 3, 8
+    F = pkg.synthetic.random_forcing(500, k, Nw, seed=3)
+    tmp = _case_dir(tmp_path, tag, pkg, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", F)}, Nw=Nw, w=0.6, TL=1.0,
+                    TR="true" if tag == "tr" else "false", opt=opt, transrun="false", q=1, disc="true", weights="false")
+    _run_flow(tmp, world)
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g[f"small_files_{tag}"])
+    S = io.read_mat_dense(f"{res}/S_hat")
+    assert np.abs(S.imag).max() == 0 and np.abs(S.real / g[f"small_S_{tag}"].real - 1).max() <= 1e-10
+    U, V = _read_modes(io, res, k, Nw, opt)
+    assert U.shape == g[f"small_U_{tag}"].shape
+    for iw in range(Nw):
+        for j in range(k):
+            assert principal_angle(U[:, iw, j:j + 1], g[f"small_U_{tag}"][:, iw, j:j + 1]) <= 1e-6
+            assert principal_angle(V[:, iw, j:j + 1], g[f"small_V_{tag}"][:, iw, j:j + 1]) <= 1e-6
+
+
+def test_executable_flow_transient_run_and_weights_on_cpu_ranks(pkg, tmp_path):
+    io = pkg.petsc_io
+    g = np.load(os.path.join(GOLDEN, "ref_gl_executable.npz"))
+    tmp = _case_dir(tmp_path, "trans", pkg, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")),
+                                             "F_hat": ("dense", np.zeros((500, 8), complex)), "results/q0": ("vec", g["trans_q0"])},
+                    Nw=8, w=0.6, TL=1.0, TR="false", opt=1, transrun="true", q=1, disc="true", weights="false")
+    _run_flow(tmp, 3)
+    res = os.path.join(tmp, "results", "TransientSnapshots_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g["trans_files"])
+    assert np.allclose(io.read_vec(f"{res}/q_transient_norms").real, g["trans_norms"], rtol=1e-12)
+    assert rel_err(io.read_vec(f"{res}/q_transient_last_snapshot"), g["trans_last"]) < 1e-12
+    assert rel_err(io.read_vec(f"{res}/q_transient_2"), g["trans_q2"]) < 1e-12
+    # weighted solve, SaveResultsOpt 1 this time (the fixture was written with 2): B 500 x 120, C 90 x 500 over 3 ranks
+    gw = np.load(os.path.join(GOLDEN, "ref_gl_weighted.npz"))
+    kw, Nww = int(gw["k"]), int(gw["Nw"])
+    mats, shapes = weight_mats(500)
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", gw["F"])}
+    for n in mats:
+        files[n] = ("csr", shapes[n], mats[n])
+    tmp = _case_dir(tmp_path, "weighted", pkg, files, Nw=Nww, w=1.0, TL=1.0, TR="false", opt=1, transrun="false", q=1, disc="false",
+                    weights="true")
+    _run_flow(tmp, 3)
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    S = io.read_mat_dense(f"{res}/S_hat")
+    assert np.abs(S.real / gw["S_hat"].real - 1).max() <= 1e-10
+    U, V = _read_modes(io, res, kw, Nww, 1)
+    assert U.shape == gw["U_hat"].shape and V.shape == gw["V_hat"].shape          # 90 x Nw x k, 120 x Nw x k
+    for iw in range(Nww):
+        assert principal_angle(U[:, iw, :1], gw["U_hat"][:, iw, :1]) <= 1e-6
+        assert principal_angle(V[:, iw, :1], gw["V_hat"][:, iw, :1]) <= 1e-6
+
+
+def test_executable_random_forcing_does_not_depend_on_the_rank_count(pkg, tmp_path):
+    # InputForcingFlg: false -> RandSeed-seeded forcing drawn per global row block: 2 and 3 ranks give the same gains
+    io = pkg.petsc_io
+    S = []
+    for world in (2, 3):
+        tmp = _case_dir(tmp_path, f"rand{world}", pkg, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL"))}, Nw=4, w=1.0, TL=0.5,
+                        TR="false", opt=2, transrun="false", q=0, disc="true", weights="false")
+        y = os.path.join(tmp, "variables.yaml")
+        text = open(y).read().replace("InputForcingFlg:    true", "InputForcingFlg:    false").replace("k:                  7", "k:                  2")
+        open(y, "w").write(text)
+        _run_flow(tmp, world)
+        S.append(io.read_mat_dense(os.path.join(tmp, "results", "ResolventModes_0", "S_hat")).real)
+    assert S[0].shape == (2, 4) and np.allclose(S[0], S[1], rtol=1e-11)
+
+
 # ------------------------------------------------------------------------------------------------------ GPU, 2 ranks
 def _torchrun(tmp, nproc=2, port=29541, layout=None):
     env = dict(os.environ)

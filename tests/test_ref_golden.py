@@ -263,6 +263,42 @@ def test_live_oracle_vs_reference_code_on_lns_stencil(O, pkg, seed):
     assert np.array_equal(R.permute_mat(P, 3, reverse=True), Y)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_live_oracle_vs_reference_code_randomised(O, pkg, seed):
+    # random small cases: operator size and sparsity, real / complex operator, even / odd Nw, k, transient removal, direction
+    R = _ref()
+    rng = np.random.default_rng(100 + seed)
+    N = int(rng.integers(6, 60))
+    real = bool(rng.integers(0, 2))
+    Nw = int(rng.choice([2, 4, 6, 8] if real else [2, 3, 4, 5, 7, 8]))
+    Nw_eff = Nw // 2 if real else Nw
+    k = int(rng.integers(1, 4))
+    rp, ci, va = [0], [], []
+    for r in range(N):                                   # random off-diagonal pattern, strictly diagonally dominant (stable)
+        cols = np.unique(np.append(rng.choice(N, size=min(N, int(rng.integers(1, 6))), replace=False), r))
+        v = rng.standard_normal(cols.size) + (0 if real else 1j * rng.standard_normal(cols.size))
+        v = v * (0.4 * 30.0 / max(np.abs(v).sum(), 1e-9))
+        v[cols == r] = -30.0 + (0 if real else 2j * rng.standard_normal())
+        ci.append(cols)
+        va.append(v)
+        rp.append(rp[-1] + cols.size)
+    A = O.Csr(N, N, np.array(rp), np.concatenate(ci), np.concatenate(va).astype(np.complex128))
+    w = float(rng.uniform(1.0, 4.0))
+    grid = O.setup_time_freq_grid(w, Nw, 0.004, 0.3)
+    assert grid == R.setup_time_freq_grid(w, Nw, 0.004, 0.3)
+    dt, Ns, Nt, RR = grid
+    F = pkg.synthetic.random_forcing(N, k, Nw_eff, seed=seed)
+    TR = bool(rng.integers(0, 2)) and N >= Nw + 1        # the trial basis needs Nw+1 independent snapshots
+    for direct in (True, False):
+        v = O.Vars(N=N, k=k, Nw=Nw, Nw_eff=Nw_eff, Ns=Ns, Nt=Nt, ResRatio=RR, dt=dt, w=w, RealOperator=real, TransientRemoval=TR,
+                   DirAdj=direct)
+        dft, idft = O.create_dft_idft_mats(Nw, Nw_eff, Ns, real, True)
+        rd, ri = R.create_dft_idft_mats(v)
+        assert np.array_equal(dft, rd) and np.array_equal(idft, ri)
+        got = O.ts_action_rk4(A if direct else A.hermitian_transpose(), v, dft, idft, F)
+        assert rel_err(got, R.ts_action_rk4(A, v, F)) < (1e-8 if TR else ROUND), (N, real, Nw, k, TR, direct)
+
+
 # ========================================================================================================= GPU: CUDA path
 gpu = pytest.mark.gpu
 
