@@ -241,7 +241,12 @@ class Run:
         path = v["RootDir"] + v["OperatorDir"]
         self.log(f"Loading the operator: {path} ")
         try:
-            rd = self.io.MatRowReader(path)
+            if v["OperatorDir"].startswith("synthetic:"):
+                # an extension for the large BASELINE.json configurations: generate the rows tools/make_case.py would have
+                # written instead of reading a 65 GB file (synthetic.SyntheticRows; same rows, tested)
+                rd = pkg.synthetic.SyntheticRows(v["OperatorDir"][len("synthetic:"):])
+            else:
+                rd = self.io.MatRowReader(path)
         except (OSError, ValueError) as e:
             raise UserError(f"cannot read the operator {path}: {e}")
         if rd.M != rd.N:

@@ -155,3 +155,46 @@ def random_forcing(N: int, k: int, Nw_eff: int, seed: int = 14) -> np.ndarray:
     for c in range(k * Nw_eff):
         F[:, c] = rng.random(N) + 1j * rng.random(N)
     return F
+
+
+class SyntheticRows:
+    """Row source with the interface of petsc_io.MatRowReader (M, N, rows(r0, r1)) that GENERATES the rows of a BASELINE.json
+    operator instead of reading them: `gl:<N>`, `lns2d:<ny>x<nx>`, `lns3d:<nz>x<ny>x<nx>` (5 variables per point).  The
+    multi-GPU executable accepts `OperatorDir: synthetic:<spec>` so that the 2e7-DOF configurations (a 65 GB file) can be run
+    without writing and re-reading the operator; tools/make_case.py writes the very same rows to a PETSc-binary file."""
+
+    def __init__(self, spec: str, nvar: int = 5):
+        kind, _, arg = spec.partition(":")
+        self.kind = kind
+        if kind == "gl":
+            self.M = self.N = int(arg)
+            self.align = 1
+        elif kind in ("lns2d", "lns3d"):
+            self.shape = tuple(int(s) for s in arg.lower().split("x"))
+            if len(self.shape) != (2 if kind == "lns2d" else 3):
+                raise ValueError(f"{spec}: wrong number of grid dimensions")
+            self.nvar = nvar
+            self.M = self.N = int(np.prod(self.shape)) * nvar
+            self.align = nvar
+        else:
+            raise ValueError(f"unknown synthetic operator '{spec}' (gl:<N>, lns2d:<ny>x<nx>, lns3d:<nz>x<ny>x<nx>)")
+
+    def rows(self, r0: int, r1: int):
+        r0, r1 = max(0, int(r0)), min(self.M, int(r1))
+        if getattr(self, "_memo_key", None) == (r0, r1):       # the executable asks for its own range twice in a row
+            return self._memo
+        out = self._rows(r0, r1)
+        self._memo_key, self._memo = (r0, r1), out
+        return out
+
+    def _rows(self, r0: int, r1: int):
+        if r1 <= r0:
+            return np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0, np.complex128)
+        if self.kind == "gl":
+            _, rp, ci, va = ginzburg_landau(self.M, row_range=(r0, r1))
+            return rp, ci, va
+        a = r0 - r0 % self.align
+        b = r1 + (-r1) % self.align
+        _, rp, ci, va = lns_stencil(self.shape, nvar=self.nvar, complex_coupling=True, row_range=(a, b))
+        s, e = rp[r0 - a], rp[r1 - a]
+        return rp[r0 - a: r1 - a + 1] - s, ci[s:e], va[s:e]

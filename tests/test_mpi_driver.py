@@ -321,6 +321,35 @@ def test_executable_random_forcing_does_not_depend_on_the_rank_count(pkg, tmp_pa
     assert S[0].shape == (2, 4) and np.allclose(S[0], S[1], rtol=1e-11)
 
 
+def test_synthetic_operator_rows_equal_the_case_file(pkg, tmp_path):
+    # `OperatorDir: synthetic:lns3d:4x5x6` generates exactly the rows tools/make_case.py streams to the PETSc-binary file,
+    # for arbitrary (unaligned) row ranges; and the executable produces the same gains from either source
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_case
+    io = pkg.petsc_io
+    case = str(tmp_path / "case")
+    make_case.write_case(pkg, case, "lns3d", shape=(4, 5, 6), k=2, Nw=4, w=2.0, TL=0.5, TR=False, q=0, opt=2, forcing=True)
+    rd, sy = io.MatRowReader(os.path.join(case, "A")), pkg.synthetic.SyntheticRows("lns3d:4x5x6")
+    assert (rd.M, rd.N) == (sy.M, sy.N) == (600, 600)
+    for a, b in ((0, 600), (0, 1), (3, 7), (197, 403), (598, 600), (250, 250)):
+        for x, y in zip(rd.rows(a, b), sy.rows(a, b)):
+            assert np.array_equal(x, y)
+    gl = pkg.synthetic.SyntheticRows("gl:1000")
+    _, rp, ci, va = pkg.synthetic.ginzburg_landau(1000)
+    r = gl.rows(123, 777)
+    assert np.array_equal(r[1], ci[rp[123]:rp[777]]) and np.array_equal(r[2], va[rp[123]:rp[777]])
+    with pytest.raises(ValueError):
+        pkg.synthetic.SyntheticRows("lns3d:4x5")
+    _run_flow(case, 2)
+    S_file = io.read_mat_dense(os.path.join(case, "results", "ResolventModes_0", "S_hat")).real
+    y = os.path.join(case, "variables.yaml")
+    text = open(y).read().replace("OperatorDir:        A", "OperatorDir:        synthetic:lns3d:4x5x6")
+    open(y, "w").write(text)
+    _run_flow(case, 3)
+    S_syn = io.read_mat_dense(os.path.join(case, "results", "ResolventModes_1", "S_hat")).real
+    assert S_file.shape == (2, 4) and np.allclose(S_file, S_syn, rtol=1e-11)
+
+
 # ------------------------------------------------------------------------------------------------------ GPU, 2 ranks
 def _torchrun(tmp, nproc=2, port=29541, layout=None):
     env = dict(os.environ)
