@@ -502,7 +502,10 @@ class Run:
             self.io.write_mat_dense(folder + "S_hat", S.astype(np.complex128))
         c0, _ = self.pkg.dist.split_ownership(v["Nc"], self.world, self.rank)
         b0, _ = self.pkg.dist.split_ownership(v["Nb"], self.world, self.rank)
-        if v["SaveResultsOpt"] == 1:
+        if os.environ.get("RSVDT_MPI_SAVE") == "gains":
+            # benchmark runs of the 2e7-DOF configurations: the modes are 2 x 82 GB of output; keep the gains only
+            self.log("RSVDT_MPI_SAVE=gains: the resolvent modes are not written\n")
+        elif v["SaveResultsOpt"] == 1:
             self.log(f"{k} matrices of size {v['Nc']} x {Nwe} for response modes\n{k} matrices of size {v['Nb']} x {Nwe} for forcing modes\n")
             for j in range(k):                                  # mode j across all frequencies: columns iw*k + j
                 self.write_dense(f"{folder}U_hat_k{j + 1}_allFreqs", v["Nc"], Nwe, c0, U[:, j::k])

@@ -342,11 +342,18 @@ def test_synthetic_operator_rows_equal_the_case_file(pkg, tmp_path):
         pkg.synthetic.SyntheticRows("lns3d:4x5")
     _run_flow(case, 2)
     S_file = io.read_mat_dense(os.path.join(case, "results", "ResolventModes_0", "S_hat")).real
-    y = os.path.join(case, "variables.yaml")
-    text = open(y).read().replace("OperatorDir:        A", "OperatorDir:        synthetic:lns3d:4x5x6")
-    open(y, "w").write(text)
-    _run_flow(case, 3)
-    S_syn = io.read_mat_dense(os.path.join(case, "results", "ResolventModes_1", "S_hat")).real
+    syn = str(tmp_path / "syn")                 # the same case without an operator file; gains only (benchmark mode)
+    make_case.write_case(pkg, syn, "lns3d", shape=(4, 5, 6), k=2, Nw=4, w=2.0, TL=0.5, TR=False, q=0, opt=2, forcing=True,
+                         synthetic=True)
+    assert not os.path.exists(os.path.join(syn, "A")) and "synthetic:lns3d:4x5x6" in open(os.path.join(syn, "variables.yaml")).read()
+    os.environ["RSVDT_MPI_SAVE"] = "gains"
+    try:
+        _run_flow(syn, 3)
+    finally:
+        del os.environ["RSVDT_MPI_SAVE"]
+    res = os.path.join(syn, "results", "ResolventModes_0")
+    assert sorted(os.listdir(res)) == ["S_hat", "variables.yaml"]
+    S_syn = io.read_mat_dense(os.path.join(res, "S_hat")).real
     assert S_file.shape == (2, 4) and np.allclose(S_file, S_syn, rtol=1e-11)
 
 

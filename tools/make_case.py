@@ -29,7 +29,7 @@ import __graft_entry__ as entry  # noqa: E402
 YAML = """# written by tools/make_case.py: {desc}
 RootDir:            {root}/
 ResultsDir:         results/
-OperatorDir:        A
+OperatorDir:        {operator}
 k:                  {k}
 q:                  {q}
 Nw:                 {Nw}
@@ -78,7 +78,7 @@ def selection_rows(shape, nvar, box):
 
 
 def write_case(pkg, out, config, n=None, shape=None, k=8, Nw=32, w=2.0, dt=0.003, TL=0.5, TR=False, q=1, opt=1, weights=False,
-               forcing=False, chunk_points=200_000, nvar=5):
+               forcing=False, chunk_points=200_000, nvar=5, synthetic=False):
     io, syn = pkg.petsc_io, pkg.synthetic
     os.makedirs(os.path.join(out, "results"), exist_ok=True)
     if config == "gl":
@@ -96,10 +96,14 @@ def write_case(pkg, out, config, n=None, shape=None, k=8, Nw=32, w=2.0, dt=0.003
         step, real = chunk_points * nvar, False
         desc = f"{nvar} variables x {3 ** len(shape_t)}-point stencil on {'x'.join(map(str, shape_t))}, N = {N}"
         nv = nvar
-    wtr = io.AijStreamWriter(os.path.join(out, "A"), N, N)
-    for a in range(0, N, step):
-        wtr.append_rows(*gen(a, min(N, a + step)))
-    wtr.close()
+    operator = "A"
+    if synthetic:   # rsvdt_mpi.py generates the same rows per rank (synthetic.SyntheticRows); no operator file is written
+        operator = "synthetic:" + (f"gl:{N}" if config == "gl" else f"{config}:" + "x".join(map(str, shape_t)))
+    else:
+        wtr = io.AijStreamWriter(os.path.join(out, "A"), N, N)
+        for a in range(0, N, step):
+            wtr.append_rows(*gen(a, min(N, a + step)))
+        wtr.close()
     Nb = Nc = N
     if weights:
         # B / C select a sub-box (the middle half of every dimension for the forcing, the downstream half of the slowest one
@@ -128,7 +132,7 @@ def write_case(pkg, out, config, n=None, shape=None, k=8, Nw=32, w=2.0, dt=0.003
     b = lambda x: "true" if x else "false"  # noqa: E731
     with open(os.path.join(out, "variables.yaml"), "w") as f:
         f.write(YAML.format(desc=desc, root=os.path.abspath(out), k=k, q=q, Nw=Nw, w=w, TL=TL, dt=dt, TR=b(TR), opt=opt,
-                            forcing=b(forcing), weights=b(weights)))
+                            forcing=b(forcing), weights=b(weights), operator=operator))
     return dict(N=N, Nb=Nb, Nc=Nc, Nw_eff=Nw_eff, desc=desc)
 
 
@@ -148,10 +152,12 @@ def main():
     ap.add_argument("--opt", type=int, default=1, help="SaveResultsOpt")
     ap.add_argument("--weights", action="store_true")
     ap.add_argument("--forcing", action="store_true", help="write F_hat and set InputForcingFlg")
+    ap.add_argument("--synthetic", action="store_true",
+                    help="do not write A: OperatorDir becomes synthetic:<spec>, which rsvdt_mpi.py generates per rank")
     a = ap.parse_args()
     pkg = entry.load_package()
     info = write_case(pkg, a.out, a.config, n=a.n, shape=a.shape, k=a.k, Nw=a.Nw, w=a.w, dt=a.dt, TL=a.TL, TR=a.TR, q=a.q,
-                      opt=a.opt, weights=a.weights, forcing=a.forcing)
+                      opt=a.opt, weights=a.weights, forcing=a.forcing, synthetic=a.synthetic)
     print(f"{a.out}: {info['desc']}; N_b = {info['Nb']}, N_c = {info['Nc']}, Nw_eff = {info['Nw_eff']}")
 
 
