@@ -116,17 +116,26 @@ def localize_banded(plan: Plan, rowptr, col_global, val):
 
 def transpose_slab(rowptr, col, val, row_offset: int, c_lo: int, c_hi: int):
     """rows [c_lo, c_hi) of A^H from a slab of rows of A (global row of slab row i is row_offset + i) that contains
-    every entry with a column in [c_lo, c_hi)."""
+    every entry with a column in [c_lo, c_hi).  The entries arrive row by row, so one STABLE sort by column leaves every
+    row of A^H with ascending columns (a third of the time of a two-key sort at 3e8 entries)."""
     rowptr = np.asarray(rowptr, np.int64)
     col = np.asarray(col, np.int64)
     rows = np.repeat(np.arange(rowptr.size - 1, dtype=np.int64), np.diff(rowptr)) + row_offset
     sel = (col >= c_lo) & (col < c_hi)
     r, c, v = rows[sel], col[sel], np.conj(np.asarray(val)[sel])
-    order = np.lexsort((r, c))
+    order = np.argsort(c, kind="stable")
     r, c, v = r[order], c[order], v[order]
     rp = np.zeros(c_hi - c_lo + 1, np.int64)
     np.cumsum(np.bincount(c - c_lo, minlength=c_hi - c_lo), out=rp[1:])
     return rp, r, v
+
+
+def slice_rows(rowptr, col, val, row_offset: int, r_lo: int, r_hi: int):
+    """rows [r_lo, r_hi) (global) out of a slab whose first row is global row `row_offset`"""
+    rowptr = np.asarray(rowptr, np.int64)
+    a, b = r_lo - row_offset, r_hi - row_offset
+    s, e = rowptr[a], rowptr[b]
+    return rowptr[a:b + 1] - s, np.asarray(col)[s:e], np.asarray(val)[s:e]
 
 
 def local_weight(nrows, ncols, rowptr, col, val, nranks, rank):
@@ -254,13 +263,14 @@ def local_operator(N, nranks, rank, gen_rows, max_bw, layout, band=None, with_ad
     -> (plan, (rowptr, col_local, val) of A, same of A^H, local sum of Im(A)^2 over the owned rows)"""
     r0, r1 = split_ownership(N, nranks, rank)
     if layout == 0:
-        rp, cg, va = gen_rows(r0, r1)
-        if with_adjoint:
+        if with_adjoint:     # one pass over the source: the slab that holds every entry of columns [r0, r1) contains the owned rows
             s0, s1 = max(0, r0 - max_bw), min(N, r1 + max_bw)
             srp, scg, sva = gen_rows(s0, s1)
+            rp, cg, va = slice_rows(srp, scg, sva, s0, r0, r1)
             hrp, hcg, hva = transpose_slab(srp, scg, sva, s0, r0, r1)
             del srp, scg, sva
         else:   # measurement runs that only use the direct operator: A stands in for A^H (never applied)
+            rp, cg, va = gen_rows(r0, r1)
             hrp, hcg, hva = rp, cg, va
         plan = plan_general(N, nranks, rank, np.concatenate([cg, hcg]))
         A = (rp, localize_general(plan, cg), va)
@@ -272,9 +282,9 @@ def local_operator(N, nranks, rank, gen_rows, max_bw, layout, band=None, with_ad
     h = max(lo, hi)
     plan = plan_banded(N, nranks, rank, h, h)
     e0, e1 = plan.ext0, plan.ext0 + plan.n_ext
-    rp, cg, va = gen_rows(e0, e1)
     s0, s1 = max(0, e0 - max_bw), min(N, e1 + max_bw)
     srp, scg, sva = gen_rows(s0, s1)
+    rp, cg, va = slice_rows(srp, scg, sva, s0, e0, e1)
     hrp, hcg, hva = transpose_slab(srp, scg, sva, s0, e0, e1)
     A = localize_banded(plan, rp, cg, va)
     AH = localize_banded(plan, hrp, hcg, hva)

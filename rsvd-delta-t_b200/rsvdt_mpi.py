@@ -253,24 +253,27 @@ class Run:
             raise UserError(f"the operator must be square, current size = {rd.M} x {rd.N}")
         N = rd.M
         r0, r1 = pkg.dist.split_ownership(N, self.world, self.rank)
-        rp, cg, va = rd.rows(r0, r1)
-        rows = np.repeat(np.arange(r0, r1, dtype=np.int64), np.diff(rp))
-        d = cg - rows
-        ext = torch.tensor([int(-d.min()) if d.size else 0, int(d.max()) if d.size else 0], dtype=torch.int64, device=self.dev)
-        dist.all_reduce(ext, op=dist.ReduceOp.MAX)
-        lo, hi = max(int(ext[0].item()), 0), max(int(ext[1].item()), 0)
-        # the halo mailboxes are sized for k test vectors when the ranks connect, and k comes from the forcing file when
-        # there is one (CreateRandomMat.c:30) divided by Nw_eff, which depends on whether A is real (LNSStructure.c:37-44)
-        im2 = torch.tensor([float(np.sum(va.imag ** 2))], dtype=torch.float64, device=self.dev)
-        dist.all_reduce(im2)
-        real = float(im2.item()) ** 0.5 < 1e-12
+        if hasattr(rd, "hints"):          # a generated operator knows its band and type: no pass over the rows needed here
+            lo, hi, real = rd.hints()
+        else:
+            rp, cg, va = rd.rows(r0, r1)
+            rows = np.repeat(np.arange(r0, r1, dtype=np.int64), np.diff(rp))
+            d = cg - rows
+            ext = torch.tensor([int(-d.min()) if d.size else 0, int(d.max()) if d.size else 0], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(ext, op=dist.ReduceOp.MAX)
+            lo, hi = max(int(ext[0].item()), 0), max(int(ext[1].item()), 0)
+            # the halo mailboxes are sized for k test vectors when the ranks connect, and k comes from the forcing file when
+            # there is one (CreateRandomMat.c:30) divided by Nw_eff, which depends on whether A is real (LNSStructure.c:37-44)
+            im2 = torch.tensor([float(np.sum(va.imag ** 2))], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(im2)
+            real = float(im2.item()) ** 0.5 < 1e-12
+            del rp, cg, va, rows, d
         if v["InputForcingFlg"] and not v["TransRun"]:
             try:
                 fr = self.io.MatRowReader(v["RootDir"] + v["InputForcingDir"])
             except (OSError, ValueError) as e:
                 raise UserError(f"cannot read the input forcing {v['RootDir'] + v['InputForcingDir']}: {e}")
             v["k"] = max(fr.N // (v["Nw"] // 2 if real else v["Nw"]), 1)
-        del va
         max_bw = max(lo, hi, 1)
         min_rows = N // self.world
         layout = 1 if (max_bw <= 8 and 8 * max_bw < min_rows) else 0

@@ -179,6 +179,22 @@ class SyntheticRows:
         else:
             raise ValueError(f"unknown synthetic operator '{spec}' (gl:<N>, lns2d:<ny>x<nx>, lns3d:<nz>x<ny>x<nx>)")
 
+    def hints(self):
+        """(max(row - col), max(col - row), real-valued?) without generating the operator: the band of a block stencil is that
+        of an interior point; grids with a dimension < 3 (no interior) are scanned whole, they are tiny."""
+        if self.kind == "gl":
+            return 3, 3, False      # the 4-entry windows are shifted at the ends (explicit zeros up to 3 columns away)
+        if min(self.shape) >= 3:
+            centre = 0
+            for s_ in self.shape:
+                centre = centre * s_ + s_ // 2
+            a, b = centre * self.nvar, (centre + 1) * self.nvar
+        else:
+            a, b = 0, self.M
+        rp, ci, _ = self._rows(a, b)
+        d = ci - np.repeat(np.arange(a, b, dtype=np.int64), np.diff(rp))
+        return int(max(-d.min(), 0)), int(max(d.max(), 0)), False
+
     def rows(self, r0: int, r1: int):
         r0, r1 = max(0, int(r0)), min(self.M, int(r1))
         if getattr(self, "_memo_key", None) == (r0, r1):       # the executable asks for its own range twice in a row

@@ -120,3 +120,47 @@ def test_split_ownership_matches_petsc_decide():
             assert rs[p][1] - rs[p][0] == N // P + (1 if p < N % P else 0)
             if p:
                 assert rs[p][0] == rs[p - 1][1]
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 5])
+def test_local_operator_rows_equal_the_global_matrix(nranks):
+    # dist.local_operator (one pass over the row source: owned rows sliced out of the slab that also yields the rows of A^H by a
+    # stable sort) against the global matrices, both local layouts, every rank of 1 / 2 / 3 / 5
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    D = pkg.dist
+    calls = []
+    for name, src, bw, band in (("lns", pkg.synthetic.SyntheticRows("lns2d:6x7"), None, None),
+                                ("gl", pkg.synthetic.SyntheticRows("gl:211"), 2, (2, 1))):
+        N = src.M
+        rp, ci, va = src.rows(0, N)
+        Ad = _dense_rows(rp, ci, va, N)
+        AHd = Ad.conj().T
+        if bw is None:
+            bw = int(np.abs(ci - np.repeat(np.arange(N), np.diff(rp))).max())
+
+        def gen(a, b):
+            calls.append((a, b))
+            return src.rows(a, b)
+
+        for rank in range(nranks):
+            calls.clear()
+            plan, A, AH, im2 = D.local_operator(N, nranks, rank, gen, bw, 0)
+            assert len(calls) == 1                                            # the source is read once
+            assert im2 == pytest.approx(float(np.sum(Ad[plan.r0:plan.r1].imag ** 2)))
+            for (lrp, lci, lva), ref in ((A, Ad), (AH, AHd)):
+                cg = np.where(lci < plan.n_own, lci + plan.r0, plan.ghost_global[np.maximum(lci - plan.n_own, 0)] if plan.ghost_global.size else 0)
+                assert np.array_equal(_dense_rows(lrp, cg, lva, N), ref[plan.r0:plan.r1])
+                for r in range(lrp.size - 1):
+                    assert (np.diff(cg[lrp[r]:lrp[r + 1]]) > 0).all()           # ascending global columns within a row
+            if band is not None and N // nranks > 8 * max(band):
+                calls.clear()
+                plan, A, AH, im2 = D.local_operator(N, nranks, rank, gen, bw, 1, band)
+                assert len(calls) == 1
+                for (lrp, lci, lva), ref in ((A, Ad), (AH, AHd)):
+                    loc = _dense_rows(lrp, lci, lva, plan.n_ext)
+                    own = slice(plan.own0, plan.own0 + plan.n_own)
+                    want = ref[plan.r0:plan.r1, plan.ext0:plan.ext0 + plan.n_ext]
+                    assert np.array_equal(loc[own], want)
+                    assert np.abs(ref[plan.r0:plan.r1]).sum() == pytest.approx(np.abs(want).sum())   # nothing of an owned row was dropped
