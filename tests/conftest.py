@@ -48,8 +48,13 @@ def rel_err(a, b):
 
 
 def principal_angle(U, V):
-    """largest principal angle between span(U) and span(V)"""
+    """largest principal angle between span(U) and span(V).  Small angles are taken from the sine -- the norm of the part of
+    span(V) outside span(U) -- because arccos of a cosine within 1e-16 of one cannot resolve anything below 2e-8."""
     Qu, _ = np.linalg.qr(U)
     Qv, _ = np.linalg.qr(V)
     s = np.linalg.svd(Qu.conj().T @ Qv, compute_uv=False)
-    return float(np.arccos(np.clip(s.min(), -1.0, 1.0)))
+    cos = float(np.clip(s.min(), -1.0, 1.0))
+    if cos < 0.9:
+        return float(np.arccos(cos))
+    sin = float(np.linalg.norm(Qv - Qu @ (Qu.conj().T @ Qv), 2))
+    return float(np.arcsin(min(sin, 1.0)))
