@@ -639,11 +639,13 @@ int main(int argc, char **argv)
     int device = 0;
     for (int i = 1; i + 1 < argc; i++)
         if (!strcmp(argv[i], "-device")) device = atoi(argv[i + 1]);
+
+    /* PreProcessing.c:27-66.  The input file is read before the CUDA handle is created, so that a wrong variables.yaml is
+     * reported the way the reference reports it on any machine (tests/test_host_driver.py compares the messages with the
+     * reference executable's on CPU); everything after it needs the device. */
+    CHK(ReadUserInput(argc, argv, &RSVDt, &Weight_mat, &TR_vars, &dirs));
     int rc = rsvdt_create(device, &H);                                                                        /* SlepcInitialize, main.c:107 */
     if (rc) return seterr(rc, "no usable CUDA device (this build has no CPU fallback)");
-
-    /* PreProcessing.c:27-66 */
-    CHK(ReadUserInput(argc, argv, &RSVDt, &Weight_mat, &TR_vars, &dirs));
     if (!TR_vars.TransRun) printf("********************************************\n*************** Problem info ***************\n********************************************\n\n");
     CHK(SetupTimeFreqGrid(&RSVDt, &TR_vars));
     CHK(LNSStructure(&RSVDt, &TR_vars, &dirs));

@@ -471,3 +471,48 @@ def test_mpi_driver_two_gpus_weighted_solve_matches_reference_executable(pkg, tm
     for iw in range(Nww):
         assert principal_angle(U[:, iw, :1], gw["U_hat"][:, iw, :1]) <= 1e-6
         assert principal_angle(V[:, iw, :1], gw["V_hat"][:, iw, :1]) <= 1e-6
+
+
+# --------------------------------------------------------------- input rules against the reference executable itself (live)
+@pytest.mark.parametrize("drop,add,expect", [
+    ("TransientLength", "", "Must specify 'TransientLength'"),
+    ("dt", "", "Must specify 'dt'"),
+    ("w", "", "Must specify 'dt'"),                                    # sic (ReadUserInput.c:28)
+    ("Nw", "", "Must specify 'Nw'"),
+    ("RootDir", "", "Must specify 'RootDir'"),
+    ("ResultsDir", "", "Must specify 'ResultsDir'"),
+    ("OperatorDir", "", "Must specify 'OperatorDir'"),
+    (None, "InputForcingFlg: true\n", "Must specify 'InputForcingDir'"),
+    (None, "OutputMatrixFlg: true\n", "Must specify 'OutputMatrixDir'"),
+    (None, "DiscFlg: true\n", "Discounting flag is on! Either set Discounting to zero or specify 'beta'"),
+    (None, "DiscFlg: true\nbeta: -2\n", "'beta' must be positive, current value: -2"),
+])
+def test_input_errors_match_the_reference_executable(drv, tmp_path, drop, add, expect):
+    # the same broken variables.yaml given to the reference executable (oracle/_ref/RSVDt_ref, the reference's ReadUserInput.c)
+    # and to the drop-in's input reader: same complaint, non-zero exit
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    text = BASE + "TransICDir: none\n"
+    if drop:
+        text = "\n".join(line for line in text.splitlines() if not line.startswith(drop + ":")) + "\n"
+    (tmp_path / "variables.yaml").write_text(text + add)
+    out = R.run_executable(str(tmp_path))
+    assert out.returncode != 0 and expect in out.stderr, out.stderr[-500:]
+    with pytest.raises(drv.UserError) as ei:
+        drv.read_user_input(["RSVDt", "-inputs", str(tmp_path / "variables.yaml")], lambda m: None)
+    assert str(ei.value) == expect
+
+
+def test_input_defaults_match_the_reference_executable(drv, tmp_path):
+    # the warnings the reference prints for missing optional keys (its defaults) are the ones the drop-in prints
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    (tmp_path / "variables.yaml").write_text(BASE + "TransICDir: none\n")
+    out = R.run_executable(str(tmp_path))                              # stops later, at the missing operator file
+    ref_warn = [ln for ln in out.stdout.splitlines() if ln.startswith("Warning:")]
+    logs = []
+    drv.read_user_input(["RSVDt", "-inputs", str(tmp_path / "variables.yaml")], logs.append)
+    mine = [ln for ln in logs if ln.startswith("Warning:")]
+    assert len(ref_warn) >= 12 and mine == ref_warn
