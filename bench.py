@@ -170,6 +170,24 @@ def cpu_arm(pkg, *a):
     return CpuPort(pkg, *a)
 
 
+def cpu_baseline_block(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, target_s=12.0):
+    """the `cpu_baseline` object of the bench line: the reference's own code (oracle/_ref) when it was built -- with the oracle
+    port timed next to it for comparison -- else the port alone; each on a sample sized for ~target_s of CPU work"""
+    def timed(arm, budget):
+        _, probe_s, _ = arm.sample(10)
+        n = int(min(max(budget / max(probe_s / 10, 1e-6), 20), 2000))
+        v, secs, cores = arm.sample(n)
+        return {"value": v, "unit": UNIT, "cores": cores, "kind": arm.kind,
+                "sample": f"1 test vector x {n} forced RK4 steps of the same N=1e6 workload ({secs:.1f} s of CPU work); {arm.what}"}
+
+    arm = cpu_arm(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, 1)
+    cpu = timed(arm, target_s)
+    if arm.kind == "reference":
+        del arm
+        cpu["port"] = timed(CpuPort(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, 1), target_s / 2)
+    return cpu
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on all host threads: oracle/_ref (the reference's
     own sources on the PETSc API shim) when built, else the oracle port."""
@@ -348,12 +366,7 @@ def main():
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) -------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        arm = cpu_arm(pkg, N, rowptr, col, val, dt, Ns, Nt, RR, 1)
-        _, probe_s, _ = arm.sample(10)                                  # size the sample for ~12 s of CPU work on this host
-        nsample = int(min(max(12.0 / max(probe_s / 10, 1e-6), 20), 2000))
-        v, secs, cores = arm.sample(nsample)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": arm.kind,
-               "sample": f"1 test vector x {nsample} forced RK4 steps of the same N=1e6 workload ({secs:.1f} s of CPU work); {arm.what}"}
+        cpu = cpu_baseline_block(pkg, N, rowptr, col, val, dt, Ns, Nt, RR)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
