@@ -548,11 +548,20 @@ class Run:
         self.log("\n********************************************\n*************** RSVD-\\Delta t **************\n"
                  "********************************************")
 
+        rend = v["Nt"] + v["Ns"] + (v["ResRatio"] if v["TransientRemoval"] else 0)      # TSActionRK4.c:38-41
+        self.phase_times = []
+
         def timed(banner, fn, done):
             self.log(banner)
             t0 = time.time()
             fn()
-            self.log(f"{done}{hms(time.time() - t0)} ***")
+            self.dist.barrier()
+            sec = time.time() - t0
+            self.phase_times.append((done.strip("* ").replace(" elapsed time =", ""), sec))
+            self.log(f"{done}{hms(sec)} ***")
+            if "action" in done:   # not in the reference: the rate of the stepping loop, the metric BASELINE.json quotes
+                self.log(f"    {sec:.3f} s for {rend} RK4 steps of {v['N']} x {v['k']} unknowns: "
+                         f"{v['N'] * v['k'] * rend / max(sec, 1e-9):.3e} DOF*vector*steps/s (incl. transform / transient removal)")
 
         direct = lambda: timed("\n*** Direct action begins! ***", r.DirectActionRK4, "*** Direct action elapsed time = ")   # noqa: E731
         adjoint = lambda: timed("\n*** Adjoint action begins! ***", r.AdjointActionRK4, "*** Adjoint action elapsed time = ")  # noqa: E731
