@@ -176,7 +176,27 @@ typedef int (*rsvdt_allgather_fn)(const void *send_device_ptr, void *recv_device
 int rsvdt_set_allgather(rsvdt_handle h, rsvdt_allgather_fn fn, void *user);
 void *rsvdt_cuda_stream(rsvdt_handle h);
 
+/* CreateRandomMat.c:36-39 (the InputForcingFlg = false path) on the device: Y_hat <- nrows x (k*Nw_eff) entries uniform in
+ * [0,1) + i[0,1) from a counter-based generator keyed by (seed, global row, column): a row-partitioned run (global_row0 =
+ * first owned row) fills the same matrix as one GPU.  (The reference's RandSeed is ineffective) */
+int rsvdt_create_random_mat(rsvdt_handle h, int64_t nrows, int64_t global_row0, uint64_t seed);
+
+/* ---- synthetic operators of BASELINE.json, generated on the device (measurement aid, no reference counterpart) ------------
+ * The block-stencil operators of rsvd-delta-t_b200/synthetic.py (lns_stencil: nvar unknowns per grid point, 3^ndim-point
+ * stencil, dense nvar x nvar blocks) written by a kernel straight into the tiled block-CSR layout of the stage kernel,
+ * bit-identical to the host generator (tested), so that the 2e7-DOF configurations need no 65 GB file and no host-side
+ * conversion.  blocks: [3^ndim][nvar][nvar] complex, mod_tab: [997], diag_tab: [499] complex (synthetic.stencil_tables).
+ * This rank owns grid points [pt0, pt1) (x fastest); ghost_pts = sorted grid points outside that range its rows reference
+ * (row-partitioned runs: after rsvdt_dist_init(layout 0); single GPU: pt0 = 0, pt1 = all points, no ghosts).
+ * Only even numbers of vectors can be advanced on such an operator (no CSR copy exists for the other kernels). */
+int rsvdt_set_operator_stencil(rsvdt_handle h, int ndim, const int64_t *shape, int nvar, const double *blocks_re_im,
+                               const double *mod_tab, const double *diag_tab_re_im, int64_t pt0, int64_t pt1,
+                               const int64_t *ghost_pts, int64_t n_ghost, int with_adjoint, int disc_flg, double beta,
+                               int real_operator);
+
 /* ---- test / measurement hooks (no reference counterpart) ------------------------------------------ */
+/* the RK4 state y left on the device by the last stepping call, nrows x k column-major (host) */
+int rsvdt_get_state(rsvdt_handle h, double *y_host, int64_t nrows);
 /* snapshots Y_all of the last action: N x (Nstore*k), test-vector-major columns (TSActionRK4.c:62-70,126-130);
  * only kept when rsvdt_keep_snapshots(h, 1) was called before the action. */
 int rsvdt_keep_snapshots(rsvdt_handle h, int keep);
@@ -187,7 +207,8 @@ int rsvdt_get_snapshots(rsvdt_handle h, double *Yall_host);
 int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *ms_total);
 /* number of kernels launched by this handle since creation / since the last reset */
 int64_t rsvdt_kernel_launches(rsvdt_handle h, int reset);
-/* tuning knobs: name in {"chunk_steps","stage_variant","idft_variant","use_graph"}; returns RSVDT_ERR_ARG if unknown */
+/* tuning knobs: name in {"chunk_steps","stage_variant","idft_variant","use_graph","use_banded","use_bcsr","use_tiled",
+ * "tiled_ctas","use_fused_halo",...}; returns RSVDT_ERR_ARG if unknown */
 int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value);
 /* device-event timing of one kernel family over the last timed window: which in {"stage","idft","dft","all"} */
 int rsvdt_last_kernel_ms(rsvdt_handle h, const char *which, float *ms, int64_t *launches);

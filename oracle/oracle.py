@@ -235,6 +235,15 @@ def time_forced_steps(Op: Csr, v: Vars, idft, Y_hat_in, ncols, nsteps) -> float:
                                        C.c_int64(nsteps))
 
 
+def forced_state(Op: Csr, v: Vars, idft, Y_hat_in, nsteps, ncols=None):
+    """y after `nsteps` forced RK4 steps of TSActionRK4.c:116-122 for test vectors 0..ncols-1 -> N x ncols"""
+    ncols = v.k if ncols is None else ncols
+    y = np.empty((v.N, ncols), c128, order="F")
+    vc = v.c()
+    lib().orc_forced_state(Op.c, C.byref(vc), _p(_F(idft)), _p(_F(Y_hat_in)), C.c_int64(ncols), C.c_int64(nsteps), _p(y))
+    return y
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 

@@ -566,6 +566,24 @@ double orc_time_forced_steps(const orc_csr *Op, const orc_vars *v, const orc_cpl
     return t;
 }
 
+/* TSActionRK4.c:89-122 truncated after nsteps steps: the state of every test vector (checker of the bench-size run) */
+void orc_forced_state(const orc_csr *Op, const orc_vars *v, const orc_cplx *idft, const orc_cplx *Y_hat_in, orc_int ncols,
+                      orc_int nsteps, orc_cplx *y_out)
+{
+    const orc_int N = v->N, Nw_eff = v->Nw_eff;
+    orc_cplx *F_hat_k = (orc_cplx *)malloc((size_t)N * Nw_eff * sizeof(orc_cplx));
+    orc_cplx *work = (orc_cplx *)malloc((size_t)7 * N * sizeof(orc_cplx));
+    for (orc_int ik = 0; ik < ncols; ik++) {
+        orc_cplx *y = y_out + ik * N;
+        for (orc_int iw = 0; iw < Nw_eff; iw++) /* the test-vector-major slice of PermuteMat */
+            memcpy(F_hat_k + iw * N, Y_hat_in + (ik + iw * v->k) * N, (size_t)N * sizeof(orc_cplx));
+        memset(y, 0, (size_t)N * sizeof(orc_cplx));                               /* TSActionRK4.c:91 */
+        orc_create_forcing_on_fly(N, Nw_eff, F_hat_k, idft, 0, work + N);         /* :103 */
+        for (orc_int i = 1; i <= nsteps; i++) orc_tsrk4(Op, v, F_hat_k, idft, i, y, work);   /* :116-118 */
+    }
+    free(F_hat_k); free(work);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * TransientRunRK4.c:128-158
  * ---------------------------------------------------------------------------------------------- */

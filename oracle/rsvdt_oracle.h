@@ -117,6 +117,11 @@ void orc_mat_mat_mult(const orc_csr *M, int hermitian_transpose, orc_int ncols, 
 double orc_time_forced_steps(const orc_csr *Op, const orc_vars *v, const orc_cplx *idft, const orc_cplx *Y_hat_in,
                              orc_int ncols, orc_int nsteps);
 
+/* the state y after `nsteps` forced RK4 steps of the same loop for test vectors 0..ncols-1: y_out is N x ncols, column-major
+ * (what TSActionRK4.c:116-122 holds in `y` after i = nsteps) */
+void orc_forced_state(const orc_csr *Op, const orc_vars *v, const orc_cplx *idft, const orc_cplx *Y_hat_in, orc_int ncols,
+                      orc_int nsteps, orc_cplx *y_out);
+
 int orc_num_threads(void);
 
 #endif

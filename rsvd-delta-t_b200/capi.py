@@ -42,7 +42,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... (csrc/Makefile), in-tree."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in ("kernels.cu", "capi.cu", "kernels.cuh")] + [HEADER_PATH]
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("kernels.cu", "stage_tiled.cu", "stencil_gen.cu", "capi.cu", "kernels.cuh", "stage_tiled.cuh")] + [HEADER_PATH]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
         cmd = ["make", "-C", os.path.join(_HERE, "csrc")] + ([] if verbose else ["-s"])
@@ -158,6 +158,26 @@ class RSVDt:
         self.N = int(n_own)
         self.real_operator = bool(real_operator)
 
+    def set_operator_stencil(self, shape, nvar=5, pt_range=None, ghost_pts=None, with_adjoint=True, complex_coupling=True,
+                             DiscFlg=False, beta=0.0, **gen):
+        """synthetic.lns_stencil(shape, nvar, ...) generated on the device in the tiled block-CSR layout (include/rsvdt.h);
+        pt_range = (pt0, pt1) grid points owned by this rank, ghost_pts = sorted grid points outside it that its rows touch"""
+        from . import synthetic
+        shape = tuple(int(x) for x in shape)
+        blocks, mod_tab, diag_tab = synthetic.stencil_tables(len(shape), nvar, complex_coupling, **gen)
+        npts = int(np.prod(shape))
+        pt0, pt1 = (0, npts) if pt_range is None else pt_range
+        gh = np.ascontiguousarray(ghost_pts if ghost_pts is not None else np.zeros(0, np.int64), np.int64)
+        shp = np.array(shape, np.int64)
+        self._ck(lib().rsvdt_set_operator_stencil(self._h, C.c_int(len(shape)), _p(shp), C.c_int(nvar),
+                                                  _p(np.ascontiguousarray(blocks, c128)), _p(np.ascontiguousarray(mod_tab, np.float64)),
+                                                  _p(np.ascontiguousarray(diag_tab, c128)), C.c_int64(pt0), C.c_int64(pt1),
+                                                  _p(gh), C.c_int64(gh.size), C.c_int(int(with_adjoint)), C.c_int(int(DiscFlg)),
+                                                  C.c_double(beta), C.c_int(int(not complex_coupling))))
+        self.N = int((pt1 - pt0) * nvar)
+        self.real_operator = not complex_coupling
+        return self.real_operator
+
     def set_grid(self, k, Nw, Ns, Nt, ResRatio, dt, w, TransientRemoval=False, RealOperator=None):
         ro = self.real_operator if RealOperator is None else RealOperator
         g = Grid(k, Nw, Nw // 2 if ro else Nw, Ns, Nt, ResRatio, dt, w, int(bool(ro)), int(bool(TransientRemoval)))
@@ -188,6 +208,17 @@ class RSVDt:
         Y = _F(Y)
         assert Y.shape[1] == self.grid.k * self.grid.Nw_eff
         self._ck(lib().rsvdt_set_yhat(self._h, _p(Y), C.c_int64(Y.shape[0])))
+
+    def CreateRandomMat(self, nrows=None, global_row0=0, seed=1373):
+        """CreateRandomMat.c:36-39 on the device (uniform [0,1) + i[0,1)); RandSeed default of ReadUserInput.c:121-125"""
+        nrows = self.N if nrows is None else nrows
+        self._ck(lib().rsvdt_create_random_mat(self._h, C.c_int64(nrows), C.c_int64(global_row0), C.c_uint64(seed)))
+
+    def get_state(self):
+        """the RK4 state left by the last stepping call: N x k"""
+        y = np.empty((self.N, self.grid.k), c128, order="F")
+        self._ck(lib().rsvdt_get_state(self._h, _p(y), C.c_int64(self.N)))
+        return y
 
     def get_Y_hat(self):
         rows = lib().rsvdt_yhat_rows(self._h)

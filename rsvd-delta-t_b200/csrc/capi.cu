@@ -5,8 +5,10 @@
 // launched the call fails with RSVDT_ERR_CUDA.
 #include "../../include/rsvdt.h"
 #include "kernels.cuh"
+#include "stage_tiled.cuh"
 
 #include <algorithm>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -20,6 +22,16 @@ namespace {
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept
+    {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }   // every early return through CU()/RS() frees its temporaries
     cudaError_t alloc(size_t n)
     {
         release();
@@ -38,6 +50,22 @@ struct DevBuf {
     void swap(DevBuf &o) { std::swap(p, o.p); std::swap(bytes, o.bytes); }
 };
 
+// host-side loops over block rows / tiles at operator upload (1e8-1e9 entries): plain threads, the runs are independent
+template <class F>
+void parallel_for(int64_t n, F fn)
+{
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt ? std::min(nt, 16u) : 4u;
+    if (n < 4096 || nt <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n + nt - 1) / nt;
+    for (unsigned i = 0; i < nt; i++) {
+        const int64_t a = (int64_t)i * per, b = std::min(n, a + per);
+        if (a < b) th.emplace_back([=]() { fn(a, b); });
+    }
+    for (auto &t : th) t.join();
+}
+
 struct CsrOwned {
     CsrDev d;
     DevBuf rowptr, col, val;
@@ -55,12 +83,20 @@ struct CsrOwned {
     BcsrDev bcsr;
     DevBuf b_rowptr, b_col, b_val;
     bool bcsr_valid = false;
+    // tiled block-CSR form (stage_tiled.cuh): the layout the TMA-staged stage kernel streams
+    TbcsrDev tb;
+    DevBuf t_chunks, t_tileptr, t_order, t_flags;
+    bool tbcsr_valid = false;
+    bool stencil_only = false;                    // generated on the device: no CSR / block-CSR copies exist
+    std::vector<unsigned char> tile_ghost;        // [ntiles] 1: a block column of the tile is a ghost (row-partitioned runs)
     int plan_nv = -1, plan_variant = -1, plan_mode = -1, ntiles = 0, nslow = 0;
     bool plan_ok = false;
     void release()
     {
         rowptr.release(); col.release(); val.release(); dia.release(); tile_ok.release(); slow_ranges.release();
         b_rowptr.release(); b_col.release(); b_val.release(); bcsr = BcsrDev(); bcsr_valid = false;
+        t_chunks.release(); t_tileptr.release(); t_order.release(); t_flags.release(); tb = TbcsrDev(); tbcsr_valid = false;
+        stencil_only = false; tile_ghost.clear();
         d = CsrDev(); set = false; dia_valid = false; plan_nv = -1; plan_ok = false; row_regular.clear();
     }
 };
@@ -85,7 +121,7 @@ struct rsvdt_context {
     bool real_operator = false;
 
     // row partition over GPUs (PETSc's MPIAIJ layout; one process per GPU): halo messages, peer mailboxes, flags
-    struct DistMsg { int peer; int count; int64_t dest_row0; int64_t mb_off_rows; DevBuf rows; };
+    struct DistMsg { int peer; int count; int64_t dest_row0; int64_t mb_off_rows; DevBuf rows; std::vector<int32_t> rows_h; };
     struct DistIn { int peer; int count; int64_t dest_row0; int64_t mb_off_rows; };
     struct Dist {
         bool on = false, connected = false;
@@ -107,6 +143,14 @@ struct rsvdt_context {
         rsvdt_allgather_fn allgather = nullptr;
         void *allgather_user = nullptr;
         DevBuf gather_send, gather_recv;
+        // exchange fused into the tiled stage kernel (layout 0; stage_tiled.cuh): three more mailbox slots in ghost order after
+        // the two of the unfused path, one more flag per rank, tables of the tiles that send
+        bool fz_ready = false;
+        unsigned long long fz_epoch = 0;
+        const cplx *fz_last_out = nullptr;    // block vector whose halo rows sit in mailbox slot fz_epoch % 3
+        int fz_last_nv = 0;
+        std::vector<int64_t> peer_in_rows;    // in_rows_total of every peer (mailbox slot size over there)
+        DevBuf fz_send_index, fz_send_dest, fz_out_tiles, fz_out_done;
     } dist;
 
     // Weight_matrices (Variables.h:69-80): 0=W_f_sqrt_inv 1=B 2=W_q_sqrt_inv 3=W_q_sqrt 4=C, and their conj-transposes
@@ -132,6 +176,8 @@ struct rsvdt_context {
     int64_t use_banded = -1;  // -1: automatic; 0: stage kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged DIA step
     int64_t tma_variant = 0;  // 0: tiles sized for 3 CTAs/SM, 1: for 2 CTAs/SM
     int64_t use_bcsr = 1;     // block-CSR stage kernel when the operator has dense B x B blocks
+    int64_t use_tiled = 1;    // ... and its TMA-staged tiled form (stage_tiled.cu) when the number of vectors is even
+    int64_t tiled_ctas = 2;   // resident CTAs per SM of the tiled stage kernel (ring depth follows from the shared memory left)
     int64_t use_small = 1;    // single-CTA persistent kernel when the whole block vector fits in one SM's shared memory
 
     // CUDA graphs of a whole snapshot-free chunk of RK4 steps (launch-bound small problems): [direct][slice buffer]
@@ -141,6 +187,7 @@ struct rsvdt_context {
         int64_t nsteps = 0, launches = 0;
     } graphs[2][2];
     int64_t use_graph = 1;
+    int64_t use_fused_halo = 1;   // row-partitioned runs, layout 0: the tiled stage kernel exchanges the halo rows itself
     int64_t use_overlap = 0;  // row-partitioned runs: hide the halo exchange behind the interior rows (measured: the three
                               // launches per stage cost more than the exchange they hide at plane-sized halos; off by default)
     int64_t use_pipeline = 0; // (measured: no gain, the two kernels compete for SM residency) synthesise the next chunk's forcing on a low-priority stream while the current chunk steps
@@ -344,6 +391,56 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
         dst.bcsr.bcol = dst.b_col.as<int32_t>();
         dst.bcsr.bval = dst.b_val.as<cplx>();
         dst.bcsr_valid = true;
+        // ---- tiled form: chunk p of a tile = the p-th block of each of its TB block rows, entries [e][tb], then columns [tb]
+        {
+            const int TB = TBCSR_TB;
+            const int64_t ntiles = (nbrows + TB - 1) / TB;
+            std::vector<int64_t> tptr((size_t)ntiles + 1, 0);
+            for (int64_t t = 0; t < ntiles; t++) {
+                int64_t mx = 0;
+                for (int64_t br = t * TB; br < std::min(nbrows, (t + 1) * TB); br++) mx = std::max(mx, brp[(size_t)br + 1] - brp[(size_t)br]);
+                tptr[(size_t)t + 1] = tptr[(size_t)t] + mx;
+            }
+            const size_t cb = tbcsr_chunk_bytes(B, TB);
+            const int64_t nchunks = tptr[(size_t)ntiles];
+            dst.tile_ghost.assign((size_t)ntiles, 0);
+            for (int64_t br = 0; br < nbrows; br++)
+                for (int64_t q = brp[(size_t)br]; q < brp[(size_t)br + 1]; q++)
+                    if (bc[(size_t)q] >= nbrows) { dst.tile_ghost[(size_t)(br / TB)] = 1; break; }
+            std::vector<unsigned char> chunks;
+            try { chunks.resize((size_t)std::max<int64_t>(nchunks, 1) * cb); } catch (const std::bad_alloc &) { return fail(h, RSVDT_ERR_MEM, "host memory for the tiled operator"); }
+            parallel_for(ntiles, [&](int64_t t0, int64_t t1) {
+                for (int64_t t = t0; t < t1; t++) {
+                    const int64_t nch = tptr[(size_t)t + 1] - tptr[(size_t)t];
+                    for (int64_t pch = 0; pch < nch; pch++) {
+                        unsigned char *base = chunks.data() + (size_t)(tptr[(size_t)t] + pch) * cb;
+                        cplx *cv = reinterpret_cast<cplx *>(base);
+                        int32_t *cc = reinterpret_cast<int32_t *>(base + (size_t)B * B * TB * sizeof(cplx));
+                        for (int tbi = 0; tbi < TB; tbi++) {
+                            const int64_t br = t * TB + tbi;
+                            const bool on = br < nbrows && pch < brp[(size_t)br + 1] - brp[(size_t)br];
+                            cc[tbi] = on ? bc[(size_t)(brp[(size_t)br] + pch)] : -1;
+                            for (int e = 0; e < B * B; e++)
+                                cv[(size_t)e * TB + tbi] = on ? bv[(size_t)((brp[(size_t)br] + pch) * BS + e)] : make_double2(0.0, 0.0);
+                        }
+                    }
+                }
+            });
+            CU(dst.t_tileptr.alloc(tptr.size() * sizeof(int64_t)));
+            CU(dst.t_chunks.alloc(chunks.size()));
+            CU(cudaMemcpy(dst.t_tileptr.p, tptr.data(), tptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(dst.t_chunks.p, chunks.data(), chunks.size(), cudaMemcpyHostToDevice));
+            dst.tb.B = B;
+            dst.tb.TB = TB;
+            dst.tb.nbrows = nbrows;
+            dst.tb.nbcols_own = nbrows;   // single GPU / in-buffer ghosts: every block column is a row range of the stage vector
+            dst.tb.ntiles = ntiles;
+            dst.tb.nchunks = nchunks;
+            dst.tb.tile_ptr = dst.t_tileptr.as<int64_t>();
+            dst.tb.chunks = dst.t_chunks.as<unsigned char>();
+            dst.tb.chunk_bytes = cb;
+            dst.tbcsr_valid = true;
+        }
         break;
     }
     // ---- diagonal pattern analysis (square, narrow-band operators only) ------------------------------------------
@@ -506,14 +603,60 @@ int dist_wait_unpack(rsvdt_handle h, cplx *buf, int nvec)
 int dist_exchange(rsvdt_handle h, cplx *buf, int nvec)
 {
     if (!h->dist.on) return RSVDT_OK;
+    h->dist.fz_last_out = nullptr;   // the ghost rows of `buf` are (re)filled in place: the next fused stage gathers them from there
     RS(dist_push(h, buf, nvec, h->stream));
     return dist_wait_unpack(h, buf, nvec);
 }
 
 // ---- one RK4 step on a block of nv vectors (TSRK4.c:18-47 / TSTransRK4.c:15-36) ---------------------------
 // y: state (in/out), xa/xb/acc: work, f_prev/f_half/f_next: forcing slices or nullptr, snap: optional copy of y_{n+1}
+bool tiled_active(rsvdt_handle h, const CsrOwned &Op, int nv)
+{
+    return (Op.stencil_only || (h->use_bcsr && h->use_tiled)) && Op.tbcsr_valid && tbcsr_stage_supported(Op.tb.B, nv);
+}
+// the stage kernel itself moves the halo rows (no push / signal / unpack launches)
+bool fused_active(rsvdt_handle h, const CsrOwned &Op, int nv)
+{
+    const auto &D = h->dist;
+    return D.on && D.layout == 0 && D.fz_ready && h->use_fused_halo && nv <= D.nvec_max && Op.t_flags.p && tiled_active(h, Op, nv);
+}
+
 cudaError_t launch_stage_any(rsvdt_handle h, const CsrOwned &Op, int nv, int mode, const StageArgs &a)
 {
+    if (tiled_active(h, Op, nv)) {
+        HaloFuse hf;
+        if (fused_active(h, Op, nv)) {
+            auto &D = h->dist;
+            const unsigned long long E = ++D.fz_epoch;
+            const int64_t slot_elems = D.in_rows_total * (int64_t)D.nvec_max;
+            unsigned long long *flags = D.flags.as<unsigned long long>();
+            hf.enabled = 1;
+            hf.epoch = E;
+            const bool from_mail = E > 1 && a.xin == D.fz_last_out && nv == D.fz_last_nv;
+            hf.wait_epoch = from_mail ? 1 : 0;
+            hf.ghost_src = from_mail ? D.mailbox.as<cplx>() + (int64_t)(2 + (E - 1) % 3) * slot_elems
+                                     : a.xin + Op.tb.nbcols_own * Op.tb.B * (int64_t)nv;   // in-buffer ghost rows (exchanged by the caller)
+            hf.n_in = (int)D.in.size();
+            hf.n_out = (int)D.out.size();
+            for (int q = 0; q < hf.n_in; q++) hf.in_flag[q] = flags + D.nranks + D.in[(size_t)q].peer;
+            for (int i = 0; i < hf.n_out; i++) {
+                const auto &m = D.out[(size_t)i];
+                const int64_t peer_slot = D.peer_in_rows[(size_t)m.peer] * (int64_t)D.nvec_max;
+                hf.out_mail[i] = reinterpret_cast<cplx *>(D.peer_mailbox[(size_t)m.peer]) + (int64_t)(2 + E % 3) * peer_slot;
+                hf.out_flag[i] = reinterpret_cast<unsigned long long *>(D.peer_flags[(size_t)m.peer]) + D.nranks + D.rank;
+            }
+            hf.out_done = D.fz_out_done.as<unsigned long long>();
+            hf.out_tiles = D.fz_out_tiles.as<int32_t>();
+            hf.tile_flags = Op.t_flags.as<unsigned char>();
+            hf.send_index = D.fz_send_index.as<int32_t>();
+            hf.send_dest = D.fz_send_dest.as<int64_t>();
+            hf.timeout_flag = flags + 2 * D.nranks + 1;
+            D.fz_last_out = mode == 2 ? a.acc_out : a.xout;
+            D.fz_last_nv = nv;
+        }
+        return launch_rk4_stage_tbcsr(Op.tb, nv, mode, a, hf, (int)h->tiled_ctas, h->stream);
+    }
+    if (Op.stencil_only) return cudaErrorNotSupported;   // device-generated operators exist in the tiled form only (even nv)
     if (h->use_bcsr && Op.bcsr_valid && bcsr_stage_supported(Op.bcsr.B, nv))
         return launch_rk4_stage_bcsr(Op.bcsr, nv, mode, a, (int)h->stage_variant, h->stream);
     return launch_rk4_stage(Op.d, nv, mode, a, (int)h->stage_variant, h->stream);
@@ -547,7 +690,8 @@ int rk4_step(rsvdt_handle h, const CsrOwned &Op, int nv, cplx *y, cplx *xa, cplx
 {
     const double dt = h->g.dt;
     StageArgs a;
-    if (h->dist.on && h->dist.overlap && h->use_overlap) {
+    const bool fused = fused_active(h, Op, nv);
+    if (!fused && h->dist.on && h->dist.overlap && h->use_overlap) {
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = y; a.ybase = y; a.f = f_prev; a.xout = xa; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6;
@@ -570,28 +714,28 @@ int rk4_step(rsvdt_handle h, const CsrOwned &Op, int nv, cplx *y, cplx *xa, cplx
         a.xin = y; a.ybase = y; a.f = f_prev; a.xout = xa; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6;
         CU(launch_stage_any(h, Op, nv, 0, a));
     }
-    RS(dist_exchange(h, xa, nv));
+    if (!fused) RS(dist_exchange(h, xa, nv));
     {   // k2 = Op x2 + F2 ; x3 = y + dt/2 k2 ; acc += dt/6*2 k2                   TSRK4.c:31-32,45
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xa; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xb; a.acc_out = acc; a.cx = dt / 2; a.ca = dt / 6 * 2;
         CU(launch_stage_any(h, Op, nv, 1, a));
     }
-    RS(dist_exchange(h, xb, nv));
+    if (!fused) RS(dist_exchange(h, xb, nv));
     {   // k3 = Op x3 + F2 ; x4 = y + dt k3 ; acc += dt/6*2 k3                     TSRK4.c:33-34,46
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xb; a.ybase = y; a.f = f_half; a.acc_in = acc; a.xout = xa; a.acc_out = acc; a.cx = dt; a.ca = dt / 6 * 2;
         CU(launch_stage_any(h, Op, nv, 1, a));
     }
-    RS(dist_exchange(h, xa, nv));
+    if (!fused) RS(dist_exchange(h, xa, nv));
     {   // k4 = Op x4 + F3 ; y = acc + dt/6 k4 ; snapshot                         TSRK4.c:35,47 ; SaveSnapshots.c:26-28
         Bracket br(h, &h->ev_stage);
         a = StageArgs();
         a.xin = xa; a.f = f_next; a.acc_in = acc; a.acc_out = y; a.snap = snap; a.ca = dt / 6;
         CU(launch_stage_any(h, Op, nv, 2, a));
     }
-    RS(dist_exchange(h, y, nv));
+    if (!fused) RS(dist_exchange(h, y, nv));   // (fused: the halo of y_{n+1} is in the peers' mailboxes, read by the next stage 1)
     h->launches += 4;
     return RSVDT_OK;
 }
@@ -961,6 +1105,8 @@ int dft_snapshots(rsvdt_handle h, const cplx *snaps, cplx *Yhat_out)
 }
 
 int dist_allreduce(rsvdt_handle h, void *dev_ptr, int64_t n_doubles);
+int check_halo_timeout(rsvdt_handle h);
+int build_fused(rsvdt_handle h);
 
 // TransientRemovalStrategy.c:30-40 on the device.  snaps: Y_all as a stack [Nw+1][row][ik]; Yhat_out: stack [Nw_eff][row][ik].
 //   CreateMtilde.c:41-54      V = QR(Y_all_k) -> shifted CholeskyQR3 per test vector (the snapshot matrices reach cond ~1e7,
@@ -1096,6 +1242,7 @@ int ts_action(rsvdt_handle h, bool direct)
         } else if ((rc = dft_snapshots(h, h->snaps.as<cplx>(), Fhat.as<cplx>())) != RSVDT_OK) break;       // :148
         cudaError_t es = cudaStreamSynchronize(h->stream);
         if (es != cudaSuccess) { rc = fail(h, RSVDT_ERR_CUDA, "action failed: %s", cudaGetErrorString(es)); break; }
+        if ((rc = check_halo_timeout(h)) != RSVDT_OK) break;
     } while (0);
     if (rc == RSVDT_OK) {
         h->Yhat.swap(Fhat);
@@ -1230,6 +1377,145 @@ int svd_all(rsvdt_handle h, DevBuf &Y, int64_t rows, double *dst_sigma)
 }  // namespace
 
 // =====================================================================================================
+namespace {
+
+// Tables of the exchange fused into the tiled stage kernel (stage_tiled.cuh, HaloFuse).  Not an error if the partition does
+// not qualify (rows wanted by more than two peers, requests that are not whole block rows, more than 8 peers): the
+// unfused exchange stays in use.
+int build_fused(rsvdt_handle h)
+{
+    auto &D = h->dist;
+    D.fz_ready = false;
+    if (D.layout != 0 || !h->A.tbcsr_valid) return RSVDT_OK;
+    if (D.out.size() > (size_t)TBCSR_MAX_PEERS || D.in.size() > (size_t)TBCSR_MAX_PEERS) return RSVDT_OK;
+    const int B = h->A.tb.B, TB = h->A.tb.TB;
+    const int64_t ntiles = h->A.tb.ntiles;
+    if (h->AH.set && (!h->AH.tbcsr_valid || h->AH.tb.B != B || h->AH.tb.ntiles != ntiles)) return RSVDT_OK;
+    // mailbox rows of the fused slots are ghost rows: incoming message i must fill ghost rows [mb_off_rows, +count)
+    for (auto &m : D.in)
+        if (m.dest_row0 - h->N != m.mb_off_rows) return RSVDT_OK;
+    std::vector<int32_t> send_index((size_t)ntiles, -1);
+    std::vector<int64_t> send_dest;
+    std::vector<int32_t> out_tiles(std::max<size_t>(D.out.size(), 1), 0);
+    for (size_t i = 0; i < D.out.size(); i++) {
+        const auto &m = D.out[i];
+        if (m.count % B) return RSVDT_OK;
+        std::vector<unsigned char> seen((size_t)ntiles, 0);
+        for (int j = 0; j < m.count; j += B) {
+            const int64_t r0 = m.rows_h[(size_t)j];
+            if (r0 % B || r0 >= h->N) return RSVDT_OK;
+            for (int r = 1; r < B; r++)
+                if (m.rows_h[(size_t)(j + r)] != r0 + r) return RSVDT_OK;
+            const int64_t br = r0 / B, t = br / TB;
+            const int tbi = (int)(br % TB);
+            if (send_index[(size_t)t] < 0) {
+                send_index[(size_t)t] = (int32_t)(send_dest.size() / (size_t)(2 * TB));
+                send_dest.resize(send_dest.size() + (size_t)(2 * TB), -1);
+            }
+            int64_t *d = send_dest.data() + (size_t)send_index[(size_t)t] * 2 * TB;
+            const int64_t v = ((int64_t)i << 48) | (m.mb_off_rows + j);
+            if (d[tbi] < 0) d[tbi] = v;
+            else if (d[TB + tbi] < 0) d[TB + tbi] = v;
+            else return RSVDT_OK;
+            if (!seen[(size_t)t]) { seen[(size_t)t] = 1; out_tiles[i]++; }
+        }
+    }
+    CU(D.fz_send_index.alloc(std::max<size_t>(send_index.size(), 1) * sizeof(int32_t)));
+    CU(D.fz_send_dest.alloc(std::max<size_t>(send_dest.size(), 1) * sizeof(int64_t)));
+    CU(D.fz_out_tiles.alloc(out_tiles.size() * sizeof(int32_t)));
+    CU(D.fz_out_done.alloc(out_tiles.size() * sizeof(unsigned long long)));
+    if (!send_index.empty()) CU(cudaMemcpy(D.fz_send_index.p, send_index.data(), send_index.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!send_dest.empty()) CU(cudaMemcpy(D.fz_send_dest.p, send_dest.data(), send_dest.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(D.fz_out_tiles.p, out_tiles.data(), out_tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemset(D.fz_out_done.p, 0, out_tiles.size() * sizeof(unsigned long long)));
+    // per operator: tile flags (bit0 reads ghosts, bit1 sends) and the processing order (sending tiles, then ghost readers, then the rest)
+    for (CsrOwned *Op : {&h->A, &h->AH}) {
+        if (!Op->set || !Op->tbcsr_valid) continue;
+        std::vector<unsigned char> fl((size_t)ntiles, 0);
+        for (int64_t t = 0; t < ntiles; t++)
+            fl[(size_t)t] = (unsigned char)((!Op->tile_ghost.empty() && Op->tile_ghost[(size_t)t] ? 1 : 0) | (send_index[(size_t)t] >= 0 ? 2 : 0));
+        std::vector<int32_t> order;
+        order.reserve((size_t)ntiles);
+        for (int pass = 0; pass < 3; pass++)
+            for (int64_t t = 0; t < ntiles; t++) {
+                const int cls = (fl[(size_t)t] & 2) ? 0 : (fl[(size_t)t] ? 1 : 2);
+                if (cls == pass) order.push_back((int32_t)t);
+            }
+        CU(Op->t_flags.alloc(std::max<size_t>(fl.size(), 1)));
+        CU(Op->t_order.alloc(std::max<size_t>(order.size(), 1) * sizeof(int32_t)));
+        CU(cudaMemcpy(Op->t_flags.p, fl.data(), fl.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(Op->t_order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        Op->tb.tile_order = Op->t_order.as<int32_t>();
+    }
+    D.fz_ready = true;
+    return RSVDT_OK;
+}
+
+// a stage kernel gave up waiting for a peer's halo rows (stage_tiled.cu): report it instead of returning garbage
+int check_halo_timeout(rsvdt_handle h)
+{
+    auto &D = h->dist;
+    if (!D.on || !D.fz_ready || !D.flags.p) return RSVDT_OK;
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, D.flags.as<unsigned long long>() + 2 * D.nranks + 1, sizeof v, cudaMemcpyDeviceToHost));
+    if (v) return fail(h, RSVDT_ERR_CUDA, "halo exchange: a peer GPU did not publish its boundary rows (rank %d gave up waiting)", D.rank);
+    return RSVDT_OK;
+}
+
+// one operator (A or A^H) of a synthetic block-stencil generated on the device in the tiled block-CSR layout
+int build_stencil_operator(rsvdt_handle h, CsrOwned &Op, StencilSpec sp, int64_t n_ext)
+{
+    Op.release();
+    const int TB = TBCSR_TB, B = sp.B;
+    const int64_t nbrows = sp.pt1 - sp.pt0;
+    const int64_t ntiles = (nbrows + TB - 1) / TB;
+    DevBuf counts, hasg;
+    CU(counts.alloc((size_t)ntiles * sizeof(int32_t)));
+    CU(stencil_tile_counts(sp, TB, ntiles, counts.as<int32_t>(), h->stream));
+    std::vector<int32_t> cnt((size_t)ntiles);
+    CU(cudaMemcpyAsync(cnt.data(), counts.p, (size_t)ntiles * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<int64_t> tptr((size_t)ntiles + 1, 0);
+    for (int64_t t = 0; t < ntiles; t++) tptr[(size_t)t + 1] = tptr[(size_t)t] + cnt[(size_t)t];
+    const size_t cb = tbcsr_chunk_bytes(B, TB);
+    const int64_t nchunks = tptr[(size_t)ntiles];
+    CU(Op.t_tileptr.alloc(tptr.size() * sizeof(int64_t)));
+    CU(Op.t_chunks.alloc((size_t)std::max<int64_t>(nchunks, 1) * cb));
+    CU(hasg.alloc((size_t)ntiles));
+    CU(cudaMemsetAsync(hasg.p, 0, (size_t)ntiles, h->stream));
+    CU(cudaMemcpyAsync(Op.t_tileptr.p, tptr.data(), tptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CU(stencil_fill(sp, TB, ntiles, Op.t_tileptr.as<int64_t>(), Op.t_chunks.as<unsigned char>(), hasg.as<unsigned char>(), h->stream));
+    Op.tile_ghost.assign((size_t)ntiles, 0);
+    CU(cudaMemcpyAsync(Op.tile_ghost.data(), hasg.p, (size_t)ntiles, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->launches += 2;
+    Op.tb.B = B;
+    Op.tb.TB = TB;
+    Op.tb.nbrows = nbrows;
+    Op.tb.nbcols_own = nbrows;
+    Op.tb.ntiles = ntiles;
+    Op.tb.nchunks = nchunks;
+    Op.tb.tile_ptr = Op.t_tileptr.as<int64_t>();
+    Op.tb.chunks = Op.t_chunks.as<unsigned char>();
+    Op.tb.chunk_bytes = cb;
+    Op.tbcsr_valid = true;
+    Op.stencil_only = true;
+    int nb = 1;
+    int64_t band = 1;
+    for (int i = 0; i < sp.d; i++) nb *= 3;
+    for (int i = sp.d - 1, st = 1; i >= 0; st *= (int)sp.shape[i], i--) band += st;
+    Op.d = CsrDev();
+    Op.d.nrows = nbrows * B;
+    Op.d.ncols = n_ext;
+    Op.d.nnz = nchunks * (int64_t)TB * B * B;
+    Op.d.max_row_nnz = (int64_t)nb * B;
+    Op.lo_bw = Op.hi_bw = band * B;   // (keeps the band kernels away from an operator that has no CSR form)
+    Op.set = true;
+    return RSVDT_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 const char *rsvdt_version(void) { return "rsvdt-b200 0.1 (sm_100a)"; }
@@ -1281,7 +1567,8 @@ int rsvdt_destroy(rsvdt_handle h)
         if (h->dist.peer_mailbox[(size_t)p]) cudaIpcCloseMemHandle(h->dist.peer_mailbox[(size_t)p]);
         if (h->dist.peer_flags[(size_t)p]) cudaIpcCloseMemHandle(h->dist.peer_flags[(size_t)p]);
     }
-    DevBuf *dbufs[] = {&h->dist.mailbox, &h->dist.flags, &h->dist.msgs_dev, &h->dist.ins_dev, &h->dist.peer_flags_dev};
+    DevBuf *dbufs[] = {&h->dist.mailbox, &h->dist.flags, &h->dist.msgs_dev, &h->dist.ins_dev, &h->dist.peer_flags_dev,
+                       &h->dist.fz_send_index, &h->dist.fz_send_dest, &h->dist.fz_out_tiles, &h->dist.fz_out_done};
     for (DevBuf *b : dbufs) b->release();
     DevBuf *bufs[] = {&h->Yhat, &h->Uhat, &h->Vhat, &h->Shat, &h->y, &h->xa, &h->xb, &h->acc, &h->slices[0], &h->slices[1],
                       &h->coef, &h->snaps, &h->small, &h->smallM, &h->status, &h->gram_partial, &h->scalars};
@@ -1723,6 +2010,87 @@ int rsvdt_set_operator_csr_local(rsvdt_handle h, int64_t N_global, int64_t n_own
     return RSVDT_OK;
 }
 
+int rsvdt_set_operator_stencil(rsvdt_handle h, int ndim, const int64_t *shape, int nvar, const double *blocks_re_im,
+                               const double *mod_tab, const double *diag_tab_re_im, int64_t pt0, int64_t pt1,
+                               const int64_t *ghost_pts, int64_t n_ghost, int with_adjoint, int disc_flg, double beta,
+                               int real_operator)
+{
+    RS(bind(h));
+    if (ndim < 1 || ndim > 3 || !shape || !(nvar == 3 || nvar == 4 || nvar == 5) || !blocks_re_im || !mod_tab || !diag_tab_re_im)
+        return fail(h, RSVDT_ERR_ARG, "bad stencil operator arguments (1-3 grid dimensions, 3-5 variables per point)");
+    int64_t npts = 1;
+    int nb = 1;
+    for (int i = 0; i < ndim; i++) { if (shape[i] <= 0) return fail(h, RSVDT_ERR_ARG, "bad grid shape"); npts *= shape[i]; nb *= 3; }
+    if (pt0 < 0 || pt1 <= pt0 || pt1 > npts || n_ghost < 0 || (n_ghost > 0 && !ghost_pts)) return fail(h, RSVDT_ERR_ARG, "bad point range");
+    if ((npts + n_ghost) * nvar > (int64_t)INT32_MAX) return fail(h, RSVDT_ERR_ARG, "more than 2^31-1 local columns not supported");
+    if (disc_flg && beta < 0) return fail(h, RSVDT_ERR_USER, "'beta' must be positive, current value: %g", beta);
+    if (h->dist.on) {
+        if (h->dist.layout != 0) return fail(h, RSVDT_ERR_ARG, "stencil operators are partitioned in layout 0");
+    } else {
+        if (pt0 != 0 || pt1 != npts || n_ghost != 0) return fail(h, RSVDT_ERR_ARG, "single-GPU run: the whole grid, no ghosts");
+        h->dist = rsvdt_context::Dist();
+    }
+    h->N = (pt1 - pt0) * nvar;
+    h->n_ext = h->N + n_ghost * nvar;
+    h->own0 = 0;
+    h->N_global = npts * nvar;
+    h->real_operator = real_operator != 0;
+    DevBuf dblocks, dmod, ddiag, dghost;
+    CU(dblocks.alloc((size_t)nb * nvar * nvar * sizeof(cplx)));
+    CU(dmod.alloc(997 * sizeof(double)));
+    CU(ddiag.alloc(499 * sizeof(cplx)));
+    CU(dghost.alloc(std::max<size_t>((size_t)n_ghost, 1) * sizeof(int64_t)));
+    CU(cudaMemcpy(dblocks.p, blocks_re_im, (size_t)nb * nvar * nvar * sizeof(cplx), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dmod.p, mod_tab, 997 * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ddiag.p, diag_tab_re_im, 499 * sizeof(cplx), cudaMemcpyHostToDevice));
+    if (n_ghost) CU(cudaMemcpy(dghost.p, ghost_pts, (size_t)n_ghost * sizeof(int64_t), cudaMemcpyHostToDevice));
+    StencilSpec sp;
+    sp.d = ndim;
+    for (int i = 0; i < ndim; i++) sp.shape[i] = shape[i];
+    sp.B = nvar;
+    sp.pt0 = pt0;
+    sp.pt1 = pt1;
+    sp.blocks = dblocks.as<cplx>();
+    sp.mod_tab = dmod.as<double>();
+    sp.diag_tab = ddiag.as<cplx>();
+    sp.ghost_pts = dghost.as<int64_t>();
+    sp.n_ghost = n_ghost;
+    sp.shift = disc_flg ? beta : 0.0;
+    sp.hermitian = 0;
+    RS(build_stencil_operator(h, h->A, sp, h->n_ext));
+    h->AH.release();
+    if (with_adjoint) {
+        sp.hermitian = 1;
+        RS(build_stencil_operator(h, h->AH, sp, h->n_ext));
+    }
+    return RSVDT_OK;
+}
+
+int rsvdt_create_random_mat(rsvdt_handle h, int64_t nrows, int64_t global_row0, uint64_t seed)
+{
+    RS(bind(h));
+    if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "grid not set");
+    if (nrows <= 0 || global_row0 < 0) return fail(h, RSVDT_ERR_ARG, "bad Y_hat arguments");
+    int64_t srows, roff;
+    stack_geom(h, nrows, &srows, &roff);
+    const size_t bytes = stack_bytes(h->g.Nw_eff, srows, h->g.k);
+    RS(ensure(h, h->Yhat, bytes));
+    if (srows != nrows) CU(cudaMemsetAsync(h->Yhat.p, 0, bytes, h->stream));
+    CU(launch_random_stack(h->Yhat.as<cplx>(), nrows, srows, roff, (int)h->g.Nw_eff, (int)h->g.k, global_row0, (unsigned long long)seed, h->stream));
+    h->launches++;
+    CU(cudaStreamSynchronize(h->stream));
+    h->yhat_rows = nrows;
+    return RSVDT_OK;
+}
+
+int rsvdt_get_state(rsvdt_handle h, double *y_host, int64_t nrows)
+{
+    RS(bind(h));
+    if (!y_host || nrows != h->N || !h->grid_set || h->y.bytes < stack_bytes(1, h->n_ext, h->g.k))
+        return fail(h, RSVDT_ERR_STATE, "no RK4 state with %lld rows on the device", (long long)nrows);
+    return download_stack(h, h->y, y_host, nrows, 1, (int)h->g.k, 0, 1, h->n_ext, h->own0);
+}
+
 int rsvdt_dist_set_messages(rsvdt_handle h, int nout, const int *out_peer, const int *out_count, const int64_t *out_rows,
                             const int64_t *out_dest_row0, int nin, const int *in_peer, const int *in_count,
                             const int64_t *in_dest_row0)
@@ -1752,6 +2120,7 @@ int rsvdt_dist_set_messages(rsvdt_handle h, int nout, const int *out_peer, const
         off += m.count;
         CU(m.rows.alloc(std::max<size_t>(rows.size(), 1) * sizeof(int32_t)));
         if (m.count) CU(cudaMemcpy(m.rows.p, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        m.rows_h = rows;
         D.max_out = std::max(D.max_out, m.count);
         D.out.push_back(std::move(m));
     }
@@ -1784,11 +2153,20 @@ int rsvdt_dist_set_messages(rsvdt_handle h, int nout, const int *out_peer, const
             D.hi_begin = hi_begin;
         }
     }
-    // mailbox: two epoch-parity slots per incoming message; flags: one counter per rank
-    CU(D.mailbox.alloc(std::max<size_t>((size_t)2 * D.in_rows_total * D.nvec_max * sizeof(cplx), 256)));
-    CU(D.flags.alloc((size_t)D.nranks * sizeof(unsigned long long)));
-    CU(cudaMemset(D.flags.p, 0, (size_t)D.nranks * sizeof(unsigned long long)));
+    // mailbox: two epoch-parity slots per incoming message (unfused exchange) + three slots in ghost order (exchange fused
+    // into the stage kernel); flags: [0, P) epoch of the unfused exchange per peer, [P, 2P) epoch of the fused one,
+    // [2P] rows per mailbox slot (read by the peers at import), [2P+1] set by a kernel whose wait for a peer gave up
+    CU(D.mailbox.alloc(std::max<size_t>((size_t)5 * D.in_rows_total * D.nvec_max * sizeof(cplx), 256)));
+    CU(D.flags.alloc((size_t)(2 * D.nranks + 2) * sizeof(unsigned long long)));
+    CU(cudaMemset(D.flags.p, 0, (size_t)(2 * D.nranks + 2) * sizeof(unsigned long long)));
+    {
+        const unsigned long long rows_per_slot = (unsigned long long)D.in_rows_total;
+        CU(cudaMemcpy(D.flags.as<unsigned long long>() + 2 * D.nranks, &rows_per_slot, sizeof rows_per_slot, cudaMemcpyHostToDevice));
+    }
     D.epoch = 0;
+    D.fz_epoch = 0;
+    D.fz_ready = false;
+    D.fz_last_out = nullptr;
     return RSVDT_OK;
 }
 
@@ -1859,8 +2237,14 @@ int rsvdt_dist_ipc_import(rsvdt_handle h, const unsigned char *all_bytes, const 
         CU(cudaMemcpy(D.peer_flags_dev.p, pf.data(), pf.size() * sizeof(void *), cudaMemcpyHostToDevice));
     }
     if (!ih.empty()) CU(cudaMemcpy(D.ins_dev.p, ih.data(), ih.size() * sizeof(HaloInHost), cudaMemcpyHostToDevice));
+    D.peer_in_rows.assign((size_t)D.nranks, 0);
+    for (auto &m : D.out) {
+        unsigned long long v = 0;
+        CU(cudaMemcpy(&v, reinterpret_cast<unsigned long long *>(D.peer_flags[(size_t)m.peer]) + 2 * D.nranks, sizeof v, cudaMemcpyDeviceToHost));
+        D.peer_in_rows[(size_t)m.peer] = (int64_t)v;
+    }
     D.connected = true;
-    return RSVDT_OK;
+    return build_fused(h);
 }
 
 int rsvdt_set_allreduce(rsvdt_handle h, rsvdt_allreduce_fn fn, void *user)
@@ -1922,6 +2306,7 @@ int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *m
     h->last_ms_all = ms;
     if (rc != RSVDT_OK) return rc;
     CU(e);
+    RS(check_halo_timeout(h));
     *ms_total = ms;
     return RSVDT_OK;
 }
@@ -1943,9 +2328,12 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "use_banded")) h->use_banded = value;
     else if (!strcmp(name, "tma_variant")) h->tma_variant = value;
     else if (!strcmp(name, "use_bcsr")) h->use_bcsr = value;
+    else if (!strcmp(name, "use_tiled")) h->use_tiled = value;
+    else if (!strcmp(name, "tiled_ctas")) { if (value < 1 || value > 3) return fail(h, RSVDT_ERR_ARG, "tiled_ctas out of range"); h->tiled_ctas = value; }
     else if (!strcmp(name, "use_small")) h->use_small = value;
     else if (!strcmp(name, "use_graph")) h->use_graph = value;
     else if (!strcmp(name, "use_overlap")) h->use_overlap = value;
+    else if (!strcmp(name, "use_fused_halo")) h->use_fused_halo = value;
     else if (!strcmp(name, "use_pipeline")) h->use_pipeline = value;
     else return fail(h, RSVDT_ERR_ARG, "unknown option '%s'", name);
     return RSVDT_OK;

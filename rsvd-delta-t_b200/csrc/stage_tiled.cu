@@ -1,0 +1,379 @@
+// stage_tiled.cu -- K1f: fused RK4 stage on the tiled block-CSR operator (stage_tiled.cuh).
+//
+//   TSRK4.c:18-47 / TSTransRK4.c:15-36: ksum = Op*xin + f ; xout = ybase + cx*ksum ; acc_out = (ybase|acc_in) + ca*ksum.
+//
+// Why this shape (B200): the block-CSR stage kernel K1e streams 10.8 KB of operator entries per block row (27 blocks of
+// 5 x 5 complex) through per-thread 256-bit loads; ncu shows it latency-bound (12 warps/SM, 130 registers, issue 16 %,
+// DRAM 38-46 %).  Here the operator never passes through registers on its way in: ONE producer lane per CTA issues
+// cp.async.bulk copies of whole 12.9 KB chunks (the p-th block of 32 consecutive block rows + their column indices)
+// into a ring of shared-memory stages, completion counted by mbarriers, so up to 100 KB per CTA are in flight whatever
+// the consumer warps are doing.  Consumer thread = (block row, two test vectors): it reads the operator entries from
+// shared memory (one conflict-free 128-byte wavefront per warp instruction, broadcast over the vector pairs), gathers
+// the stage-vector rows with 256-bit loads one block ahead of their use, and keeps B x 2 complex accumulators in
+// registers.  Persistent CTAs walk the tiles in an order that puts the halo tiles first.
+//
+// Bound: HBM.  Algorithmic bytes per block row and stage: nblocks*(B*B*16 + 4) (operator) + B*nv*16*(4..6) (vectors).
+#include "stage_tiled.cuh"
+
+#define DEVFN __device__ __forceinline__
+
+namespace {
+
+struct __align__(32) cplx2 { cplx a, b; };
+
+DEVFN void cfma(cplx &s, const cplx a, const cplx b)
+{
+    s.x = fma(a.x, b.x, s.x);
+    s.x = fma(-a.y, b.y, s.x);
+    s.y = fma(a.x, b.y, s.y);
+    s.y = fma(a.y, b.x, s.y);
+}
+DEVFN cplx axpy1(double c, const cplx s, const cplx y) { return make_double2(fma(c, s.x, y.x), fma(c, s.y, y.y)); }
+
+// gathered stage-vector rows: coherent loads (ghost rows may have been written by a peer GPU while this kernel runs, after
+// the acquire of its flag), cached in L1 -- a row is re-used by up to 27 block rows of the neighbourhood
+DEVFN cplx2 ld_x(const cplx *p)
+{
+    cplx2 v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a.x), "=d"(v.a.y), "=d"(v.b.x), "=d"(v.b.y) : "l"(p) : "memory");
+    return v;
+}
+// read-once block vectors (forcing, y, accumulator): keep them out of L1
+DEVFN cplx2 ld_stream(const cplx *p)
+{
+    cplx2 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a.x), "=d"(v.a.y), "=d"(v.b.x), "=d"(v.b.y) : "l"(p) : "memory");
+    return v;
+}
+DEVFN void st2(cplx *p, const cplx v0, const cplx v1)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v0.x), "d"(v0.y), "d"(v1.x), "d"(v1.y) : "memory");
+}
+// store into a peer GPU's mailbox (NVLink): write-through, no allocation wanted locally
+DEVFN void st2_peer(cplx *p, const cplx v0, const cplx v1)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v0.x), "d"(v0.y), "d"(v1.x), "d"(v1.y) : "memory");
+}
+
+DEVFN unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+DEVFN void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DEVFN void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVFN void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+DEVFN void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+DEVFN void tma_load_1d(void *sdst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+DEVFN void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory"); }
+
+DEVFN unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+DEVFN void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr long long HALO_SPIN_LIMIT = 40000000ll;   // tens of seconds of polling: a dead peer must not hang the node
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NCW consumer warps (TB * nv/2 threads, thread = (block row of the tile, pair of test vectors)) + 1 producer warp.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int B, int NCW, int MINB>
+__global__ void __launch_bounds__((NCW + 1) * 32, MINB)
+rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int mode, const int nstages, const StageArgs a,
+                       const HaloFuse hf)
+{
+    constexpr int TB = TBCSR_TB;
+    constexpr int BB = B * B;
+    constexpr unsigned CHUNK = BB * TB * sizeof(cplx) + TB * sizeof(int32_t);
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
+    unsigned long long *empty = full + nstages;
+    unsigned char *ring = smem + 128 * ((2 * nstages * 8 + 127) / 128);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < nstages; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t ntiles = op.ntiles;
+    if (tid >= NCW * 32) {
+        // ---------------- producer: one lane keeps the ring full, running ahead over tile boundaries -----------------
+        if (tid == NCW * 32) {
+            unsigned it = 0;
+            for (int64_t i = blockIdx.x; i < ntiles; i += gridDim.x) {
+                const int64_t t = op.tile_order ? op.tile_order[i] : i;
+                const int64_t c0 = op.tile_ptr[t], c1 = op.tile_ptr[t + 1];
+                for (int64_t c = c0; c < c1; c++, it++) {
+                    const unsigned s = it % (unsigned)nstages, ph = (it / (unsigned)nstages) & 1u;
+                    mbar_wait(empty + s, ph ^ 1u);
+                    mbar_expect_tx(full + s, CHUNK);
+                    tma_load_1d(ring + (size_t)s * CHUNK, op.chunks + (size_t)c * CHUNK, CHUNK, full + s);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------------------------------------------------------------------------------
+    const int tb = tid / nvp;
+    const int iv0 = (tid - tb * nvp) * 2;
+    const bool lane_on = tb < TB;
+    const int tbs = lane_on ? tb : 0;
+    const int lane = tid & 31;
+    const bool has_f = a.f != nullptr;
+    unsigned it = 0;
+
+    for (int64_t i = blockIdx.x; i < ntiles; i += gridDim.x) {
+        const int64_t t = op.tile_order ? op.tile_order[i] : i;
+        const int nchunk = (int)(op.tile_ptr[t + 1] - op.tile_ptr[t]);
+        const int64_t br = t * TB + tbs;
+        const bool row_on = lane_on && br < op.nbrows;
+        const int64_t u0 = br * B * nv + iv0;
+
+        unsigned char tflags = 0;
+        if (hf.enabled) {
+            tflags = hf.tile_flags[t];
+            if (tflags && hf.epoch > 1) {
+                // wait until every incoming peer has published epoch E-1 (their rows of the previous stage are in my mailbox,
+                // and they are done reading the slot this launch's senders overwrite)
+                if (lane == 0) {
+                    for (int q = 0; q < hf.n_in; q++) {
+                        long long spins = 0;
+                        while (ld_acquire_sys(hf.in_flag[q]) < hf.epoch - 1) {
+                            if (++spins > HALO_SPIN_LIMIT) { *hf.timeout_flag = 1ull; break; }
+                        }
+                    }
+                }
+                __syncwarp();
+                asm volatile("fence.acq_rel.sys;\n" ::: "memory");
+            }
+        }
+
+        cplx acc[B][2];
+#pragma unroll
+        for (int r = 0; r < B; r++) {
+            cplx2 v;
+            v.a = v.b = make_double2(0.0, 0.0);
+            if (has_f && row_on) v = ld_stream(a.f + u0 + r * nv);
+            acc[r][0] = v.a;
+            acc[r][1] = v.b;
+        }
+
+        // x rows of one block: B rows x 2 test vectors
+        cplx xa[B][2], xb[B][2];
+        int col_a = -1, col_b = -1;
+        auto fetch = [&](unsigned itc, cplx (&xr)[B][2]) -> int {
+            const unsigned s = itc % (unsigned)nstages, ph = (itc / (unsigned)nstages) & 1u;
+            mbar_wait(full + s, ph);
+            const int32_t *cols = reinterpret_cast<const int32_t *>(ring + (size_t)s * CHUNK + (size_t)BB * TB * sizeof(cplx));
+            const int c = row_on ? cols[tbs] : -1;
+            if (c >= 0) {
+                const cplx *xp = (c < op.nbcols_own) ? a.xin + (int64_t)c * B * nv + iv0
+                                                     : hf.ghost_src + ((int64_t)c - op.nbcols_own) * B * nv + iv0;
+#pragma unroll
+                for (int j = 0; j < B; j++) {
+                    const cplx2 v = ld_x(xp + j * nv);
+                    xr[j][0] = v.a;
+                    xr[j][1] = v.b;
+                }
+            }
+            return c;
+        };
+        auto compute = [&](unsigned itc, const cplx (&xr)[B][2], int c) {
+            const unsigned s = itc % (unsigned)nstages;
+            if (c >= 0) {
+                const cplx *av = reinterpret_cast<const cplx *>(ring + (size_t)s * CHUNK) + tbs;
+#pragma unroll
+                for (int j = 0; j < B; j++) {
+#pragma unroll
+                    for (int r = 0; r < B; r++) {
+                        const cplx e = av[(j * B + r) * TB];
+                        cfma(acc[r][0], e, xr[j][0]);
+                        cfma(acc[r][1], e, xr[j][1]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        };
+
+        if (nchunk > 0) col_a = fetch(it, xa);
+        for (int c = 0; c < nchunk; c += 2) {
+            if (c + 1 < nchunk) col_b = fetch(it + 1, xb);
+            compute(it, xa, col_a);
+            if (c + 1 < nchunk) {
+                if (c + 2 < nchunk) col_a = fetch(it + 2, xa);
+                compute(it + 1, xb, col_b);
+            }
+            it += (c + 1 < nchunk) ? 2 : 1;
+        }
+
+        // ---------------- epilogue: stage AXPYs, local stores, peer stores of the halo rows -----------------------------
+        int64_t dest[2] = {-1, -1};
+        if (hf.enabled && (tflags & 2) && row_on) {
+            const int64_t si = hf.send_index[t];
+            dest[0] = hf.send_dest[(si * 2 + 0) * TB + tbs];
+            dest[1] = hf.send_dest[(si * 2 + 1) * TB + tbs];
+        }
+        if (row_on) {
+#pragma unroll
+            for (int r = 0; r < B; r++) {
+                const int64_t u = u0 + r * nv;
+                const cplx s0 = acc[r][0], s1 = acc[r][1];
+                cplx o0, o1;   // the vector the next stage gathers (xout, or y_{n+1} in the last stage)
+                if (mode == 0) {
+                    const cplx2 y = ld_stream(a.ybase + u);
+                    o0 = axpy1(a.cx, s0, y.a);
+                    o1 = axpy1(a.cx, s1, y.b);
+                    st2(a.xout + u, o0, o1);
+                    st2(a.acc_out + u, axpy1(a.ca, s0, y.a), axpy1(a.ca, s1, y.b));
+                } else if (mode == 1) {
+                    const cplx2 y = ld_stream(a.ybase + u);
+                    const cplx2 ac = ld_stream(a.acc_in + u);
+                    o0 = axpy1(a.cx, s0, y.a);
+                    o1 = axpy1(a.cx, s1, y.b);
+                    st2(a.xout + u, o0, o1);
+                    st2(a.acc_out + u, axpy1(a.ca, s0, ac.a), axpy1(a.ca, s1, ac.b));
+                } else {
+                    const cplx2 ac = ld_stream(a.acc_in + u);
+                    o0 = axpy1(a.ca, s0, ac.a);
+                    o1 = axpy1(a.ca, s1, ac.b);
+                    st2(a.acc_out + u, o0, o1);
+                    if (a.snap) st2(a.snap + u, o0, o1);
+                }
+#pragma unroll
+                for (int d = 0; d < 2; d++)
+                    if (dest[d] >= 0) {
+                        const int slot = (int)(dest[d] >> 48);
+                        const int64_t grow = dest[d] & 0xFFFFFFFFFFFFll;   // first ghost row (on the peer) of this block row
+                        st2_peer(hf.out_mail[slot] + (grow + r) * nv + iv0, o0, o1);
+                    }
+            }
+        }
+        if (hf.enabled && (tflags & 2)) {
+            // all rows of this tile are on their way: count the tile; the last sending tile of the launch publishes the epoch
+            __threadfence_system();
+            named_bar_sync(1, NCW * 32);
+            if (tid == 0) {
+                const int64_t si = hf.send_index[t];
+                unsigned mask = 0;
+                for (int j = 0; j < 2 * TB; j++) {
+                    const int64_t dd = hf.send_dest[si * 2 * TB + j];
+                    if (dd >= 0) mask |= 1u << (int)(dd >> 48);
+                }
+                for (int p = 0; p < hf.n_out; p++)
+                    if (mask & (1u << p)) {
+                        const unsigned long long done = atomicAdd(hf.out_done + p, 1ull) + 1ull;
+                        if (done == hf.epoch * (unsigned long long)hf.out_tiles[p]) {
+                            __threadfence_system();
+                            st_release_sys(hf.out_flag[p], hf.epoch);
+                        }
+                    }
+            }
+        }
+    }
+}
+
+template <int B, int NCW>
+cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm, cudaStream_t s)
+{
+    static int n_sm = 0;
+    static size_t smem_max = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        smem_max = (size_t)v;
+    }
+    if (ctas_per_sm < 1 || ctas_per_sm > 3) ctas_per_sm = 2;
+    const size_t chunk = tbcsr_chunk_bytes(B, TBCSR_TB);
+    if (chunk != Op.chunk_bytes) return cudaErrorInvalidValue;
+    // shared memory per SM: 228 KB, 1 KB reserved per CTA
+    const size_t budget = std::min(smem_max, (size_t)(228 * 1024) / ctas_per_sm - 1024);
+    int nst = (int)((budget - 256) / chunk);
+    if (nst > 12) nst = 12;
+    if (nst < 3) return cudaErrorInvalidValue;
+    const size_t smem = 128 * ((2 * (size_t)nst * 8 + 127) / 128) + (size_t)nst * chunk;
+    const int threads = (NCW + 1) * 32;
+    const unsigned grid = (unsigned)std::min<int64_t>(Op.ntiles, (int64_t)n_sm * ctas_per_sm);
+    if (grid == 0) return cudaSuccess;
+    const int nvp = nv / 2;
+    cudaError_t e;
+#define GO(MINB)                                                                                                              \
+    do {                                                                                                                      \
+        e = cudaFuncSetAttribute(rk4_stage_tbcsr_kernel<B, NCW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                                       \
+        rk4_stage_tbcsr_kernel<B, NCW, MINB><<<grid, threads, smem, s>>>(Op, nv, nvp, mode, nst, a, hf);                      \
+    } while (0)
+    if (ctas_per_sm <= 2) GO(2);   // (1 CTA/SM runs the 2-CTA build: same registers, deeper ring)
+    else GO(3);
+#undef GO
+    return cudaGetLastError();
+}
+
+template <int B>
+cudaError_t launch_b(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int cps, cudaStream_t s)
+{
+    const int ncw = (TBCSR_TB * (nv / 2) + 31) / 32;
+    switch (ncw) {
+        case 1: return launch_t<B, 1>(Op, nv, mode, a, hf, cps, s);
+        case 2: return launch_t<B, 2>(Op, nv, mode, a, hf, cps, s);
+        case 3: return launch_t<B, 3>(Op, nv, mode, a, hf, cps, s);
+        case 4: return launch_t<B, 4>(Op, nv, mode, a, hf, cps, s);
+        case 5: return launch_t<B, 5>(Op, nv, mode, a, hf, cps, s);
+        case 6: return launch_t<B, 6>(Op, nv, mode, a, hf, cps, s);
+        case 7: return launch_t<B, 7>(Op, nv, mode, a, hf, cps, s);
+        case 8: return launch_t<B, 8>(Op, nv, mode, a, hf, cps, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+bool tbcsr_stage_supported(int B, int nv)
+{
+    if (!(B == 3 || B == 4 || B == 5) || nv < 2 || nv % 2) return false;
+    const int ncw = (TBCSR_TB * (nv / 2) + 31) / 32;
+    return ncw <= 8;
+}
+
+cudaError_t launch_rk4_stage_tbcsr(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm,
+                                   cudaStream_t s)
+{
+    if (!tbcsr_stage_supported(Op.B, nv)) return cudaErrorInvalidValue;
+    switch (Op.B) {
+        case 3: return launch_b<3>(Op, nv, mode, a, hf, ctas_per_sm, s);
+        case 4: return launch_b<4>(Op, nv, mode, a, hf, ctas_per_sm, s);
+        case 5: return launch_b<5>(Op, nv, mode, a, hf, ctas_per_sm, s);
+        default: return cudaErrorInvalidValue;
+    }
+}

@@ -293,6 +293,46 @@ def local_operator(N, nranks, rank, gen_rows, max_bw, layout, band=None, with_ad
     return plan, A, AH, im2
 
 
+def plan_stencil(shape, nvar, nranks, rank) -> Plan:
+    """layout 0 plan of a block-stencil operator from its geometry alone (synthetic.stencil_ghost_points): the PETSC_DECIDE row
+    split must fall on grid points (N/P divisible by nvar ... or the rows are split inside a point, which the block kernels
+    cannot take)"""
+    from . import synthetic
+    npts = int(np.prod(shape))
+    N = npts * nvar
+    ranges = all_ranges(N, nranks)
+    r0, r1 = ranges[rank]
+    if r0 % nvar or r1 % nvar:
+        raise ValueError(f"row split [{r0}, {r1}) of rank {rank} cuts a grid point ({nvar} variables per point)")
+    gp = synthetic.stencil_ghost_points(shape, r0 // nvar, r1 // nvar)
+    ghosts = (gp[:, None] * nvar + np.arange(nvar, dtype=np.int64)[None, :]).reshape(-1)
+    p = Plan(0, rank, nranks, N, r0, r1, r0, (r1 - r0) + ghosts.size, 0, {}, ghosts)
+    if ghosts.size:
+        own = owner_of(ghosts, ranges)
+        for q in np.unique(own):
+            sel = np.nonzero(own == q)[0]
+            p.requests[int(q)] = (ghosts[sel], (r1 - r0) + int(sel[0]))
+    p.ghost_points = gp
+    return p
+
+
+def setup_rank_stencil(pkg, device, shape, nvar, grid, group=None, with_adjoint=True, complex_coupling=True, DiscFlg=False,
+                       beta=0.0):
+    """row-partitioned handle on a device-generated block-stencil operator (capi.RSVDt.set_operator_stencil)"""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    plan = plan_stencil(shape, nvar, world, rank)
+    r = pkg.capi.RSVDt(device)
+    r.dist_init(rank, world, 0)
+    r.set_operator_stencil(shape, nvar, (plan.r0 // nvar, plan.r1 // nvar), plan.ghost_points, with_adjoint, complex_coupling,
+                           DiscFlg, beta)
+    r.set_grid(grid["k"], grid["Nw"], grid["Ns"], grid["Nt"], grid["ResRatio"], grid["dt"], grid["w"],
+               grid.get("TransientRemoval", False))
+    connect(r, plan, group)
+    return r, plan
+
+
 def setup_rank(pkg, device, N, gen_rows, max_bw, layout, band, grid, group=None, DiscFlg=False, beta=0.0,
                with_adjoint=True):
     """one-stop construction of a row-partitioned handle; grid = dict(k, Nw, Ns, Nt, ResRatio, dt, w, TransientRemoval)"""

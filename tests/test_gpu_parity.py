@@ -79,10 +79,17 @@ def test_action_faithful_twiddles_within_reference_tolerance(pkg, O, A_GL):
                                                       ((9, 11), True, 5, 4, dict(stage_variant=1)),
                                                       ((9, 11), True, 5, 4, dict(use_bcsr=0, stage_variant=1)),
                                                       ((9, 11), True, 5, 3, dict(use_bcsr=0)),
-                                                      ((6, 7), True, 4, 6, {}), ((5, 6), True, 3, 2, {})])
+                                                      ((6, 7), True, 4, 6, {}), ((5, 6), True, 3, 2, {}),
+                                                      ((9, 11), True, 5, 4, dict(use_tiled=0)),
+                                                      ((4, 5, 6), True, 5, 8, dict(use_tiled=0)),
+                                                      ((4, 5, 6), True, 5, 8, {}), ((4, 5, 7), True, 5, 10, {}),
+                                                      ((4, 5, 6), True, 5, 8, dict(tiled_ctas=3)),
+                                                      ((4, 5, 6), True, 5, 8, dict(tiled_ctas=1)),
+                                                      ((6, 7), True, 4, 6, dict(use_tiled=0)), ((5, 6), True, 3, 2, dict(use_tiled=0)),
+                                                      ((5, 6), True, 3, 16, {}), ((3, 3, 3), True, 5, 12, {})])
 def test_action_lns_stencil(pkg, O, shape, cplx, nvar, k, opts):
-    # block-stencil operators: the block-CSR stage kernel (B = 5, 4, 3; one or two test vectors per thread) and the
-    # plain CSR kernel against the oracle
+    # block-stencil operators: the TMA-staged tiled block-CSR stage kernel (default for an even number of test vectors), the
+    # block-CSR stage kernel (B = 5, 4, 3; one or two test vectors per thread) and the plain CSR kernel against the oracle
     N, rp, ci, va = pkg.synthetic.lns_stencil(shape, nvar=nvar, complex_coupling=cplx)
     A = O.Csr(N, N, rp, ci, va)
     Nw = 8
@@ -94,6 +101,27 @@ def test_action_lns_stencil(pkg, O, shape, cplx, nvar, k, opts):
     for direct in (True, False):
         ref = _oracle_action(O, A, v, F, direct)
         assert rel_err(r.TSActionRK4(F, direct=direct), ref) < ACTION_TOL
+    r.close()
+
+
+def test_lns_stage_kernels_bit_identical(pkg, O):
+    # CSR, block-CSR and tiled block-CSR stage kernels sum every row in the same order: identical bits, both directions,
+    # on a grid whose block rows do not fill the last tile and whose boundary rows have fewer blocks (padded chunks)
+    shape, k, Nw = (5, 6, 7), 8, 4
+    N, rp, ci, va = pkg.synthetic.lns_stencil(shape, nvar=5)
+    A = O.Csr(N, N, rp, ci, va)
+    v = make_vars(O, pkg, N, k, Nw, 2.0, 0.003, 0.3)
+    F = _forcing(N, k * v.Nw_eff, 11)
+    r = _handle(pkg, A, v)
+    outs = {}
+    for name, opts in (("tiled", {}), ("bcsr", dict(use_tiled=0)), ("csr", dict(use_tiled=0, use_bcsr=0))):
+        for o in ("use_tiled", "use_bcsr"):
+            r.set_option(o, opts.get(o, 1))
+        outs[name] = [r.TSActionRK4(F, direct=d) for d in (True, False)]
+    for d in (0, 1):
+        assert np.array_equal(outs["tiled"][d], outs["bcsr"][d])
+        assert np.array_equal(outs["tiled"][d], outs["csr"][d])
+    assert rel_err(outs["tiled"][0], _oracle_action(O, A, v, F, True)) < ACTION_TOL
     r.close()
 
 
