@@ -205,6 +205,9 @@ int rsvdt_get_snapshots(rsvdt_handle h, double *Yall_host);
  * (= current Y_hat, not consumed), timed with CUDA events on the launching stream.  Reports the total time, the
  * time inside the RK4-stage kernels alone and inside the forcing-synthesis kernels alone (ms). */
 int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *ms_total);
+/* how the stage kernel reads the operator for `nvec` vectors: out4 = {format (0 CSR, 1 block-CSR, 2 tiled block-CSR),
+ * bytes of operator data one RK4 stage streams, stored entries (padding included), owned rows} */
+int rsvdt_operator_info(rsvdt_handle h, int direct, int nvec, int64_t *out4);
 /* number of kernels launched by this handle since creation / since the last reset */
 int64_t rsvdt_kernel_launches(rsvdt_handle h, int reset);
 /* tuning knobs: name in {"chunk_steps","stage_variant","idft_variant","use_graph","use_banded","use_bcsr","use_tiled",

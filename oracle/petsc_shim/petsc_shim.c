@@ -763,7 +763,7 @@ PetscErrorCode ShimVecCreateFrom(PetscInt n, const PetscScalar *a, Vec *v)
 PetscScalar *ShimVecArray(Vec v) { return v->a; }
 
 /* MatLoad: binary Mat record {classid, M, N, nz, rowlens[M], cols[nz], vals[nz]}; nz = -1 marks the dense-native
- * record (column-major values).  Either record can be loaded into either an AIJ or a dense Mat, as in PETSc. */
+ * record (M*N values stored row by row, MatView_Dense_Binary of PETSc >= 3.14).  Either record can be loaded into either an AIJ or a dense Mat, as in PETSc. */
 PetscErrorCode MatLoad(Mat A, PetscViewer viewer)
 {
     FILE *f = viewer->f;
@@ -797,7 +797,10 @@ PetscErrorCode MatLoad(Mat A, PetscViewer viewer)
     }
     if (A->type == MT_DENSE) {
         mat_alloc_dense(A);
-        if (nz == -1) memcpy(A->a, vals, (size_t)M * (size_t)N * sizeof(PetscScalar));
+        if (nz == -1) {   /* dense-native values are stored row by row (MatLoad_Dense_Binary, PETSc >= 3.14) */
+            for (PetscInt r = 0; r < M; r++)
+                for (PetscInt c = 0; c < N; c++) A->a[r + A->lda * c] = vals[r * N + c];
+        }
         else {
             PetscInt p = 0;
             for (PetscInt r = 0; r < M; r++)
@@ -815,7 +818,7 @@ PetscErrorCode MatLoad(Mat A, PetscViewer viewer)
                 A->ia[r + 1] = (r + 1) * N;
                 for (PetscInt c = 0; c < N; c++) {
                     A->ja[r * N + c] = c;
-                    A->va[r * N + c] = vals[r + M * c];
+                    A->va[r * N + c] = vals[r * N + c];
                 }
             }
         } else {

@@ -168,15 +168,18 @@ def trans_steps(A: Csr, v: Vars, nsteps, q0):
     return q
 
 
-def time_forced_steps(A: Csr, v: Vars, F_hat_k, ncols, warm, nsteps):
-    """seconds spent in `nsteps` calls of TSRK4.c on each of `ncols` test vectors (run one after the other)"""
+def time_forced_steps(A: Csr, v: Vars, F_hat_k, ncols, warm, nsteps, want_state=False):
+    """seconds spent in `nsteps` calls of TSRK4.c on each of `ncols` test vectors (run one after the other);
+    want_state: also the vector y the reference's loop holds after step warm + nsteps (of the last test vector)"""
     Fk = _F(F_hat_k)
     assert Fk.shape == (v.N, v.Nw_eff)
     sec = C.c_double()
     vc = v.c()
+    y = np.empty(v.N, c128) if want_state else None
     _check(lib().ref_time_forced_steps(C.byref(vc), _p(A.rowptr), _p(A.col), _p(A.val), _p(Fk), C.c_int64(ncols),
-                                       C.c_int64(warm), C.c_int64(nsteps), C.byref(sec), None), "TSRK4 timing")
-    return sec.value
+                                       C.c_int64(warm), C.c_int64(nsteps), C.byref(sec), _p(y) if want_state else None),
+           "TSRK4 timing")
+    return (sec.value, y) if want_state else sec.value
 
 
 def run_executable(workdir, yaml_name="variables.yaml", timeout=3600, threads=None, autoinit=False):

@@ -315,6 +315,13 @@ class RSVDt:
         self._ck(lib().rsvdt_time_forced_steps(self._h, C.c_int(int(direct)), C.c_int64(nsteps), C.byref(ms)))
         return ms.value
 
+    def operator_info(self, direct=True, nvec=None):
+        out = np.zeros(4, np.int64)
+        nvec = self.grid.k if nvec is None else nvec
+        self._ck(lib().rsvdt_operator_info(self._h, C.c_int(int(direct)), C.c_int(int(nvec)), _p(out)))
+        return {"format": ("csr", "bcsr", "tiled-bcsr")[int(out[0])], "bytes_per_stage": int(out[1]), "stored_entries": int(out[2]),
+                "rows": int(out[3])}
+
     def kernel_launches(self, reset=False) -> int:
         return lib().rsvdt_kernel_launches(self._h, C.c_int(int(reset)))
 

@@ -2311,6 +2311,29 @@ int rsvdt_time_forced_steps(rsvdt_handle h, int direct, int64_t nsteps, float *m
     return RSVDT_OK;
 }
 
+int rsvdt_operator_info(rsvdt_handle h, int direct, int nvec, int64_t *out4)
+{
+    if (!h || !out4) return RSVDT_ERR_ARG;
+    const CsrOwned &Op = direct ? h->A : h->AH;
+    if (!Op.set) return fail(h, RSVDT_ERR_STATE, "operator not set");
+    out4[3] = h->N;
+    if (tiled_active(h, Op, nvec)) {
+        out4[0] = 2;
+        out4[1] = (int64_t)((size_t)Op.tb.nchunks * Op.tb.chunk_bytes + (size_t)(Op.tb.ntiles + 1) * sizeof(int64_t));
+        out4[2] = Op.tb.nchunks * (int64_t)Op.tb.TB * Op.tb.B * Op.tb.B;
+    } else if (h->use_bcsr && Op.bcsr_valid && bcsr_stage_supported(Op.bcsr.B, nvec)) {
+        const int64_t BS = (Op.bcsr.B * Op.bcsr.B + 1) & ~1;
+        out4[0] = 1;
+        out4[1] = Op.bcsr.nblocks * (BS * (int64_t)sizeof(cplx) + 4) + (Op.bcsr.nbrows + 1) * 8;
+        out4[2] = Op.bcsr.nblocks * (int64_t)Op.bcsr.B * Op.bcsr.B;
+    } else {
+        out4[0] = 0;
+        out4[1] = Op.d.nnz * (int64_t)(sizeof(cplx) + 4) + (Op.d.nrows + 1) * 8;
+        out4[2] = Op.d.nnz;
+    }
+    return RSVDT_OK;
+}
+
 int64_t rsvdt_kernel_launches(rsvdt_handle h, int reset)
 {
     if (!h) return -1;

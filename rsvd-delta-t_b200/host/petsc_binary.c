@@ -87,7 +87,8 @@ int pb_read_mat(const char *path, pb_csr *out)
     out->val = (double *)malloc((size_t)(nnz > 0 ? nnz : 1) * 16);
     if (!out->rowptr || !out->col || !out->val) { fclose(f); pb_free_csr(out); return pb_fail("out of memory"); }
     if (native_dense) {
-        /* column-major scalars; convert to a full CSR */
+        /* PETSc >= 3.14 (MatView_Dense_Binary / MatLoad_Dense_Binary; the reference targets 3.19): the M*N scalars of the
+         * dense-native record are stored ROW by row, val[r*N + c]; convert to a full CSR */
         const int64_t rest = file_size(f) - ftell(f);
         const int cplx = rest >= M * N * 16;
         double *tmp = (double *)malloc((size_t)M * N * (cplx ? 16 : 8));
@@ -96,8 +97,8 @@ int pb_read_mat(const char *path, pb_csr *out)
         for (int64_t r = 0; r < M; r++)
             for (int64_t c = 0; c < N; c++) {
                 out->col[r * N + c] = c;
-                out->val[2 * (r * N + c)] = cplx ? tmp[2 * (c * M + r)] : tmp[c * M + r];
-                out->val[2 * (r * N + c) + 1] = cplx ? tmp[2 * (c * M + r) + 1] : 0.0;
+                out->val[2 * (r * N + c)] = cplx ? tmp[2 * (r * N + c)] : tmp[r * N + c];
+                out->val[2 * (r * N + c) + 1] = cplx ? tmp[2 * (r * N + c) + 1] : 0.0;
             }
         free(tmp);
         fclose(f);

@@ -6,7 +6,7 @@ TransientRunRK4.c:82-86,201-209):
 
   Mat  : int MAT_FILE_CLASSID (1211216), M, N, nnz; M row lengths; nnz column indices; nnz scalars.
          Dense matrices written by MatView in the default format use the same record with every entry
-         present (row by row).  nnz == -1 is PETSc's "native dense" record (column-major values) and is
+         present (row by row).  nnz == -1 is PETSc's "native dense" record (values row by row, as MatView_Dense_Binary of PETSc >= 3.14 writes them) and is
          accepted on input.
   Vec  : int VEC_FILE_CLASSID (1211214), n; n scalars.
 
@@ -41,14 +41,14 @@ def read_mat(path: str):
     hdr = np.frombuffer(buf[: 4 * isz], it).astype(np.int64)
     M, N, nnz = int(hdr[1]), int(hdr[2]), int(hdr[3])
     off = 4 * isz
-    if nnz == -1:  # native dense: column-major scalars
+    if nnz == -1:  # native dense: M*N scalars, row by row (MatLoad_Dense_Binary, PETSc 3.19)
         rest = len(buf) - off
         cplx = rest >= M * N * 16
         if cplx:
             vals = np.frombuffer(buf[off: off + M * N * 16], ">f8").reshape(-1, 2)
-            dense = (vals[:, 0] + 1j * vals[:, 1]).reshape(N, M).T
+            dense = (vals[:, 0] + 1j * vals[:, 1]).reshape(M, N)
         else:
-            dense = np.frombuffer(buf[off: off + M * N * 8], ">f8").astype(np.complex128).reshape(N, M).T
+            dense = np.frombuffer(buf[off: off + M * N * 8], ">f8").astype(np.complex128).reshape(M, N)
         rowptr = np.arange(M + 1, dtype=np.int64) * N
         col = np.tile(np.arange(N, dtype=np.int64), M)
         return M, N, rowptr, col, np.ascontiguousarray(dense).reshape(-1)
@@ -180,11 +180,9 @@ class MatRowReader:
         p0, p1 = int(self.rowptr[r0]), int(self.rowptr[r1])
         rp = (self.rowptr[r0:r1 + 1] - p0).astype(np.int64)
         with open(self.path, "rb") as f:
-            if self.native_dense:   # column-major values: gather the rows column by column
-                out = np.empty((r1 - r0, self.N), np.complex128)
-                for c in range(self.N):
-                    out[:, c] = self._scalars(f, c * self.M + r0, r1 - r0)
-                return rp, np.tile(np.arange(self.N, dtype=np.int64), r1 - r0), out.reshape(-1)
+            if self.native_dense:   # values row by row: the rows asked for are one contiguous range
+                out = self._scalars(f, r0 * self.N, (r1 - r0) * self.N)
+                return rp, np.tile(np.arange(self.N, dtype=np.int64), r1 - r0), np.ascontiguousarray(out, dtype=np.complex128)
             f.seek(self.off_col + p0 * self.isz)
             col = np.frombuffer(f.read((p1 - p0) * self.isz), self.it).astype(np.int64)
             val = self._scalars(f, p0, p1 - p0)
