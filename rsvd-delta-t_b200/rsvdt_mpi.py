@@ -195,11 +195,6 @@ def hms(sec):
 
 # ---------------------------------------------------------------------------------------------------------- the run
 class Run:
-    # Test seam: a factory standing in for dist.setup_rank.  tests/test_mpi_driver.py sets it (together with
-    # RSVDT_MPI_HOSTONLY=1, i.e. gloo and no CUDA) to drive this file's host logic -- input rules, partitioned I/O, result
-    # files -- on CPU with the oracle as the numerical engine.  The product never sets it.
-    backend = None
-
     def __init__(self, argv):
         import torch
         import torch.distributed as dist
@@ -285,13 +280,24 @@ class Run:
         if self.hostonly:
             self.log(f"host-only dry run: N = {N}, rows [{r0}, {r1}) on rank {self.rank}, band {lo}/{hi}, layout {layout}, "
                      f"real = {real}, k = {v['k']}")
-            if Run.backend is None:
-                raise UserError("host-only dry run stops before rsvdt_create (no CPU fallback)")
-        setup_rank = Run.backend if (self.hostonly and Run.backend is not None) else pkg.dist.setup_rank
         band = (lo, hi)
+        # block-stencil operators of BASELINE.json: written by a kernel straight into the device layout (bit-identical to the
+        # host generator, tests/test_stencil_gen.py) instead of passing 65 GB of CSR through the host
+        on_device = (not self.hostonly and getattr(rd, "kind", "") in ("lns2d", "lns3d") and not v["TransRun"]
+                     and v["k"] % 2 == 0 and os.environ.get("RSVDT_SYNTH_ON_DEVICE", "1") != "0")
         while True:
-            self.r, self.plan = setup_rank(pkg, self.local_rank, N, rd.rows, max_bw, layout, band if layout == 1 else None,
-                                           grid, DiscFlg=v["DiscFlg"], beta=v["beta"])
+            try:
+                if on_device:
+                    layout = 0
+                    self.r, self.plan = pkg.dist.setup_rank_stencil(pkg, self.local_rank, rd.shape, rd.nvar, grid,
+                                                                    DiscFlg=v["DiscFlg"], beta=v["beta"])
+                else:
+                    self.r, self.plan = pkg.dist.setup_rank(pkg, self.local_rank, N, rd.rows, max_bw, layout,
+                                                            band if layout == 1 else None, grid, DiscFlg=v["DiscFlg"], beta=v["beta"])
+            except pkg.capi.RsvdtError as e:
+                if self.hostonly:      # no CUDA device behind a host-only dry run: this is where it ends
+                    raise UserError("host-only dry run stops before rsvdt_create (no CPU fallback)")
+                raise UserError(str(e))
             if layout == 0:
                 break
             # layout 1 needs rows the fused band kernel accepts on EVERY rank, for the number of vectors this run advances
@@ -388,6 +394,10 @@ class Run:
                 raise UserError(f"Input forcing has {rd.N} columns, not a multiple of Nw = {v['Nw_eff']}")
         else:
             self.log("Generating a random forcing matrix")
+            if not self.hostonly and hasattr(self.r, "CreateRandomMat"):
+                # CreateRandomMat.c:36-39 on the device, keyed by (seed, global row, column): no 10 GB host array per rank
+                self.r.CreateRandomMat(b1 - b0, b0, v["RandSeed"])
+                return
             F = random_rows(v["RandSeed"], b0, b1, v["k"] * v["Nw_eff"])
         if int(self.r.grid.k) != v["k"]:
             raise UserError(f"internal: the ranks were connected for k = {int(self.r.grid.k)} test vectors, the forcing has {v['k']}")

@@ -219,7 +219,9 @@ def _flow_worker(rank, world, port, tmp, q):
         from oracle import oracle as O
         import fake_backend
         drv = importlib.import_module("rsvdt_b200.rsvdt_mpi")
-        drv.Run.backend = staticmethod(fake_backend.make_backend(O))
+        # the test seam lives here, not in the product: the oracle-backed stand-in replaces dist.setup_rank for this process
+        drv_pkg = sys.modules["rsvdt_b200"]
+        drv_pkg.dist.setup_rank = fake_backend.make_backend(O)
         os.chdir(tmp)
         if rank != 0:
             sys.stdout = open(os.devnull, "w")
