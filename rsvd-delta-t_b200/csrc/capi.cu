@@ -85,7 +85,7 @@ struct CsrOwned {
     bool bcsr_valid = false;
     // tiled block-CSR form (stage_tiled.cuh): the layout the TMA-staged stage kernel streams
     TbcsrDev tb;
-    DevBuf t_chunks, t_tileptr, t_order, t_flags;
+    DevBuf t_chunks, t_tileptr, t_order, t_flags, t_winptr, t_win;
     bool tbcsr_valid = false;
     bool stencil_only = false;                    // generated on the device: no CSR / block-CSR copies exist
     std::vector<unsigned char> tile_ghost;        // [ntiles] 1: a block column of the tile is a ghost (row-partitioned runs)
@@ -95,7 +95,8 @@ struct CsrOwned {
     {
         rowptr.release(); col.release(); val.release(); dia.release(); tile_ok.release(); slow_ranges.release();
         b_rowptr.release(); b_col.release(); b_val.release(); bcsr = BcsrDev(); bcsr_valid = false;
-        t_chunks.release(); t_tileptr.release(); t_order.release(); t_flags.release(); tb = TbcsrDev(); tbcsr_valid = false;
+        t_chunks.release(); t_tileptr.release(); t_order.release(); t_flags.release(); t_winptr.release(); t_win.release();
+        tb = TbcsrDev(); tbcsr_valid = false;
         stencil_only = false; tile_ghost.clear();
         d = CsrDev(); set = false; dia_valid = false; plan_nv = -1; plan_ok = false; row_regular.clear();
     }
@@ -150,7 +151,7 @@ struct rsvdt_context {
         const cplx *fz_last_out = nullptr;    // block vector whose halo rows sit in mailbox slot fz_epoch % 3
         int fz_last_nv = 0;
         std::vector<int64_t> peer_in_rows;    // in_rows_total of every peer (mailbox slot size over there)
-        DevBuf fz_send_index, fz_send_dest, fz_out_tiles, fz_out_done;
+        DevBuf fz_send_index, fz_send_dest, fz_send_mask, fz_out_tiles, fz_out_done;
     } dist;
 
     // Weight_matrices (Variables.h:69-80): 0=W_f_sqrt_inv 1=B 2=W_q_sqrt_inv 3=W_q_sqrt 4=C, and their conj-transposes
@@ -177,6 +178,7 @@ struct rsvdt_context {
     int64_t tma_variant = 0;  // 0: tiles sized for 3 CTAs/SM, 1: for 2 CTAs/SM
     int64_t use_bcsr = 1;     // block-CSR stage kernel when the operator has dense B x B blocks
     int64_t use_tiled = 1;    // ... and its TMA-staged tiled form (stage_tiled.cu) when the number of vectors is even
+    int64_t tiled_stages = 0; // operator ring depth of the tiled stage kernel; 0 = what shared memory holds
     int64_t tiled_ctas = 2;   // resident CTAs per SM of the tiled stage kernel (ring depth follows from the shared memory left)
     int64_t use_small = 1;    // single-CTA persistent kernel when the whole block vector fits in one SM's shared memory
 
@@ -396,9 +398,28 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
             const int TB = TBCSR_TB;
             const int64_t ntiles = (nbrows + TB - 1) / TB;
             std::vector<int64_t> tptr((size_t)ntiles + 1, 0);
+            // Tiles whose blocks line up on few block diagonals (stencils) are cut by diagonal: chunk = one diagonal, rows that
+            // lack it padded in place -- the order of the blocks inside a row is kept (ascending columns), and the chunk's
+            // columns become affine in the block row, which is what the x windows of the stage kernel need.  Other tiles are
+            // cut by position in the row (p-th block of every row).
+            std::vector<std::vector<int64_t>> tile_diags((size_t)ntiles);
             for (int64_t t = 0; t < ntiles; t++) {
                 int64_t mx = 0;
-                for (int64_t br = t * TB; br < std::min(nbrows, (t + 1) * TB); br++) mx = std::max(mx, brp[(size_t)br + 1] - brp[(size_t)br]);
+                std::vector<int64_t> dg;
+                bool ascending = true;   // (the diagonal cut keeps the order of a row's blocks only if they ascend)
+                for (int64_t br = t * TB; br < std::min(nbrows, (t + 1) * TB); br++) {
+                    mx = std::max(mx, brp[(size_t)br + 1] - brp[(size_t)br]);
+                    for (int64_t q = brp[(size_t)br]; q < brp[(size_t)br + 1]; q++) {
+                        dg.push_back((int64_t)bc[(size_t)q] - br);
+                        if (q > brp[(size_t)br] && bc[(size_t)q] <= bc[(size_t)q - 1]) ascending = false;
+                    }
+                }
+                std::sort(dg.begin(), dg.end());
+                dg.erase(std::unique(dg.begin(), dg.end()), dg.end());
+                if (ascending && (int64_t)dg.size() <= mx + std::max<int64_t>(4, mx / 4)) {
+                    mx = (int64_t)dg.size();
+                    tile_diags[(size_t)t] = std::move(dg);
+                }
                 tptr[(size_t)t + 1] = tptr[(size_t)t] + mx;
             }
             const size_t cb = tbcsr_chunk_bytes(B, TB);
@@ -412,20 +433,49 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
             parallel_for(ntiles, [&](int64_t t0, int64_t t1) {
                 for (int64_t t = t0; t < t1; t++) {
                     const int64_t nch = tptr[(size_t)t + 1] - tptr[(size_t)t];
+                    const std::vector<int64_t> &dg = tile_diags[(size_t)t];
                     for (int64_t pch = 0; pch < nch; pch++) {
                         unsigned char *base = chunks.data() + (size_t)(tptr[(size_t)t] + pch) * cb;
                         cplx *cv = reinterpret_cast<cplx *>(base);
                         int32_t *cc = reinterpret_cast<int32_t *>(base + (size_t)B * B * TB * sizeof(cplx));
                         for (int tbi = 0; tbi < TB; tbi++) {
                             const int64_t br = t * TB + tbi;
-                            const bool on = br < nbrows && pch < brp[(size_t)br + 1] - brp[(size_t)br];
-                            cc[tbi] = on ? bc[(size_t)(brp[(size_t)br] + pch)] : -1;
+                            int64_t q = -1;   // the block of row br that belongs to this chunk
+                            if (br < nbrows) {
+                                if (dg.empty()) { if (pch < brp[(size_t)br + 1] - brp[(size_t)br]) q = brp[(size_t)br] + pch; }
+                                else {
+                                    const int32_t want = (int32_t)(br + dg[(size_t)pch]);
+                                    const int32_t *b0 = bc.data() + brp[(size_t)br], *b1 = bc.data() + brp[(size_t)br + 1];
+                                    const int32_t *f = std::lower_bound(b0, b1, want);
+                                    if (f != b1 && *f == want) q = f - bc.data();
+                                }
+                            }
+                            cc[tbi] = q >= 0 ? bc[(size_t)q] : -1;
                             for (int e = 0; e < B * B; e++)
-                                cv[(size_t)e * TB + tbi] = on ? bv[(size_t)((brp[(size_t)br] + pch) * BS + e)] : make_double2(0.0, 0.0);
+                                cv[(size_t)e * TB + tbi] = q >= 0 ? bv[(size_t)(q * BS + e)] : make_double2(0.0, 0.0);
                         }
+                        cc[TB] = TBCSR_GATHER; cc[TB + 1] = cc[TB + 2] = cc[TB + 3] = 0;
                     }
                 }
             });
+            // x windows (stage_tiled.cuh): planned from the chunk columns, written into the chunk headers
+            {
+                std::vector<int32_t> ccols((size_t)std::max<int64_t>(nchunks, 1) * TB);
+                for (int64_t pch = 0; pch < nchunks; pch++)
+                    memcpy(ccols.data() + (size_t)pch * TB, chunks.data() + (size_t)pch * cb + (size_t)B * B * TB * sizeof(cplx), (size_t)TB * sizeof(int32_t));
+                TbcsrPlan plan;
+                tbcsr_plan_windows(ntiles, tptr.data(), ccols.data(), nbrows, out_cols / B, TB, TBCSR_WMAX, plan);
+                for (int64_t pch = 0; pch < nchunks; pch++)
+                    memcpy(chunks.data() + (size_t)pch * cb + (size_t)B * B * TB * sizeof(cplx) + (size_t)TB * sizeof(int32_t), plan.hdr.data() + (size_t)pch * 4, 16);
+                CU(dst.t_winptr.alloc(plan.win_ptr.size() * sizeof(int64_t)));
+                CU(dst.t_win.alloc(std::max<size_t>(plan.win.size(), 1) * sizeof(TbcsrWindow)));
+                CU(cudaMemcpy(dst.t_winptr.p, plan.win_ptr.data(), plan.win_ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+                if (!plan.win.empty()) CU(cudaMemcpy(dst.t_win.p, plan.win.data(), plan.win.size() * sizeof(TbcsrWindow), cudaMemcpyHostToDevice));
+                dst.tb.win_ptr = dst.t_winptr.as<int64_t>();
+                dst.tb.win = dst.t_win.as<TbcsrWindow>();
+                dst.tb.wmax = TBCSR_WMAX;
+                dst.tb.nwindows_chunks = plan.window_chunks;
+            }
             CU(dst.t_tileptr.alloc(tptr.size() * sizeof(int64_t)));
             CU(dst.t_chunks.alloc(chunks.size()));
             CU(cudaMemcpy(dst.t_tileptr.p, tptr.data(), tptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -650,11 +700,12 @@ cudaError_t launch_stage_any(rsvdt_handle h, const CsrOwned &Op, int nv, int mod
             hf.tile_flags = Op.t_flags.as<unsigned char>();
             hf.send_index = D.fz_send_index.as<int32_t>();
             hf.send_dest = D.fz_send_dest.as<int64_t>();
+            hf.send_mask = D.fz_send_mask.as<int32_t>();
             hf.timeout_flag = flags + 2 * D.nranks + 1;
             D.fz_last_out = mode == 2 ? a.acc_out : a.xout;
             D.fz_last_nv = nv;
         }
-        return launch_rk4_stage_tbcsr(Op.tb, nv, mode, a, hf, (int)h->tiled_ctas, h->stream);
+        return launch_rk4_stage_tbcsr(Op.tb, nv, mode, a, hf, (int)h->tiled_ctas, (int)h->tiled_stages, h->stream);
     }
     if (Op.stencil_only) return cudaErrorNotSupported;   // device-generated operators exist in the tiled form only (even nv)
     if (h->use_bcsr && Op.bcsr_valid && bcsr_stage_supported(Op.bcsr.B, nv))
@@ -1420,6 +1471,14 @@ int build_fused(rsvdt_handle h)
             if (!seen[(size_t)t]) { seen[(size_t)t] = 1; out_tiles[i]++; }
         }
     }
+    std::vector<int32_t> send_mask(send_dest.size() / (size_t)(2 * TB), 0);
+    for (size_t si = 0; si < send_mask.size(); si++)
+        for (int j = 0; j < 2 * TB; j++) {
+            const int64_t dd = send_dest[si * 2 * TB + (size_t)j];
+            if (dd >= 0) send_mask[si] |= 1 << (int)(dd >> 48);
+        }
+    CU(D.fz_send_mask.alloc(std::max<size_t>(send_mask.size(), 1) * sizeof(int32_t)));
+    if (!send_mask.empty()) CU(cudaMemcpy(D.fz_send_mask.p, send_mask.data(), send_mask.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CU(D.fz_send_index.alloc(std::max<size_t>(send_index.size(), 1) * sizeof(int32_t)));
     CU(D.fz_send_dest.alloc(std::max<size_t>(send_dest.size(), 1) * sizeof(int64_t)));
     CU(D.fz_out_tiles.alloc(out_tiles.size() * sizeof(int32_t)));
@@ -1469,9 +1528,10 @@ int build_stencil_operator(rsvdt_handle h, CsrOwned &Op, StencilSpec sp, int64_t
     const int TB = TBCSR_TB, B = sp.B;
     const int64_t nbrows = sp.pt1 - sp.pt0;
     const int64_t ntiles = (nbrows + TB - 1) / TB;
-    DevBuf counts, hasg;
+    DevBuf counts, masks, hasg;
     CU(counts.alloc((size_t)ntiles * sizeof(int32_t)));
-    CU(stencil_tile_counts(sp, TB, ntiles, counts.as<int32_t>(), h->stream));
+    CU(masks.alloc((size_t)ntiles * sizeof(uint32_t)));
+    CU(stencil_tile_counts(sp, TB, ntiles, counts.as<int32_t>(), masks.as<uint32_t>(), h->stream));
     std::vector<int32_t> cnt((size_t)ntiles);
     CU(cudaMemcpyAsync(cnt.data(), counts.p, (size_t)ntiles * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1484,10 +1544,28 @@ int build_stencil_operator(rsvdt_handle h, CsrOwned &Op, StencilSpec sp, int64_t
     CU(hasg.alloc((size_t)ntiles));
     CU(cudaMemsetAsync(hasg.p, 0, (size_t)ntiles, h->stream));
     CU(cudaMemcpyAsync(Op.t_tileptr.p, tptr.data(), tptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    CU(stencil_fill(sp, TB, ntiles, Op.t_tileptr.as<int64_t>(), Op.t_chunks.as<unsigned char>(), hasg.as<unsigned char>(), h->stream));
+    CU(stencil_fill(sp, TB, ntiles, Op.t_tileptr.as<int64_t>(), masks.as<uint32_t>(), Op.t_chunks.as<unsigned char>(), hasg.as<unsigned char>(), h->stream));
     Op.tile_ghost.assign((size_t)ntiles, 0);
     CU(cudaMemcpyAsync(Op.tile_ghost.data(), hasg.p, (size_t)ntiles, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    {   // x windows: the chunk columns come back (4 B per block), the plan goes into the chunk headers
+        std::vector<int32_t> ccols((size_t)std::max<int64_t>(nchunks, 1) * TB);
+        const size_t coff = (size_t)B * B * TB * sizeof(cplx);
+        if (nchunks) CU(cudaMemcpy2D(ccols.data(), (size_t)TB * sizeof(int32_t), Op.t_chunks.as<unsigned char>() + coff, cb,
+                                     (size_t)TB * sizeof(int32_t), (size_t)nchunks, cudaMemcpyDeviceToHost));
+        TbcsrPlan plan;
+        tbcsr_plan_windows(ntiles, tptr.data(), ccols.data(), nbrows, n_ext / B, TB, TBCSR_WMAX, plan);
+        if (nchunks) CU(cudaMemcpy2D(Op.t_chunks.as<unsigned char>() + coff + (size_t)TB * sizeof(int32_t), cb, plan.hdr.data(), 16, 16,
+                                     (size_t)nchunks, cudaMemcpyHostToDevice));
+        CU(Op.t_winptr.alloc(plan.win_ptr.size() * sizeof(int64_t)));
+        CU(Op.t_win.alloc(std::max<size_t>(plan.win.size(), 1) * sizeof(TbcsrWindow)));
+        CU(cudaMemcpy(Op.t_winptr.p, plan.win_ptr.data(), plan.win_ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        if (!plan.win.empty()) CU(cudaMemcpy(Op.t_win.p, plan.win.data(), plan.win.size() * sizeof(TbcsrWindow), cudaMemcpyHostToDevice));
+        Op.tb.win_ptr = Op.t_winptr.as<int64_t>();
+        Op.tb.win = Op.t_win.as<TbcsrWindow>();
+        Op.tb.wmax = TBCSR_WMAX;
+        Op.tb.nwindows_chunks = plan.window_chunks;
+    }
     h->launches += 2;
     Op.tb.B = B;
     Op.tb.TB = TB;
@@ -1568,7 +1646,7 @@ int rsvdt_destroy(rsvdt_handle h)
         if (h->dist.peer_flags[(size_t)p]) cudaIpcCloseMemHandle(h->dist.peer_flags[(size_t)p]);
     }
     DevBuf *dbufs[] = {&h->dist.mailbox, &h->dist.flags, &h->dist.msgs_dev, &h->dist.ins_dev, &h->dist.peer_flags_dev,
-                       &h->dist.fz_send_index, &h->dist.fz_send_dest, &h->dist.fz_out_tiles, &h->dist.fz_out_done};
+                       &h->dist.fz_send_index, &h->dist.fz_send_dest, &h->dist.fz_send_mask, &h->dist.fz_out_tiles, &h->dist.fz_out_done};
     for (DevBuf *b : dbufs) b->release();
     DevBuf *bufs[] = {&h->Yhat, &h->Uhat, &h->Vhat, &h->Shat, &h->y, &h->xa, &h->xb, &h->acc, &h->slices[0], &h->slices[1],
                       &h->coef, &h->snaps, &h->small, &h->smallM, &h->status, &h->gram_partial, &h->scalars};
@@ -2352,6 +2430,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "tma_variant")) h->tma_variant = value;
     else if (!strcmp(name, "use_bcsr")) h->use_bcsr = value;
     else if (!strcmp(name, "use_tiled")) h->use_tiled = value;
+    else if (!strcmp(name, "tiled_stages")) h->tiled_stages = value;
     else if (!strcmp(name, "tiled_ctas")) { if (value < 1 || value > 3) return fail(h, RSVDT_ERR_ARG, "tiled_ctas out of range"); h->tiled_ctas = value; }
     else if (!strcmp(name, "use_small")) h->use_small = value;
     else if (!strcmp(name, "use_graph")) h->use_graph = value;

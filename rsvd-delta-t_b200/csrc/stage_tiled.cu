@@ -98,44 +98,95 @@ constexpr long long HALO_SPIN_LIMIT = 40000000ll;   // tens of seconds of pollin
 
 // ---------------------------------------------------------------------------------------------------------------------
 // NCW consumer warps (TB * nv/2 threads, thread = (block row of the tile, pair of test vectors)) + 1 producer warp.
+//
+// Shared memory: [mbarriers][operator ring: NSA chunks][x ring: NSX windows of WMAX padded block rows].
+// Chunk = [B*B][TB] entries, [TB] block columns, header {xoff, flags, -, -}:
+//   xoff != TBCSR_GATHER: the block columns of the chunk are affine in the block row (col = base + tb) and their rows of the
+//     stage vector sit in the current x window at block (xoff + tb); flags bit0: first chunk of its window (wait for it),
+//     bit1: last chunk of its window (release it).  The window [start, start + n) -- one contiguous range of the stage
+//     vector, e.g. the 34 blocks the three x-neighbours of 32 consecutive grid points share -- is brought in by the
+//     producer warp with n bulk copies (one per block row, padded by 16 B so that the 8 block rows a warp reads at once
+//     fall into distinct banks), so each gathered row crosses the L2 -> SM crossbar once per window instead of once per
+//     block: 2.8x fewer bytes than per-thread gathers for the 27-point stencil, and no load latency in the FMA loop.
+//   xoff == TBCSR_GATHER: general sparsity -- per-thread 256-bit gathers straight from global memory.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int B, int NCW, int MINB>
 __global__ void __launch_bounds__((NCW + 1) * 32, MINB)
-rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int mode, const int nstages, const StageArgs a,
-                       const HaloFuse hf)
+rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int mode, const int nsa, const int nsx,
+                       const int wmax, const StageArgs a, const HaloFuse hf)
 {
     constexpr int TB = TBCSR_TB;
     constexpr int BB = B * B;
-    constexpr unsigned CHUNK = BB * TB * sizeof(cplx) + TB * sizeof(int32_t);
+    constexpr unsigned CHUNK = BB * TB * sizeof(cplx) + TB * sizeof(int32_t) + 4 * sizeof(int32_t);
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
-    unsigned long long *empty = full + nstages;
-    unsigned char *ring = smem + 128 * ((2 * nstages * 8 + 127) / 128);
+    unsigned long long *empty = full + nsa;
+    unsigned long long *xfull = empty + nsa;
+    unsigned long long *xempty = xfull + nsx;
+    unsigned char *ring = smem + 128 * ((2 * (nsa + nsx) * 8 + 127) / 128);
+    const unsigned xstride = (unsigned)(B * nv) * sizeof(cplx) + 16u;   // padded block row of the stage vector
+    const unsigned xslot = xstride * (unsigned)wmax;
+    unsigned char *xring = ring + (size_t)nsa * CHUNK;
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < nstages; s++) {
+        for (int s = 0; s < nsa; s++) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, NCW);
+        }
+        for (int s = 0; s < nsx; s++) {
+            mbar_init(xfull + s, 1);
+            mbar_init(xempty + s, NCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
 
     const int64_t ntiles = op.ntiles;
+    const int lane = tid & 31;
     if (tid >= NCW * 32) {
-        // ---------------- producer: one lane keeps the ring full, running ahead over tile boundaries -----------------
-        if (tid == NCW * 32) {
-            unsigned it = 0;
-            for (int64_t i = blockIdx.x; i < ntiles; i += gridDim.x) {
-                const int64_t t = op.tile_order ? op.tile_order[i] : i;
-                const int64_t c0 = op.tile_ptr[t], c1 = op.tile_ptr[t + 1];
-                for (int64_t c = c0; c < c1; c++, it++) {
-                    const unsigned s = it % (unsigned)nstages, ph = (it / (unsigned)nstages) & 1u;
+        // ---------------- producer warp: keeps both rings full, running ahead over tile boundaries -------------------------
+        unsigned s = 0, ph = 0, xs = 0, xph = 0;
+        for (int64_t i = blockIdx.x; i < ntiles; i += gridDim.x) {
+            const int64_t t = op.tile_order ? op.tile_order[i] : i;
+            const int64_t c0 = op.tile_ptr[t], c1 = op.tile_ptr[t + 1];
+            int64_t w = op.win_ptr ? op.win_ptr[t] : 0;
+            const int64_t w1 = op.win_ptr ? op.win_ptr[t + 1] : 0;
+            if (hf.enabled && hf.epoch > 1 && w < w1 && (hf.tile_flags[t] & 1)) {
+                // ghost windows are read by the copy engine: the peers' rows of the previous stage must have landed
+                if (lane == 0) {
+                    for (int q = 0; q < hf.n_in; q++) {
+                        long long spins = 0;
+                        while (ld_acquire_sys(hf.in_flag[q]) < hf.epoch - 1) {
+                            if (++spins > HALO_SPIN_LIMIT) { *hf.timeout_flag = 1ull; break; }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.global;\n" ::: "memory");
+                }
+                __syncwarp();
+            }
+            for (int64_t c = c0; c < c1; c++) {
+                while (w < w1 && op.win[w].first_chunk == (int32_t)(c - c0)) {
+                    const TbcsrWindow wd = op.win[w];
+                    if (lane == 0) {
+                        mbar_wait(xempty + xs, xph ^ 1u);
+                        mbar_expect_tx(xfull + xs, (unsigned)wd.nblocks * (unsigned)(B * nv) * (unsigned)sizeof(cplx));
+                    }
+                    __syncwarp();
+                    const cplx *src = (wd.start < op.nbcols_own) ? a.xin + (int64_t)wd.start * B * nv
+                                                                  : hf.ghost_src + ((int64_t)wd.start - op.nbcols_own) * B * nv;
+                    for (int b = lane; b < wd.nblocks; b += 32)
+                        tma_load_1d(xring + (size_t)xs * xslot + (size_t)b * xstride, src + (int64_t)b * B * nv,
+                                    (unsigned)(B * nv) * (unsigned)sizeof(cplx), xfull + xs);
+                    if (++xs == (unsigned)nsx) { xs = 0; xph ^= 1u; }
+                    w++;
+                }
+                if (lane == 0) {
                     mbar_wait(empty + s, ph ^ 1u);
                     mbar_expect_tx(full + s, CHUNK);
                     tma_load_1d(ring + (size_t)s * CHUNK, op.chunks + (size_t)c * CHUNK, CHUNK, full + s);
                 }
+                if (++s == (unsigned)nsa) { s = 0; ph ^= 1u; }
             }
         }
         return;
@@ -146,9 +197,8 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
     const int iv0 = (tid - tb * nvp) * 2;
     const bool lane_on = tb < TB;
     const int tbs = lane_on ? tb : 0;
-    const int lane = tid & 31;
     const bool has_f = a.f != nullptr;
-    unsigned it = 0;
+    unsigned s = 0, ph = 0, xs = 0, xph = 0;
 
     for (int64_t i = blockIdx.x; i < ntiles; i += gridDim.x) {
         const int64_t t = op.tile_order ? op.tile_order[i] : i;
@@ -186,53 +236,54 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
             acc[r][1] = v.b;
         }
 
-        // x rows of one block: B rows x 2 test vectors
-        cplx xa[B][2], xb[B][2];
-        int col_a = -1, col_b = -1;
-        auto fetch = [&](unsigned itc, cplx (&xr)[B][2]) -> int {
-            const unsigned s = itc % (unsigned)nstages, ph = (itc / (unsigned)nstages) & 1u;
+        for (int c = 0; c < nchunk; c++) {
             mbar_wait(full + s, ph);
-            const int32_t *cols = reinterpret_cast<const int32_t *>(ring + (size_t)s * CHUNK + (size_t)BB * TB * sizeof(cplx));
-            const int c = row_on ? cols[tbs] : -1;
-            if (c >= 0) {
-                const cplx *xp = (c < op.nbcols_own) ? a.xin + (int64_t)c * B * nv + iv0
-                                                     : hf.ghost_src + ((int64_t)c - op.nbcols_own) * B * nv + iv0;
+            const unsigned char *chunk = ring + (size_t)s * CHUNK;
+            const int32_t *cols = reinterpret_cast<const int32_t *>(chunk + (size_t)BB * TB * sizeof(cplx));
+            const int xoff = cols[TB], cflags = cols[TB + 1];
+            const int col = row_on ? cols[tbs] : -1;
+            const cplx *av = reinterpret_cast<const cplx *>(chunk) + tbs;
+            if (xoff != TBCSR_GATHER) {
+                if (cflags & 1) mbar_wait(xfull + xs, xph);
+                if (col >= 0) {
+                    const unsigned char *xw = xring + (size_t)xs * xslot + (size_t)(xoff + tbs) * xstride + (size_t)iv0 * sizeof(cplx);
 #pragma unroll
-                for (int j = 0; j < B; j++) {
-                    const cplx2 v = ld_x(xp + j * nv);
-                    xr[j][0] = v.a;
-                    xr[j][1] = v.b;
+                    for (int j = 0; j < B; j++) {
+                        const cplx *xp = reinterpret_cast<const cplx *>(xw + (size_t)j * nv * sizeof(cplx));
+                        const cplx x0 = xp[0], x1 = xp[1];
+#pragma unroll
+                        for (int r = 0; r < B; r++) {
+                            const cplx e = av[(j * B + r) * TB];
+                            cfma(acc[r][0], e, x0);
+                            cfma(acc[r][1], e, x1);
+                        }
+                    }
                 }
-            }
-            return c;
-        };
-        auto compute = [&](unsigned itc, const cplx (&xr)[B][2], int c) {
-            const unsigned s = itc % (unsigned)nstages;
-            if (c >= 0) {
-                const cplx *av = reinterpret_cast<const cplx *>(ring + (size_t)s * CHUNK) + tbs;
+            } else if (col >= 0) {
+                const cplx *xp = (col < op.nbcols_own) ? a.xin + (int64_t)col * B * nv + iv0
+                                                       : hf.ghost_src + ((int64_t)col - op.nbcols_own) * B * nv + iv0;
+                cplx2 xr[B];
+#pragma unroll
+                for (int j = 0; j < B; j++) xr[j] = ld_x(xp + j * nv);
 #pragma unroll
                 for (int j = 0; j < B; j++) {
 #pragma unroll
                     for (int r = 0; r < B; r++) {
                         const cplx e = av[(j * B + r) * TB];
-                        cfma(acc[r][0], e, xr[j][0]);
-                        cfma(acc[r][1], e, xr[j][1]);
+                        cfma(acc[r][0], e, xr[j].a);
+                        cfma(acc[r][1], e, xr[j].b);
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty + s);
-        };
-
-        if (nchunk > 0) col_a = fetch(it, xa);
-        for (int c = 0; c < nchunk; c += 2) {
-            if (c + 1 < nchunk) col_b = fetch(it + 1, xb);
-            compute(it, xa, col_a);
-            if (c + 1 < nchunk) {
-                if (c + 2 < nchunk) col_a = fetch(it + 2, xa);
-                compute(it + 1, xb, col_b);
+            if (lane == 0) {
+                mbar_arrive(empty + s);
+                if (xoff != TBCSR_GATHER && (cflags & 2)) mbar_arrive(xempty + xs);
             }
-            it += (c + 1 < nchunk) ? 2 : 1;
+            if (xoff != TBCSR_GATHER && (cflags & 2)) {
+                if (++xs == (unsigned)nsx) { xs = 0; xph ^= 1u; }
+            }
+            if (++s == (unsigned)nsa) { s = 0; ph ^= 1u; }
         }
 
         // ---------------- epilogue: stage AXPYs, local stores, peer stores of the halo rows -----------------------------
@@ -282,12 +333,7 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
             __threadfence_system();
             named_bar_sync(1, NCW * 32);
             if (tid == 0) {
-                const int64_t si = hf.send_index[t];
-                unsigned mask = 0;
-                for (int j = 0; j < 2 * TB; j++) {
-                    const int64_t dd = hf.send_dest[si * 2 * TB + j];
-                    if (dd >= 0) mask |= 1u << (int)(dd >> 48);
-                }
+                const unsigned mask = (unsigned)hf.send_mask[hf.send_index[t]];
                 for (int p = 0; p < hf.n_out; p++)
                     if (mask & (1u << p)) {
                         const unsigned long long done = atomicAdd(hf.out_done + p, 1ull) + 1ull;
@@ -302,7 +348,8 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
 }
 
 template <int B, int NCW>
-cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm, cudaStream_t s)
+cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm, int nsa_req,
+                     cudaStream_t s)
 {
     static int n_sm = 0;
     static size_t smem_max = 0;
@@ -318,11 +365,17 @@ cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, c
     const size_t chunk = tbcsr_chunk_bytes(B, TBCSR_TB);
     if (chunk != Op.chunk_bytes) return cudaErrorInvalidValue;
     // shared memory per SM: 228 KB, 1 KB reserved per CTA
-    const size_t budget = std::min(smem_max, (size_t)(228 * 1024) / ctas_per_sm - 1024);
-    int nst = (int)((budget - 256) / chunk);
-    if (nst > 12) nst = 12;
-    if (nst < 3) return cudaErrorInvalidValue;
-    const size_t smem = 128 * ((2 * (size_t)nst * 8 + 127) / 128) + (size_t)nst * chunk;
+    const size_t budget = std::min(smem_max, (size_t)(228 * 1024) / ctas_per_sm - 1024) - 256;
+    const size_t xslot = ((size_t)B * nv * sizeof(cplx) + 16) * (size_t)Op.wmax;
+    int nsx = 0, nsa = 0;
+    if (Op.win_ptr && Op.wmax > 0 && 2 * xslot + 3 * chunk <= budget) nsx = 2;
+    TbcsrDev op = Op;
+    if (!nsx) { op.win_ptr = nullptr; op.win = nullptr; if (Op.nwindows_chunks) return cudaErrorInvalidValue; }
+    nsa = (int)((budget - (size_t)nsx * xslot) / chunk);
+    if (nsa > 12) nsa = 12;
+    if (nsa_req >= 3 && nsa_req < nsa) nsa = nsa_req;
+    if (nsa < 3) return cudaErrorInvalidValue;
+    const size_t smem = 128 * ((2 * (size_t)(nsa + nsx) * 8 + 127) / 128) + (size_t)nsa * chunk + (size_t)nsx * xslot;
     const int threads = (NCW + 1) * 32;
     const unsigned grid = (unsigned)std::min<int64_t>(Op.ntiles, (int64_t)n_sm * ctas_per_sm);
     if (grid == 0) return cudaSuccess;
@@ -332,7 +385,7 @@ cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, c
     do {                                                                                                                      \
         e = cudaFuncSetAttribute(rk4_stage_tbcsr_kernel<B, NCW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                                                       \
-        rk4_stage_tbcsr_kernel<B, NCW, MINB><<<grid, threads, smem, s>>>(Op, nv, nvp, mode, nst, a, hf);                      \
+        rk4_stage_tbcsr_kernel<B, NCW, MINB><<<grid, threads, smem, s>>>(op, nv, nvp, mode, nsa, nsx, Op.wmax, a, hf);          \
     } while (0)
     if (ctas_per_sm <= 2) GO(2);   // (1 CTA/SM runs the 2-CTA build: same registers, deeper ring)
     else GO(3);
@@ -341,18 +394,18 @@ cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, c
 }
 
 template <int B>
-cudaError_t launch_b(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int cps, cudaStream_t s)
+cudaError_t launch_b(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int cps, int nsa, cudaStream_t s)
 {
     const int ncw = (TBCSR_TB * (nv / 2) + 31) / 32;
     switch (ncw) {
-        case 1: return launch_t<B, 1>(Op, nv, mode, a, hf, cps, s);
-        case 2: return launch_t<B, 2>(Op, nv, mode, a, hf, cps, s);
-        case 3: return launch_t<B, 3>(Op, nv, mode, a, hf, cps, s);
-        case 4: return launch_t<B, 4>(Op, nv, mode, a, hf, cps, s);
-        case 5: return launch_t<B, 5>(Op, nv, mode, a, hf, cps, s);
-        case 6: return launch_t<B, 6>(Op, nv, mode, a, hf, cps, s);
-        case 7: return launch_t<B, 7>(Op, nv, mode, a, hf, cps, s);
-        case 8: return launch_t<B, 8>(Op, nv, mode, a, hf, cps, s);
+        case 1: return launch_t<B, 1>(Op, nv, mode, a, hf, cps, nsa, s);
+        case 2: return launch_t<B, 2>(Op, nv, mode, a, hf, cps, nsa, s);
+        case 3: return launch_t<B, 3>(Op, nv, mode, a, hf, cps, nsa, s);
+        case 4: return launch_t<B, 4>(Op, nv, mode, a, hf, cps, nsa, s);
+        case 5: return launch_t<B, 5>(Op, nv, mode, a, hf, cps, nsa, s);
+        case 6: return launch_t<B, 6>(Op, nv, mode, a, hf, cps, nsa, s);
+        case 7: return launch_t<B, 7>(Op, nv, mode, a, hf, cps, nsa, s);
+        case 8: return launch_t<B, 8>(Op, nv, mode, a, hf, cps, nsa, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -367,13 +420,75 @@ bool tbcsr_stage_supported(int B, int nv)
 }
 
 cudaError_t launch_rk4_stage_tbcsr(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm,
-                                   cudaStream_t s)
+                                   int ring_stages, cudaStream_t s)
 {
     if (!tbcsr_stage_supported(Op.B, nv)) return cudaErrorInvalidValue;
     switch (Op.B) {
-        case 3: return launch_b<3>(Op, nv, mode, a, hf, ctas_per_sm, s);
-        case 4: return launch_b<4>(Op, nv, mode, a, hf, ctas_per_sm, s);
-        case 5: return launch_b<5>(Op, nv, mode, a, hf, ctas_per_sm, s);
+        case 3: return launch_b<3>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, s);
+        case 4: return launch_b<4>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, s);
+        case 5: return launch_b<5>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, s);
         default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// x windows: which chunks read their rows of the stage vector from a shared-memory window, and which windows a tile needs
+// ---------------------------------------------------------------------------------------------------------------------
+void tbcsr_plan_windows(int64_t ntiles, const int64_t *tile_ptr, const int32_t *cols, int64_t nb_own, int64_t nb_total, int TB,
+                        int wmax, TbcsrPlan &out)
+{
+    (void)nb_total;
+    const int64_t nchunks = tile_ptr[ntiles];
+    out.hdr.assign((size_t)nchunks * 4, 0);
+    out.win_ptr.assign((size_t)ntiles + 1, 0);
+    out.win.clear();
+    out.window_chunks = out.gather_chunks = 0;
+    for (int64_t t = 0; t < ntiles; t++) {
+        int64_t cur = -1, cur_last = -1;   // open window (index into out.win) and the last chunk that used it
+        bool cur_ghost = false;
+        auto close = [&]() {
+            if (cur >= 0 && cur_last >= 0) out.hdr[(size_t)cur_last * 4 + 1] |= 2;
+            cur = -1;
+            cur_last = -1;
+        };
+        for (int64_t p = tile_ptr[t]; p < tile_ptr[t + 1]; p++) {
+            const int32_t *c = cols + p * TB;
+            bool any = false, affine = true;
+            int64_t base = 0, lo = 0, hi = 0;
+            for (int tb = 0; tb < TB; tb++) {
+                if (c[tb] < 0) continue;
+                const int64_t b = (int64_t)c[tb] - tb;
+                if (!any) { any = true; base = b; lo = c[tb]; }
+                else if (b != base) affine = false;
+                hi = (int64_t)c[tb] + 1;
+            }
+            bool ok = any && affine && hi - lo <= wmax;
+            const bool ghost = ok && lo >= nb_own;
+            if (ok && !ghost && hi > nb_own) ok = false;   // straddles owned rows and ghost rows: two sources
+            if (!ok) {
+                out.hdr[(size_t)p * 4] = TBCSR_GATHER;
+                if (any) out.gather_chunks++;
+                continue;
+            }
+            if (cur >= 0 && cur_ghost == ghost && lo >= out.win[(size_t)cur].start && hi <= (int64_t)out.win[(size_t)cur].start + wmax) {
+                out.win[(size_t)cur].nblocks = (int32_t)std::max<int64_t>(out.win[(size_t)cur].nblocks, hi - out.win[(size_t)cur].start);
+            } else {
+                close();
+                TbcsrWindow w;
+                w.start = (int32_t)lo;
+                w.nblocks = (int32_t)(hi - lo);
+                w.first_chunk = (int32_t)(p - tile_ptr[t]);
+                w.pad = 0;
+                out.win.push_back(w);
+                cur = (int64_t)out.win.size() - 1;
+                cur_ghost = ghost;
+                out.hdr[(size_t)p * 4 + 1] |= 1;
+            }
+            out.hdr[(size_t)p * 4] = (int32_t)(base - out.win[(size_t)cur].start);
+            cur_last = p;
+            out.window_chunks++;
+        }
+        close();
+        out.win_ptr[(size_t)t + 1] = (int64_t)out.win.size();
     }
 }

@@ -6,15 +6,25 @@
 // fewer blocks are padded, column -1), laid out for one bulk copy and conflict-free shared-memory reads:
 //     cplx  val[B*B][TB]      entry e = j*B + r of the block (column-major inside the block), block row tb fastest
 //     int32 col[TB]           block column of that block, or -1 (padding: skipped, no arithmetic)
-// chunk_bytes = B*B*TB*16 + TB*4.  Per nonzero this is 16 B + 4/(B*B) B -- the floor of a complex-double block format.
+//     int32 hdr[4]            {xoff, flags, 0, 0}: where the chunk's rows of the stage vector sit in the x window (below)
+// chunk_bytes = B*B*TB*16 + TB*4 + 16.  Per nonzero this is 16 B + ~4/(B*B) B -- the floor of a complex-double block format.
+// When the blocks of a tile line up on block diagonals (col - block row constant along a chunk: stencils), the chunks are
+// cut by diagonal instead of by position in the row (missing neighbours padded in place), and runs of neighbouring
+// diagonals share an "x window": one contiguous range of block rows of the stage vector, staged in shared memory once.
 // Summation order per row = ascending block columns, ascending column inside the block: the same as the CSR and block-CSR
 // stage kernels, so the three agree bit for bit.
 #pragma once
 
 #include "kernels.cuh"
 
+#include <vector>
+
 constexpr int TBCSR_TB = 32;          // block rows per tile
 constexpr int TBCSR_MAX_PEERS = 8;    // halo peers a rank can send to / receive from in the fused exchange
+constexpr int TBCSR_GATHER = -(1 << 30);   // chunk header xoff: no window, gather the rows from global memory
+constexpr int TBCSR_WMAX = 40;        // longest x window in block rows (TB + 8: diagonals up to 8 blocks apart share one)
+
+struct TbcsrWindow { int32_t start, nblocks, first_chunk, pad; };   // block rows [start, start + nblocks) of the stage vector
 
 struct TbcsrDev {
     int B = 0, TB = TBCSR_TB;
@@ -25,8 +35,12 @@ struct TbcsrDev {
     const unsigned char *chunks = nullptr;    // nchunks * chunk_bytes
     const int32_t *tile_order = nullptr;      // optional [ntiles]: processing order (halo tiles first)
     size_t chunk_bytes = 0;
+    const int64_t *win_ptr = nullptr;         // [ntiles + 1] windows of tile t, in the order their chunks come
+    const TbcsrWindow *win = nullptr;
+    int wmax = 0;                             // longest window (block rows); 0: no windows
+    int64_t nwindows_chunks = 0;              // chunks that need a window (if shared memory cannot hold the x ring the launch fails)
 };
-inline size_t tbcsr_chunk_bytes(int B, int TB) { return (size_t)B * B * TB * sizeof(cplx) + (size_t)TB * sizeof(int32_t); }
+__host__ __device__ inline size_t tbcsr_chunk_bytes(int B, int TB) { return (size_t)B * B * TB * sizeof(cplx) + (size_t)TB * sizeof(int32_t) + 16; }
 
 // The halo exchange done by the stage kernel itself (row-partitioned runs, layout 0).
 //   Every fused stage has an epoch E (1, 2, ...).  Tiles whose rows a peer needs store them, next to the local store,
@@ -49,13 +63,26 @@ struct HaloFuse {
     const unsigned char *tile_flags = nullptr;               // [ntiles] bit0: reads ghosts, bit1: sends
     const int32_t *send_index = nullptr;                     // [ntiles] -> row of send_dest, or -1
     const int64_t *send_dest = nullptr;                      // [nsendtiles][2][TB]: (peer slot << 48) | ghost row on the peer, or -1
+    const int32_t *send_mask = nullptr;                      // [nsendtiles] bit p: the tile sends to outgoing peer p
     unsigned long long *timeout_flag = nullptr;              // set to 1 if a wait gave up (peer dead): the host reports it
 };
 
 bool tbcsr_stage_supported(int B, int nv);
 // mode / StageArgs as for the other stage kernels (kernels.cuh)
+// ring_stages: 0 = as many operator chunks as shared memory holds (up to 12), else at most that many
 cudaError_t launch_rk4_stage_tbcsr(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm,
-                                   cudaStream_t s);
+                                   int ring_stages, cudaStream_t s);
+
+// Host-side plan of the x windows from the chunk columns (cols: [nchunks][TB] as stored): fills hdr ([nchunks][4]) and the
+// window lists.  nb_own: block columns below it are rows of the stage vector, the others ghost rows (separate source).
+struct TbcsrPlan {
+    std::vector<int32_t> hdr;
+    std::vector<int64_t> win_ptr;
+    std::vector<TbcsrWindow> win;
+    int64_t window_chunks = 0, gather_chunks = 0;
+};
+void tbcsr_plan_windows(int64_t ntiles, const int64_t *tile_ptr, const int32_t *cols, int64_t nb_own, int64_t nb_total, int TB,
+                        int wmax, TbcsrPlan &out);
 
 // Synthetic LNS block-stencil operator generated on the device, straight into the tiled layout (measurement aid for the
 // BASELINE.json configurations: the 2e7-DOF operator is 65 GB as a file).  Same entries, bit for bit, as
@@ -74,12 +101,13 @@ struct StencilSpec {
     int64_t n_ghost = 0;
     double shift = 0.0;        // discounting: subtracted from the diagonal (LNSStructure.c:53-56)
 };
-// counts_dev[t] = chunks of tile t (largest number of in-domain neighbours among its points); then, with the prefix sums
-// of the counts as tile_ptr, the fill kernel writes every chunk; tile_has_ghost[t] (optional, zeroed by the caller) is set
-// when a block column of the tile lies outside [pt0, pt1)
-cudaError_t stencil_tile_counts(const StencilSpec &sp, int TB, int64_t ntiles, int32_t *counts_dev, cudaStream_t s);
-cudaError_t stencil_fill(const StencilSpec &sp, int TB, int64_t ntiles, const int64_t *tile_ptr_dev, unsigned char *chunks,
-                         unsigned char *tile_has_ghost, cudaStream_t s);
+// counts_dev[t] = chunks of tile t = stencil offsets that occur among its points (masks_dev[t]: which); then, with the prefix
+// sums of the counts as tile_ptr, the fill kernel writes every chunk (one per block diagonal; the chunk headers are written
+// by the caller from tbcsr_plan_windows); tile_has_ghost[t] (optional, zeroed by the caller) is set when a block column of
+// the tile lies outside [pt0, pt1)
+cudaError_t stencil_tile_counts(const StencilSpec &sp, int TB, int64_t ntiles, int32_t *counts_dev, uint32_t *masks_dev, cudaStream_t s);
+cudaError_t stencil_fill(const StencilSpec &sp, int TB, int64_t ntiles, const int64_t *tile_ptr_dev, const uint32_t *masks_dev,
+                         unsigned char *chunks, unsigned char *tile_has_ghost, cudaStream_t s);
 // stack[a][roff + r][b] = uniform [0,1) + i [0,1), r < rows (CreateRandomMat.c:36-39 on the device)
 cudaError_t launch_random_stack(cplx *stack, int64_t rows, int64_t srows, int64_t roff, int na, int nb, int64_t grow0,
                                 unsigned long long seed, cudaStream_t s);

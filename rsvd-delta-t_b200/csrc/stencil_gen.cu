@@ -39,29 +39,36 @@ __device__ __forceinline__ int valid_neighbours(const Geo &g, int64_t q, int64_t
     return n;
 }
 
-__global__ void stencil_tile_counts_kernel(Geo g, int64_t pt0, int64_t pt1, int TB, int64_t ntiles, int32_t *counts)
+// which stencil offsets occur in a tile (bit b of mask) -- its chunks, one per block diagonal, in ascending column order
+__global__ void stencil_tile_counts_kernel(Geo g, int64_t pt0, int64_t pt1, int TB, int64_t ntiles, int32_t *counts, uint32_t *masks)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
-    int mx = 0;
+    uint32_t m = 0;
     for (int tb = 0; tb < TB; tb++) {
         const int64_t q = pt0 + t * TB + tb;
-        if (q < pt1) mx = max(mx, valid_neighbours(g, q, nullptr, nullptr));
+        if (q >= pt1) break;
+        int64_t nbr[27];
+        int bidx[27];
+        const int n = valid_neighbours(g, q, nbr, bidx);
+        for (int i = 0; i < n; i++) m |= 1u << bidx[i];
     }
-    counts[t] = mx;
+    counts[t] = __popc(m);
+    masks[t] = m;
 }
 
-// one thread per (tile, block row of the tile): writes its column of every chunk of the tile
+// one thread per (tile, block row of the tile): writes its column of every chunk of the tile.  Chunk of stencil offset b =
+// the (number of offsets < b present in the tile)-th chunk; a point without that neighbour gets column -1 there.
 template <int B>
-__global__ void stencil_fill_kernel(Geo g, StencilSpec sp, int TB, int64_t ntiles, const int64_t *tile_ptr, unsigned char *chunks,
-                                    unsigned char *tile_has_ghost)
+__global__ void stencil_fill_kernel(Geo g, StencilSpec sp, int TB, int64_t ntiles, const int64_t *tile_ptr, const uint32_t *masks,
+                                    unsigned char *chunks, unsigned char *tile_has_ghost)
 {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t t = gid / TB;
     const int tb = (int)(gid - t * TB);
     if (t >= ntiles) return;
-    const size_t cb = (size_t)B * B * TB * sizeof(cplx) + (size_t)TB * sizeof(int32_t);
-    const int nch = (int)(tile_ptr[t + 1] - tile_ptr[t]);
+    const size_t cb = tbcsr_chunk_bytes(B, TB);
+    const uint32_t mask = masks[t];
     const int64_t q = sp.pt0 + t * TB + tb;
     int64_t nbr[27];
     int bidx[27];
@@ -69,17 +76,21 @@ __global__ void stencil_fill_kernel(Geo g, StencilSpec sp, int TB, int64_t ntile
     const int centre = (g.nb - 1) / 2;
     const int64_t nown = sp.pt1 - sp.pt0;
     bool ghost = false;
-    for (int p = 0; p < nch; p++) {
+    int i = 0;   // next valid neighbour of this point
+    int p = 0;   // chunk index inside the tile
+    for (int b = 0; b < g.nb; b++) {
+        if (!(mask & (1u << b))) continue;
         unsigned char *base = chunks + (size_t)(tile_ptr[t] + p) * cb;
+        p++;
         cplx *cv = reinterpret_cast<cplx *>(base);
         int32_t *cc = reinterpret_cast<int32_t *>(base + (size_t)B * B * TB * sizeof(cplx));
-        if (p >= n) {
+        if (i >= n || bidx[i] != b) {
             cc[tb] = -1;
             for (int e = 0; e < B * B; e++) cv[(size_t)e * TB + tb] = make_double2(0.0, 0.0);
             continue;
         }
-        const int64_t pn = nbr[p];
-        const int b = bidx[p];
+        const int64_t pn = nbr[i];
+        i++;
         int64_t lc;
         if (pn >= sp.pt0 && pn < sp.pt1) lc = pn - sp.pt0;
         else {   // ghost block column: position in the sorted ghost list
@@ -142,7 +153,7 @@ cudaError_t launch_random_stack(cplx *stack, int64_t rows, int64_t srows, int64_
     return cudaGetLastError();
 }
 
-cudaError_t stencil_tile_counts(const StencilSpec &sp, int TB, int64_t ntiles, int32_t *counts_dev, cudaStream_t s)
+cudaError_t stencil_tile_counts(const StencilSpec &sp, int TB, int64_t ntiles, int32_t *counts_dev, uint32_t *masks_dev, cudaStream_t s)
 {
     Geo g;
     g.d = sp.d;
@@ -152,12 +163,12 @@ cudaError_t stencil_tile_counts(const StencilSpec &sp, int TB, int64_t ntiles, i
         g.stride[i] = 1;
         for (int j = i + 1; j < sp.d; j++) g.stride[i] *= sp.shape[j];
     }
-    stencil_tile_counts_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, s>>>(g, sp.pt0, sp.pt1, TB, ntiles, counts_dev);
+    stencil_tile_counts_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, s>>>(g, sp.pt0, sp.pt1, TB, ntiles, counts_dev, masks_dev);
     return cudaGetLastError();
 }
 
-cudaError_t stencil_fill(const StencilSpec &sp, int TB, int64_t ntiles, const int64_t *tile_ptr_dev, unsigned char *chunks,
-                         unsigned char *tile_has_ghost, cudaStream_t s)
+cudaError_t stencil_fill(const StencilSpec &sp, int TB, int64_t ntiles, const int64_t *tile_ptr_dev, const uint32_t *masks_dev,
+                         unsigned char *chunks, unsigned char *tile_has_ghost, cudaStream_t s)
 {
     Geo g;
     g.d = sp.d;
@@ -170,9 +181,9 @@ cudaError_t stencil_fill(const StencilSpec &sp, int TB, int64_t ntiles, const in
     const int64_t nthr = ntiles * TB;
     const unsigned blocks = (unsigned)((nthr + 127) / 128);
     switch (sp.B) {
-        case 3: stencil_fill_kernel<3><<<blocks, 128, 0, s>>>(g, sp, TB, ntiles, tile_ptr_dev, chunks, tile_has_ghost); break;
-        case 4: stencil_fill_kernel<4><<<blocks, 128, 0, s>>>(g, sp, TB, ntiles, tile_ptr_dev, chunks, tile_has_ghost); break;
-        case 5: stencil_fill_kernel<5><<<blocks, 128, 0, s>>>(g, sp, TB, ntiles, tile_ptr_dev, chunks, tile_has_ghost); break;
+        case 3: stencil_fill_kernel<3><<<blocks, 128, 0, s>>>(g, sp, TB, ntiles, tile_ptr_dev, masks_dev, chunks, tile_has_ghost); break;
+        case 4: stencil_fill_kernel<4><<<blocks, 128, 0, s>>>(g, sp, TB, ntiles, tile_ptr_dev, masks_dev, chunks, tile_has_ghost); break;
+        case 5: stencil_fill_kernel<5><<<blocks, 128, 0, s>>>(g, sp, TB, ntiles, tile_ptr_dev, masks_dev, chunks, tile_has_ghost); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
