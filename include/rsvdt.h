@@ -56,6 +56,14 @@ typedef struct {
 /* SlepcInitialize / SlepcFinalize (main.c:107,148): binds a CUDA device and creates the stream. */
 int rsvdt_create(int device, rsvdt_handle *h);
 int rsvdt_destroy(rsvdt_handle h);
+/* `mpiexec -n P RSVDt` in one process: a group handle that stands for ngpus member handles, one per GPU (devices[p], or GPU p
+ * when devices is NULL).  It takes the same whole host buffers as a single-GPU handle -- the operator, the weights, Y_hat,
+ * U_hat ... -- partitions their rows like PETSC_DECIDE (LNSStructure.c:24-26, CreateTSMats.c:15-17), runs every entry point
+ * below on one host thread per GPU, maps peer memory directly for the halo exchange and calls NCCL itself (libnccl.so.2,
+ * resolved at run time) for the all-reduce of the Gram matrices and norms and the all-gather of the weight products.
+ * Entry points a group accepts: set_operator_csr, set_grid, set_weight_csr, set_yhat / get_yhat, direct / adjoint action,
+ * qr_all_freqs, power_iteration, the two SVDs, store_u, get_u_hat / get_v_hat / get_s_hat, transient_run_rk4, destroy. */
+int rsvdt_create_group(int ngpus, const int *devices, rsvdt_handle *h);
 const char *rsvdt_last_error(rsvdt_handle h);   /* message of the last failing call (never NULL) */
 const char *rsvdt_version(void);
 

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -89,6 +90,7 @@ struct CsrOwned {
     bool tbcsr_valid = false;
     bool stencil_only = false;                    // generated on the device: no CSR / block-CSR copies exist
     std::vector<unsigned char> tile_ghost;        // [ntiles] 1: a block column of the tile is a ghost (row-partitioned runs)
+    std::vector<int32_t> base_order;              // processing order of the tiles chosen for L2 locality (empty: row order)
     int plan_nv = -1, plan_variant = -1, plan_mode = -1, ntiles = 0, nslow = 0;
     bool plan_ok = false;
     void release()
@@ -97,7 +99,7 @@ struct CsrOwned {
         b_rowptr.release(); b_col.release(); b_val.release(); bcsr = BcsrDev(); bcsr_valid = false;
         t_chunks.release(); t_tileptr.release(); t_order.release(); t_flags.release(); t_winptr.release(); t_win.release();
         tb = TbcsrDev(); tbcsr_valid = false;
-        stencil_only = false; tile_ghost.clear();
+        stencil_only = false; tile_ghost.clear(); base_order.clear();
         d = CsrDev(); set = false; dia_valid = false; plan_nv = -1; plan_ok = false; row_regular.clear();
     }
 };
@@ -106,8 +108,11 @@ struct EventPair { cudaEvent_t a, b; };
 
 }  // namespace
 
+struct rsvdt_group_ctx;
+
 struct rsvdt_context {
     int device = 0;
+    rsvdt_group_ctx *group = nullptr;     // != null: this handle stands for P member handles, one per GPU (group.inc)
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // runs the few irregular tiles of a fused step next to the main kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -134,6 +139,7 @@ struct rsvdt_context {
         int nvec_max = 0;
         DevBuf mailbox, flags, msgs_dev, ins_dev, peer_flags_dev;
         std::vector<void *> peer_mailbox, peer_flags;   // IPC-mapped peer pointers (index = rank)
+        bool peer_mapped_directly = false;              // members of a one-process group: plain peer pointers, nothing to close
         unsigned long long epoch = 0;
         int max_out = 0, max_in = 0;
         // interior / boundary split of the owned rows (layout 0): rows [0, lo_end) and [hi_begin, N) are sent to peers
@@ -178,6 +184,9 @@ struct rsvdt_context {
     int64_t tma_variant = 0;  // 0: tiles sized for 3 CTAs/SM, 1: for 2 CTAs/SM
     int64_t use_bcsr = 1;     // block-CSR stage kernel when the operator has dense B x B blocks
     int64_t use_tiled = 1;    // ... and its TMA-staged tiled form (stage_tiled.cu) when the number of vectors is even
+    int64_t tiled_flags = -1; // stage_tiled.cuh TbcsrDev::flags (-1: the default)
+    int64_t tiled_order = 8;  // grid lines per group of the z-fastest tile order of 3-D stencil operators (0: row order)
+    int64_t tiled_cv = 0;     // test vectors per consumer thread of the tiled stage kernel (0: automatic)
     int64_t tiled_stages = 0; // operator ring depth of the tiled stage kernel; 0 = what shared memory holds
     int64_t tiled_ctas = 2;   // resident CTAs per SM of the tiled stage kernel (ring depth follows from the shared memory left)
     int64_t use_small = 1;    // single-CTA persistent kernel when the whole block vector fits in one SM's shared memory
@@ -473,7 +482,8 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
                 if (!plan.win.empty()) CU(cudaMemcpy(dst.t_win.p, plan.win.data(), plan.win.size() * sizeof(TbcsrWindow), cudaMemcpyHostToDevice));
                 dst.tb.win_ptr = dst.t_winptr.as<int64_t>();
                 dst.tb.win = dst.t_win.as<TbcsrWindow>();
-                dst.tb.wmax = TBCSR_WMAX;
+                dst.tb.wmax = 1;
+                for (auto &w : plan.win) dst.tb.wmax = std::max(dst.tb.wmax, (int)w.nblocks);
                 dst.tb.nwindows_chunks = plan.window_chunks;
             }
             CU(dst.t_tileptr.alloc(tptr.size() * sizeof(int64_t)));
@@ -675,6 +685,8 @@ cudaError_t launch_stage_any(rsvdt_handle h, const CsrOwned &Op, int nv, int mod
 {
     if (tiled_active(h, Op, nv)) {
         HaloFuse hf;
+        TbcsrDev top = Op.tb;
+        if (h->tiled_flags >= 0) top.flags = (int)h->tiled_flags;
         if (fused_active(h, Op, nv)) {
             auto &D = h->dist;
             const unsigned long long E = ++D.fz_epoch;
@@ -705,7 +717,7 @@ cudaError_t launch_stage_any(rsvdt_handle h, const CsrOwned &Op, int nv, int mod
             D.fz_last_out = mode == 2 ? a.acc_out : a.xout;
             D.fz_last_nv = nv;
         }
-        return launch_rk4_stage_tbcsr(Op.tb, nv, mode, a, hf, (int)h->tiled_ctas, (int)h->tiled_stages, h->stream);
+        return launch_rk4_stage_tbcsr(top, nv, mode, a, hf, (int)h->tiled_ctas, (int)h->tiled_stages, (int)h->tiled_cv, h->stream);
     }
     if (Op.stencil_only) return cudaErrorNotSupported;   // device-generated operators exist in the tiled form only (even nv)
     if (h->use_bcsr && Op.bcsr_valid && bcsr_stage_supported(Op.bcsr.B, nv))
@@ -1158,6 +1170,7 @@ int dft_snapshots(rsvdt_handle h, const cplx *snaps, cplx *Yhat_out)
 int dist_allreduce(rsvdt_handle h, void *dev_ptr, int64_t n_doubles);
 int check_halo_timeout(rsvdt_handle h);
 int build_fused(rsvdt_handle h);
+int finish_connect(rsvdt_handle h, const int64_t *out_mb_off);
 
 // TransientRemovalStrategy.c:30-40 on the device.  snaps: Y_all as a stack [Nw+1][row][ik]; Yhat_out: stack [Nw_eff][row][ik].
 //   CreateMtilde.c:41-54      V = QR(Y_all_k) -> shifted CholeskyQR3 per test vector (the snapshot matrices reach cond ~1e7,
@@ -1496,7 +1509,8 @@ int build_fused(rsvdt_handle h)
         std::vector<int32_t> order;
         order.reserve((size_t)ntiles);
         for (int pass = 0; pass < 3; pass++)
-            for (int64_t t = 0; t < ntiles; t++) {
+            for (int64_t i = 0; i < ntiles; i++) {
+                const int64_t t = Op->base_order.empty() ? i : Op->base_order[(size_t)i];
                 const int cls = (fl[(size_t)t] & 2) ? 0 : (fl[(size_t)t] ? 1 : 2);
                 if (cls == pass) order.push_back((int32_t)t);
             }
@@ -1563,7 +1577,8 @@ int build_stencil_operator(rsvdt_handle h, CsrOwned &Op, StencilSpec sp, int64_t
         if (!plan.win.empty()) CU(cudaMemcpy(Op.t_win.p, plan.win.data(), plan.win.size() * sizeof(TbcsrWindow), cudaMemcpyHostToDevice));
         Op.tb.win_ptr = Op.t_winptr.as<int64_t>();
         Op.tb.win = Op.t_win.as<TbcsrWindow>();
-        Op.tb.wmax = TBCSR_WMAX;
+        Op.tb.wmax = 1;
+        for (auto &w : plan.win) Op.tb.wmax = std::max(Op.tb.wmax, (int)w.nblocks);
         Op.tb.nwindows_chunks = plan.window_chunks;
     }
     h->launches += 2;
@@ -1578,6 +1593,23 @@ int build_stencil_operator(rsvdt_handle h, CsrOwned &Op, StencilSpec sp, int64_t
     Op.tb.chunk_bytes = cb;
     Op.tbcsr_valid = true;
     Op.stencil_only = true;
+    if (sp.d == 3 && h->tiled_order > 0 && ntiles > 1) {
+        // L2 locality: row order re-reads a row of the stage vector one and two grid planes later (51 MB apart at 200 x 200 x
+        // 5 x 8 vectors), which the operator stream flushes out of L2 in between.  Walk the planes fastest instead: groups of
+        // `tiled_order` grid lines, each group through all local planes, so that the reuse distance is a few hundred KB.
+        const int64_t G = h->tiled_order, ny = sp.shape[1], nx = sp.shape[2];
+        std::vector<std::pair<int64_t, int32_t>> key((size_t)ntiles);
+        for (int64_t t = 0; t < ntiles; t++) {
+            const int64_t q = sp.pt0 + t * TB, z = q / (ny * nx), y = (q / nx) % ny;
+            key[(size_t)t] = {((y / G) * (sp.shape[0] + 1) + z) * (G * nx + TB) + (y % G) * nx + q % nx, (int32_t)t};
+        }
+        std::sort(key.begin(), key.end());
+        Op.base_order.resize((size_t)ntiles);
+        for (int64_t t = 0; t < ntiles; t++) Op.base_order[(size_t)t] = key[(size_t)t].second;
+        CU(Op.t_order.alloc((size_t)ntiles * sizeof(int32_t)));
+        CU(cudaMemcpy(Op.t_order.p, Op.base_order.data(), (size_t)ntiles * sizeof(int32_t), cudaMemcpyHostToDevice));
+        Op.tb.tile_order = Op.t_order.as<int32_t>();
+    }
     int nb = 1;
     int64_t band = 1;
     for (int i = 0; i < sp.d; i++) nb *= 3;
@@ -1594,6 +1626,8 @@ int build_stencil_operator(rsvdt_handle h, CsrOwned &Op, StencilSpec sp, int64_t
 
 }  // namespace
 
+#include "group.inc"
+
 extern "C" {
 
 const char *rsvdt_version(void) { return "rsvdt-b200 0.1 (sm_100a)"; }
@@ -1609,6 +1643,7 @@ int rsvdt_create(int device, rsvdt_handle *hout)
     rsvdt_handle h = new (std::nothrow) rsvdt_context();
     if (!h) return RSVDT_ERR_MEM;
     h->device = device;
+    if (const char *e = getenv("RSVDT_TILED_ORDER")) h->tiled_order = atoll(e);   // measurement hook (set before the operator)
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -1630,9 +1665,40 @@ int rsvdt_create(int device, rsvdt_handle *hout)
     return RSVDT_OK;
 }
 
+int rsvdt_create_group(int ngpus, const int *devices, rsvdt_handle *hout)
+{
+    if (!hout || ngpus < 1 || ngpus > 64) return RSVDT_ERR_ARG;
+    *hout = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < ngpus) return RSVDT_ERR_CUDA;
+    rsvdt_handle root = nullptr;
+    int rc = rsvdt_create(devices ? devices[0] : 0, &root);
+    if (rc) return rc;
+    rsvdt_group_ctx *G = new (std::nothrow) rsvdt_group_ctx();
+    if (!G) { rsvdt_destroy(root); return RSVDT_ERR_MEM; }
+    G->P = ngpus;
+    root->group = G;
+    for (int p = 0; p < ngpus; p++) {
+        rsvdt_handle mh = nullptr;
+        rc = rsvdt_create(devices ? devices[p] : p, &mh);
+        if (rc) { rsvdt_destroy(root); return rc; }
+        G->m.push_back(mh);
+    }
+    *hout = root;
+    return RSVDT_OK;
+}
+
 int rsvdt_destroy(rsvdt_handle h)
 {
     if (!h) return RSVDT_OK;
+    if (h->group) {
+        rsvdt_group_ctx *G = h->group;
+        for (size_t p = 0; p < G->comm.size(); p++)
+            if (G->comm[p]) { cudaSetDevice(G->m[p]->device); nccl().CommDestroy(G->comm[p]); }
+        for (rsvdt_handle mh : G->m) rsvdt_destroy(mh);
+        delete G;
+        h->group = nullptr;
+    }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     int64_t n;
@@ -1640,7 +1706,7 @@ int rsvdt_destroy(rsvdt_handle h)
     h->A.release(); h->AH.release();
     for (int i = 0; i < 5; i++) { h->W[i].release(); h->WH[i].release(); }
     for (auto &m : h->dist.out) m.rows.release();
-    for (int p = 0; p < (int)h->dist.peer_mailbox.size(); p++) {
+    for (int p = 0; p < (int)h->dist.peer_mailbox.size() && !h->dist.peer_mapped_directly; p++) {
         if (p == h->dist.rank) continue;
         if (h->dist.peer_mailbox[(size_t)p]) cudaIpcCloseMemHandle(h->dist.peer_mailbox[(size_t)p]);
         if (h->dist.peer_flags[(size_t)p]) cudaIpcCloseMemHandle(h->dist.peer_flags[(size_t)p]);
@@ -1684,6 +1750,7 @@ int rsvdt_setup_time_freq_grid(double w, int64_t Nw, double dt_in, double Transi
 int rsvdt_set_operator_csr(rsvdt_handle h, int64_t N, const int64_t *rowptr, const int64_t *col, const double *val,
                            int disc_flg, double beta, int *real_operator)
 {
+    if (h && h->group) return group_set_operator_csr(h, N, rowptr, col, val, disc_flg, beta, real_operator);
     RS(bind(h));
     if (N <= 0 || !rowptr || !col || !val) return fail(h, RSVDT_ERR_ARG, "bad operator arguments");
     if (disc_flg && beta < 0) return fail(h, RSVDT_ERR_USER, "'beta' must be positive, current value: %g", beta);  // ReadUserInput.c:133
@@ -1706,6 +1773,7 @@ int rsvdt_set_operator_csr(rsvdt_handle h, int64_t N, const int64_t *rowptr, con
 
 int rsvdt_set_grid(rsvdt_handle h, const rsvdt_grid *g)
 {
+    if (h && h->group) return (g ? group_set_grid(h, g) : RSVDT_ERR_ARG);
     RS(bind(h));
     if (!g) return fail(h, RSVDT_ERR_ARG, "null grid");
     if (g->k <= 0 || g->Nw <= 0 || g->Nw_eff <= 0 || g->Ns <= 0 || g->Nt < 0 || g->ResRatio <= 0 || !(g->dt > 0))
@@ -1720,6 +1788,7 @@ int rsvdt_set_grid(rsvdt_handle h, const rsvdt_grid *g)
 int rsvdt_set_weight_csr(rsvdt_handle h, int which, int64_t nrows, int64_t ncols, const int64_t *rowptr,
                          const int64_t *col, const double *val)
 {
+    if (h && h->group) return group_set_weight_csr(h, which, nrows, ncols, rowptr, col, val);
     RS(bind(h));
     if (which < 0 || which > 4 || !rowptr || !col || !val) return fail(h, RSVDT_ERR_ARG, "bad weight arguments");
     if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "set the operator before the weights");
@@ -1813,6 +1882,7 @@ int64_t rsvdt_yhat_rows(rsvdt_handle h) { return h ? h->yhat_rows : -1; }
 
 int rsvdt_set_yhat(rsvdt_handle h, const double *Y_host, int64_t nrows)
 {
+    if (h && h->group) return group_set_yhat(h, Y_host, nrows);
     RS(bind(h));
     if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "grid not set");
     if (!Y_host || nrows <= 0) return fail(h, RSVDT_ERR_ARG, "bad Y_hat arguments");
@@ -1827,6 +1897,7 @@ int rsvdt_set_yhat(rsvdt_handle h, const double *Y_host, int64_t nrows)
 
 int rsvdt_get_yhat(rsvdt_handle h, double *Y_host, int64_t nrows)
 {
+    if (h && h->group) return group_get_matrix(h, 0, Y_host, nrows);
     RS(bind(h));
     if (!Y_host || nrows != h->yhat_rows || !h->Yhat.p) return fail(h, RSVDT_ERR_STATE, "Y_hat not available with %lld rows", (long long)nrows);
     int64_t srows, roff;
@@ -1834,8 +1905,18 @@ int rsvdt_get_yhat(rsvdt_handle h, double *Y_host, int64_t nrows)
     return download_stack(h, h->Yhat, Y_host, nrows, (int)h->g.Nw_eff, (int)h->g.k, h->g.k, 1, srows, roff);
 }
 
-int rsvdt_direct_action_rk4(rsvdt_handle h) { RS(bind(h)); return action_with_weights(h, true); }
-int rsvdt_adjoint_action_rk4(rsvdt_handle h) { RS(bind(h)); return action_with_weights(h, false); }
+int rsvdt_direct_action_rk4(rsvdt_handle h)
+{
+    if (h && h->group) return group_call(h, rsvdt_direct_action_rk4);
+    RS(bind(h));
+    return action_with_weights(h, true);
+}
+int rsvdt_adjoint_action_rk4(rsvdt_handle h)
+{
+    if (h && h->group) return group_call(h, rsvdt_adjoint_action_rk4);
+    RS(bind(h));
+    return action_with_weights(h, false);
+}
 
 int rsvdt_ts_action_rk4(rsvdt_handle h, int direct, const double *F_hat_host, double *Y_hat_host)
 {
@@ -1849,6 +1930,7 @@ int rsvdt_ts_action_rk4(rsvdt_handle h, int direct, const double *F_hat_host, do
 
 int rsvdt_qr_all_freqs(rsvdt_handle h)
 {
+    if (h && h->group) return group_call(h, rsvdt_qr_all_freqs);
     RS(bind(h));
     RS(check_ready(h));
     if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
@@ -1888,6 +1970,10 @@ int rsvdt_qr_all_freqs(rsvdt_handle h)
 
 int rsvdt_power_iteration_rk4(rsvdt_handle h, int64_t q)
 {
+    if (h && h->group) {
+        rsvdt_group_ctx *G = h->group;
+        return group_run(h, [&](int p) -> int { return rsvdt_power_iteration_rk4(G->m[(size_t)p], q); });
+    }
     RS(bind(h));
     for (int64_t iq = 0; iq < q; iq++) {  // PowerIterationRK4.c:20-29
         RS(rsvdt_qr_all_freqs(h));
@@ -1900,6 +1986,7 @@ int rsvdt_power_iteration_rk4(rsvdt_handle h, int64_t q)
 
 int rsvdt_svd_all_freqs_before_adjoint(rsvdt_handle h)
 {
+    if (h && h->group) return group_call(h, rsvdt_svd_all_freqs_before_adjoint);
     RS(bind(h));
     RS(check_ready(h));
     if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
@@ -1908,6 +1995,7 @@ int rsvdt_svd_all_freqs_before_adjoint(rsvdt_handle h)
 
 int rsvdt_store_u(rsvdt_handle h)
 {
+    if (h && h->group) return group_call(h, rsvdt_store_u);
     RS(bind(h));
     if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
     int64_t srows, roff;
@@ -1922,6 +2010,7 @@ int rsvdt_store_u(rsvdt_handle h)
 
 int rsvdt_svd_all_freqs(rsvdt_handle h)
 {
+    if (h && h->group) return group_call(h, rsvdt_svd_all_freqs);
     RS(bind(h));
     RS(check_ready(h));
     if (!h->Yhat.p || h->yhat_rows <= 0) return fail(h, RSVDT_ERR_STATE, "Y_hat not set");
@@ -1940,6 +2029,7 @@ int rsvdt_svd_all_freqs(rsvdt_handle h)
 
 int rsvdt_get_u_hat(rsvdt_handle h, double *U_host)
 {
+    if (h && h->group) return group_get_matrix(h, 1, U_host, -1);
     RS(bind(h));
     if (!U_host || !h->Uhat.p) return fail(h, RSVDT_ERR_STATE, "U_hat not available");
     int64_t srows, roff;
@@ -1949,6 +2039,7 @@ int rsvdt_get_u_hat(rsvdt_handle h, double *U_host)
 
 int rsvdt_get_v_hat(rsvdt_handle h, double *V_host)
 {
+    if (h && h->group) return group_get_matrix(h, 2, V_host, -1);
     RS(bind(h));
     if (!V_host || !h->Vhat.p) return fail(h, RSVDT_ERR_STATE, "V_hat not available");
     int64_t srows, roff;
@@ -1958,6 +2049,7 @@ int rsvdt_get_v_hat(rsvdt_handle h, double *V_host)
 
 int rsvdt_get_s_hat(rsvdt_handle h, double *S_host)
 {
+    if (h && h->group) return rsvdt_get_s_hat(h->group->m[0], S_host);
     RS(bind(h));
     if (!S_host || !h->Shat.p) return fail(h, RSVDT_ERR_STATE, "S_hat not available");
     // device layout [iw][m] == column-major k x Nw_eff
@@ -1985,6 +2077,7 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
                             double TransDivVal, double TransConVal, double *norms_out, int64_t *steps_done, int *reason,
                             rsvdt_snapshot_cb cb, void *user)
 {
+    if (h && h->group) return group_transient_run(h, direct, q0_host, rend, TransSaveMod, TransDivVal, TransConVal, norms_out, steps_done, reason, cb, user);
     RS(bind(h));
     if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "operator not set");
     if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "grid not set (dt)");
@@ -2287,6 +2380,17 @@ int rsvdt_dist_ipc_import(rsvdt_handle h, const unsigned char *all_bytes, const 
         CU(cudaIpcOpenMemHandle(&D.peer_mailbox[(size_t)p], hm, cudaIpcMemLazyEnablePeerAccess));
         CU(cudaIpcOpenMemHandle(&D.peer_flags[(size_t)p], hf, cudaIpcMemLazyEnablePeerAccess));
     }
+    return finish_connect(h, out_mb_off);
+}
+
+}  // extern "C"
+
+namespace {
+// second half of the bootstrap, common to CUDA IPC (one process per GPU) and to direct peer pointers (one process, P GPUs):
+// device-side message tables, the peers' mailbox geometry, the tables of the fused exchange
+int finish_connect(rsvdt_handle h, const int64_t *out_mb_off)
+{
+    auto &D = h->dist;
     std::vector<HaloMsgHost> mh(D.out.size());
     std::vector<unsigned long long *> pf(D.out.size());
     for (size_t i = 0; i < D.out.size(); i++) {
@@ -2324,6 +2428,9 @@ int rsvdt_dist_ipc_import(rsvdt_handle h, const unsigned char *all_bytes, const 
     D.connected = true;
     return build_fused(h);
 }
+}  // namespace
+
+extern "C" {
 
 int rsvdt_set_allreduce(rsvdt_handle h, rsvdt_allreduce_fn fn, void *user)
 {
@@ -2431,6 +2538,9 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "use_bcsr")) h->use_bcsr = value;
     else if (!strcmp(name, "use_tiled")) h->use_tiled = value;
     else if (!strcmp(name, "tiled_stages")) h->tiled_stages = value;
+    else if (!strcmp(name, "tiled_cv")) h->tiled_cv = value;
+    else if (!strcmp(name, "tiled_flags")) h->tiled_flags = value;
+    else if (!strcmp(name, "tiled_order")) h->tiled_order = value;
     else if (!strcmp(name, "tiled_ctas")) { if (value < 1 || value > 3) return fail(h, RSVDT_ERR_ARG, "tiled_ctas out of range"); h->tiled_ctas = value; }
     else if (!strcmp(name, "use_small")) h->use_small = value;
     else if (!strcmp(name, "use_graph")) h->use_graph = value;

@@ -39,6 +39,8 @@ struct TbcsrDev {
     const TbcsrWindow *win = nullptr;
     int wmax = 0;                             // longest window (block rows); 0: no windows
     int64_t nwindows_chunks = 0;              // chunks that need a window (if shared memory cannot hold the x ring the launch fails)
+    int flags = 35;                           // 1: operator chunks L2 evict-first, 2: x windows L2 evict-last, 32: L2 prefetch of the
+                                              // tile's block vectors; measurement only: 8 no FMAs, 16 no block-vector loads / stores
 };
 __host__ __device__ inline size_t tbcsr_chunk_bytes(int B, int TB) { return (size_t)B * B * TB * sizeof(cplx) + (size_t)TB * sizeof(int32_t) + 16; }
 
@@ -69,9 +71,10 @@ struct HaloFuse {
 
 bool tbcsr_stage_supported(int B, int nv);
 // mode / StageArgs as for the other stage kernels (kernels.cuh)
-// ring_stages: 0 = as many operator chunks as shared memory holds (up to 12), else at most that many
+// ring_stages: 0 = as many operator chunks as shared memory holds (up to 12), else at most that many;
+// vectors_per_thread: 0 = automatic, 1 or 2 test vectors per consumer thread
 cudaError_t launch_rk4_stage_tbcsr(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm,
-                                   int ring_stages, cudaStream_t s);
+                                   int ring_stages, int vectors_per_thread, cudaStream_t s);
 
 // Host-side plan of the x windows from the chunk columns (cols: [nchunks][TB] as stored): fills hdr ([nchunks][4]) and the
 // window lists.  nb_own: block columns below it are rows of the stage vector, the others ghost rows (separate source).

@@ -636,16 +636,23 @@ int main(int argc, char **argv)
     memset(&dirs, 0, sizeof dirs);
     setvbuf(stdout, NULL, _IOLBF, 0);
 
-    int device = 0;
-    for (int i = 1; i + 1 < argc; i++)
+    /* `-ngpus P` stands for `mpiexec -n P` of the reference (README.md:221): one process, the rows of every matrix split
+     * over P GPUs like PETSc's MATMPIAIJ / VECMPI (rsvdt_create_group); `-device d` picks the GPU of a single-GPU run. */
+    int device = 0, ngpus = 1;
+    for (int i = 1; i + 1 < argc; i++) {
         if (!strcmp(argv[i], "-device")) device = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "-ngpus")) ngpus = atoi(argv[i + 1]);
+    }
+    if (ngpus < 1) return seterr(ERR_USER, "-ngpus must be at least 1");
 
     /* PreProcessing.c:27-66.  The input file is read before the CUDA handle is created, so that a wrong variables.yaml is
      * reported the way the reference reports it on any machine (tests/test_host_driver.py compares the messages with the
      * reference executable's on CPU); everything after it needs the device. */
     CHK(ReadUserInput(argc, argv, &RSVDt, &Weight_mat, &TR_vars, &dirs));
-    int rc = rsvdt_create(device, &H);                                                                        /* SlepcInitialize, main.c:107 */
-    if (rc) return seterr(rc, "no usable CUDA device (this build has no CPU fallback)");
+    int rc = ngpus > 1 ? rsvdt_create_group(ngpus, NULL, &H) : rsvdt_create(device, &H);                      /* SlepcInitialize, main.c:107 */
+    if (rc) return seterr(rc, ngpus > 1 ? "fewer usable CUDA devices than -ngpus asks for (this build has no CPU fallback)"
+                                        : "no usable CUDA device (this build has no CPU fallback)");
+    if (ngpus > 1) printf("Rows partitioned over %d GPUs like MATMPIAIJ (PETSC_DECIDE), one process\n", ngpus);
     if (!TR_vars.TransRun) printf("********************************************\n*************** Problem info ***************\n********************************************\n\n");
     CHK(SetupTimeFreqGrid(&RSVDt, &TR_vars));
     CHK(LNSStructure(&RSVDt, &TR_vars, &dirs));

@@ -430,12 +430,13 @@ def test_driver_lns_3d_solve_matches_reference_executable(pkg, O, tmp_path):
 
 
 # ------------------------------------------------------------------------------- GPU: the drop-in executable `RSVDt`
-def _run_driver(tmp, yaml_text, files, pkg, **fmt):
+def _run_driver(tmp, yaml_text, files, pkg, ngpus=1, **fmt):
     os.makedirs(os.path.join(tmp, "results"), exist_ok=True)
     write_case_files(pkg.petsc_io, tmp, files)
     with open(os.path.join(tmp, "variables.yaml"), "w") as f:
         f.write(yaml_text.format(root=tmp, **fmt))
-    out = subprocess.run([EXE, "-inputs", "variables.yaml"], cwd=tmp, capture_output=True, text=True, timeout=900)
+    cmd = [EXE, "-inputs", "variables.yaml"] + (["-ngpus", str(ngpus)] if ngpus > 1 else [])
+    out = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     return out.stdout
 
@@ -536,3 +537,92 @@ def test_driver_tutorial_as_shipped_matches_reference_executable(pkg, tmp_path):
     angv = max(principal_angle(V[:, iw, :1], g["V_lead"][:, iw:iw + 1]) for iw in range(Nw))
     print("tutorial as shipped vs reference executable: principal angles U, V", ang, angv)
     assert ang <= ANGLE_TOL and angv <= ANGLE_TOL
+
+
+# ---------------------------------------------------- GPU x P: `RSVDt -ngpus P`, one process, rows split like `mpiexec -n P`
+def _need_gpus(n):
+    _need_gpu()
+    import torch
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs on one node (run under gpurun --gpus {n})")
+
+
+@gpu
+@pytest.mark.parametrize("tag,opt", [("tr", 1), ("notr", 2)])
+def test_driver_ngpus2_results_match_reference_executable(pkg, tmp_path, tag, opt):
+    # the C host on 2 GPUs (rsvdt_create_group: threads, direct peer mapping, NCCL from the library) against the same
+    # reference-executable outputs as the single-GPU run
+    _need_gpus(2)
+    g = _load("ref_gl_executable.npz")
+    k, Nw = 3, 8
+    F = pkg.synthetic.random_forcing(500, k, Nw, seed=3)
+    tmp = str(tmp_path)
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", F)}
+    out = _run_driver(tmp, SMALL_YAML, files, pkg, ngpus=2, Nw=Nw, w=0.6, TL=1.0, TR="true" if tag == "tr" else "false", opt=opt,
+                      transrun="false", q=1, disc="true", weights="false")
+    assert "Rows partitioned over 2 GPUs" in out
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g[f"small_files_{tag}"])
+    S = pkg.petsc_io.read_mat_dense(f"{res}/S_hat")
+    Sg = g[f"small_S_{tag}"]
+    assert S.shape == Sg.shape and np.abs(S.real / Sg.real - 1).max() <= GAIN_TOL
+    U, V = _read_modes(pkg.petsc_io, res, k, Nw, opt)
+    Ug, Vg = g[f"small_U_{tag}"], g[f"small_V_{tag}"]
+    for iw in range(Nw):
+        assert principal_angle(U[:, iw, :1], Ug[:, iw, :1]) <= ANGLE_TOL
+        assert principal_angle(V[:, iw, :1], Vg[:, iw, :1]) <= ANGLE_TOL
+
+
+@gpu
+def test_driver_ngpus2_lns_3d_solve_matches_reference_executable(pkg, O, tmp_path):
+    # block-stencil operator on 2 GPUs: tiled block-CSR stage kernel with the halo exchange inside the kernel
+    _need_gpus(2)
+    g = _load("ref_lns_functions.npz")
+    A, F = _lns_case(pkg, O, g, "3d")
+    tmp = str(tmp_path)
+    files = {"A_GL": ("csr", (A.nrows, A.ncols), (A.rowptr, A.col, A.val)), "F_hat": ("dense", F)}
+    _run_driver(tmp, SMALL_YAML, files, pkg, ngpus=2, Nw=8, w=2.0, TL=0.5, TR="true", opt=2, transrun="false", q=1, disc="false",
+                weights="false")
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    S = pkg.petsc_io.read_mat_dense(f"{res}/S_hat")
+    assert np.abs(S.real[0] / g["3d_S_hat"].real[0] - 1).max() <= GAIN_TOL
+    U, V = _read_modes(pkg.petsc_io, res, 4, 8, 2)
+    for iw in range(8):
+        assert principal_angle(U[:, iw, :1], g["3d_U_lead"][:, iw:iw + 1]) <= ANGLE_TOL
+        assert principal_angle(V[:, iw, :1], g["3d_V_lead"][:, iw:iw + 1]) <= ANGLE_TOL
+
+
+@gpu
+def test_driver_ngpus2_weighted_solve_and_transient_run(pkg, tmp_path):
+    _need_gpus(2)
+    g = _load("ref_gl_weighted.npz")
+    k, Nw = int(g["k"]), int(g["Nw"])
+    mats, shapes = weight_mats(500)
+    tmp = str(tmp_path / "w")
+    os.makedirs(tmp)
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", g["F"])}
+    for n in mats:
+        files[n] = ("csr", shapes[n], mats[n])
+    _run_driver(tmp, SMALL_YAML, files, pkg, ngpus=2, Nw=Nw, w=1.0, TL=1.0, TR="false", opt=2, transrun="false", q=1, disc="false",
+                weights="true")
+    res = os.path.join(tmp, "results", "ResolventModes_0")
+    S = pkg.petsc_io.read_mat_dense(f"{res}/S_hat")
+    assert np.abs(S.real / g["S_hat"].real - 1).max() <= GAIN_TOL
+    U, V = _read_modes(pkg.petsc_io, res, k, Nw, 2)
+    assert U.shape == g["U_hat"].shape and V.shape == g["V_hat"].shape
+    for iw in range(Nw):
+        assert principal_angle(U[:, iw, :1], g["U_hat"][:, iw, :1]) <= ANGLE_TOL
+        assert principal_angle(V[:, iw, :1], g["V_hat"][:, iw, :1]) <= ANGLE_TOL
+    # transient run on 2 GPUs (norms all-reduced over NCCL, snapshots assembled from both GPUs)
+    g = _load("ref_gl_executable.npz")
+    tmp = str(tmp_path / "t")
+    os.makedirs(tmp)
+    files = {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", np.zeros((500, 8), complex)),
+             "results/q0": ("vec", g["trans_q0"])}
+    _run_driver(tmp, SMALL_YAML, files, pkg, ngpus=2, Nw=8, w=0.6, TL=1.0, TR="false", opt=1, transrun="true", q=1, disc="true",
+                weights="false")
+    res = os.path.join(tmp, "results", "TransientSnapshots_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g["trans_files"])
+    assert np.allclose(pkg.petsc_io.read_vec(f"{res}/q_transient_norms").real, g["trans_norms"], rtol=1e-11)
+    assert rel_err(pkg.petsc_io.read_vec(f"{res}/q_transient_last_snapshot"), g["trans_last"]) < 1e-11
+    assert rel_err(pkg.petsc_io.read_vec(f"{res}/q_transient_2"), g["trans_q2"]) < 1e-11
