@@ -150,6 +150,16 @@ cudaError_t launch_cross_svd_small(const cplx *G, int k, int nw, cplx *M, double
 // Y_w <- Y_w * M_w in place (row tiles staged through shared memory)
 cudaError_t launch_apply_right(cplx *Y, int64_t nrows, int k, int nw, const cplx *M, cudaStream_t s);
 
+// The same Gram matrices on FP64 tensor cores (dense_k4.cu, mma.sync m8n8k4.f64), optionally of the transformed block
+// Y_w * M_w formed on the fly (M != null; k <= 16): the second Gram of CholeskyQR2 without storing the first pass's Q.
+// partial: gram_dmma_partial_doubles() doubles.
+int gram_dmma_num_blocks(int64_t nrows);
+size_t gram_dmma_partial_doubles(int64_t nrows, int k, int nw);
+cudaError_t launch_gram_dmma(const cplx *Y, int64_t nrows, int k, int nw, int64_t slot_stride, const cplx *M, double *partial,
+                             cplx *G, cudaStream_t s);
+// C_w = A_w * B_w, k x k each
+cudaError_t launch_small_matmul(const cplx *A, const cplx *B, int k, int nw, cplx *C, cudaStream_t s);
+
 // ||q||_2^2 partial sums -> out (deterministic two-stage)
 cudaError_t launch_norm2(const cplx *q, int64_t n, double *partial, double *out, cudaStream_t s);
 

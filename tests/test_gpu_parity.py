@@ -148,14 +148,19 @@ def test_discounting(pkg, O, A_GL):
     r.close()
 
 
-def test_qr_all_freqs(pkg, O):
+@pytest.mark.parametrize("k,opts", [(10, {}), (8, {}), (3, {}), (16, {}), (20, {}), (10, dict(qr_fused=0)),
+                                    (10, dict(qr_fused=0, gram_variant=0)), (8, dict(gram_variant=0)), (32, {})])
+def test_qr_all_freqs(pkg, O, k, opts):
+    # CholeskyQR2 in four passes (second Gram of Y*M1 on the fly, FP64 tensor cores) / in six passes / with the FMA Gram kernel
     rng = np.random.default_rng(6)
-    N, k, Nw = 3000, 10, 6
+    N, Nw = 3001, 6
     Y = np.asfortranarray(rng.standard_normal((N, k * Nw)) + 1j * rng.standard_normal((N, k * Nw)))
-    Y[:, 3] = Y[:, 2] + 1e-4 * Y[:, 3]   # cond ~ 1e4 block
+    Y[:, 3 % k] = Y[:, 2 % k] + 1e-4 * Y[:, 3 % k]   # cond ~ 1e4 block
     n, rp, ci, va = pkg.synthetic.ginzburg_landau(N)
     v = make_vars(O, pkg, N, k, Nw, 3.0, 0.004, 0.3)
     r = _handle(pkg, O.Csr(N, N, rp, ci, va), v)
+    for name, val in opts.items():
+        r.set_option(name, val)
     r.set_Y_hat(Y)
     r.QRAllFreqs()
     Q = r.get_Y_hat()
