@@ -42,7 +42,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... (csrc/Makefile), in-tree."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in ("kernels.cu", "stage_tiled.cu", "stencil_gen.cu", "capi.cu", "kernels.cuh", "stage_tiled.cuh")] + [HEADER_PATH]
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("kernels.cu", "stage_tiled.cu", "stencil_gen.cu", "dense_k4.cu", "capi.cu", "group.inc", "kernels.cuh", "stage_tiled.cuh")] + [HEADER_PATH]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
         cmd = ["make", "-C", os.path.join(_HERE, "csrc")] + ([] if verbose else ["-s"])

@@ -182,6 +182,8 @@ struct rsvdt_context {
     int64_t idft_variant = 0;
     int64_t use_banded = -1;  // -1: automatic; 0: stage kernels, 1: fused CSR banded step, 2: fused DIA step, 3: TMA-staged DIA step
     int64_t tma_variant = 0;  // 0: tiles sized for 3 CTAs/SM, 1: for 2 CTAs/SM
+    int64_t gram_variant = 1; // Gram matrices of QR / SVD: 1 = FP64 tensor cores (DMMA, dense_k4.cu), 0 = FMA kernel
+    int64_t qr_fused = 1;     // CholeskyQR2 in 5 passes over Y_hat (first apply fused with the second Gram, FP64 tensor cores) instead of 6
     int64_t use_bcsr = 1;     // block-CSR stage kernel when the operator has dense B x B blocks
     int64_t use_tiled = 1;    // ... and its TMA-staged tiled form (stage_tiled.cu) when the number of vectors is even
     int64_t tiled_flags = -1; // stage_tiled.cuh TbcsrDev::flags (-1: the default)
@@ -1398,16 +1400,25 @@ int dist_allreduce(rsvdt_handle h, void *dev_ptr, int64_t n_doubles)
 
 // Gram matrices of the per-frequency blocks of a stack with `srows` rows per slot, summed over the owned rows
 // [roff, roff + rows) and over the ranks
-int gram_all(rsvdt_handle h, const cplx *Y, int64_t rows, int64_t srows = -1, int64_t roff = 0)
+// transform (optional, device, Nw_eff x k x k): the Gram matrices of Y_w * transform_w, formed on the fly (dense_k4.cu)
+int gram_all(rsvdt_handle h, const cplx *Y, int64_t rows, int64_t srows = -1, int64_t roff = 0, const cplx *transform = nullptr)
 {
     const rsvdt_grid &g = h->g;
     if (srows < 0) srows = rows;
     const int nblk = gram_num_blocks(rows);
-    RS(ensure(h, h->gram_partial, (size_t)nblk * g.Nw_eff * g.k * g.k * sizeof(cplx)));
     RS(ensure(h, h->small, (size_t)g.Nw_eff * g.k * g.k * sizeof(cplx)));
     RS(ensure(h, h->smallM, (size_t)g.Nw_eff * g.k * g.k * sizeof(cplx)));
     RS(ensure(h, h->status, (size_t)g.Nw_eff * sizeof(int)));
-    CU(launch_gram(Y + roff * g.k, rows, (int)g.k, (int)g.Nw_eff, srows * g.k, h->gram_partial.as<cplx>(), h->small.as<cplx>(), h->stream));
+    // FP64 tensor cores (DMMA) unless switched off: ncu (profiles/r2_dense_phases_ncu.txt) has the comparison with the FMA kernel
+    if (h->gram_variant != 0 || transform) {
+        if (transform && g.k > 16) return fail(h, RSVDT_ERR_ARG, "fused CholeskyQR2 pass needs k <= 16");
+        RS(ensure(h, h->gram_partial, gram_dmma_partial_doubles(rows, (int)g.k, (int)g.Nw_eff) * sizeof(double)));
+        CU(launch_gram_dmma(Y + roff * g.k, rows, (int)g.k, (int)g.Nw_eff, srows * g.k, transform, h->gram_partial.as<double>(),
+                            h->small.as<cplx>(), h->stream));
+    } else {
+        RS(ensure(h, h->gram_partial, (size_t)nblk * g.Nw_eff * g.k * g.k * sizeof(cplx)));
+        CU(launch_gram(Y + roff * g.k, rows, (int)g.k, (int)g.Nw_eff, srows * g.k, h->gram_partial.as<cplx>(), h->small.as<cplx>(), h->stream));
+    }
     h->launches += 2;
     RS(dist_allreduce(h, h->small.p, 2 * g.Nw_eff * g.k * g.k));
     return RSVDT_OK;
@@ -1430,7 +1441,10 @@ int svd_all(rsvdt_handle h, DevBuf &Y, int64_t rows, double *dst_sigma)
     DevBuf sig;
     CU(sig.alloc((size_t)g.Nw_eff * g.k * sizeof(double)));
     CU(launch_cross_svd_small(h->small.as<cplx>(), (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), sig.as<double>(), h->stream));
-    CU(launch_apply_right(Y.as<cplx>(), srows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
+    if (h->gram_variant != 0 && g.k <= 16 && g.k % 2 == 0)
+        CU(launch_apply_dmma(Y.as<cplx>(), srows, (int)g.k, (int)g.Nw_eff, srows * g.k, h->smallM.as<cplx>(), nullptr, nullptr, h->stream));
+    else
+        CU(launch_apply_right(Y.as<cplx>(), srows, (int)g.k, (int)g.Nw_eff, h->smallM.as<cplx>(), h->stream));
     h->launches += 2;
     if (dst_sigma) CU(cudaMemcpyAsync(dst_sigma, sig.p, (size_t)g.Nw_eff * g.k * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1938,8 +1952,39 @@ int rsvdt_qr_all_freqs(rsvdt_handle h)
     std::vector<int> st((size_t)g.Nw_eff);
     int64_t srows, roff;
     stack_geom(h, h->yhat_rows, &srows, &roff);
-    // CholeskyQR2 (QRAllFreqs.c:22-32 semantics: thin Q with diag(R) > 0).  If a Cholesky factorisation breaks down (a block
-    // with condition number beyond ~1e8) the pass is redone with the shift of shifted CholeskyQR3 and two more passes follow.
+    // CholeskyQR2 (QRAllFreqs.c:22-32 semantics: thin Q with diag(R) > 0) in five passes over Y_hat instead of six, all on FP64
+    // tensor cores: G1 = Y^H Y (read); Y <- Y M1 and, in the same pass, G2 = Gram of the rounded product (read + write);
+    // Y <- Y M2 (read + write).  (Folding M1 M2 into ONE apply would save another pass but loses orthogonality to
+    // cond(Y) * eps -- measured 8e-13 at cond 1e4 -- so the second factor is applied to the orthonormalised block, as
+    // CholeskyQR2 prescribes.)  Any breakdown falls through to the general loop below, on the untouched or once-scaled Y.
+    if (h->qr_fused && g.k <= 16 && g.k % 2 == 0) {
+        auto chol_ok = [&](bool *ok) -> int {
+            CU(launch_chol_inverse_big(h->small.as<cplx>(), (int)g.k, (int)g.Nw_eff, 0.0, h->smallM.as<cplx>(), h->status.as<int>(), h->stream));
+            h->launches += 1;
+            CU(cudaMemcpyAsync(st.data(), h->status.p, st.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            *ok = true;
+            for (int64_t w = 0; w < g.Nw_eff; w++) *ok = *ok && st[(size_t)w] == 0;
+            return RSVDT_OK;
+        };
+        bool ok = false;
+        RS(gram_all(h, h->Yhat.as<cplx>(), h->yhat_rows, srows, roff));
+        RS(chol_ok(&ok));
+        if (ok) {
+            cplx *Yo = h->Yhat.as<cplx>() + roff * g.k;
+            RS(ensure(h, h->gram_partial, gram_dmma_partial_doubles(h->yhat_rows, (int)g.k, (int)g.Nw_eff) * sizeof(double)));
+            CU(launch_apply_dmma(Yo, h->yhat_rows, (int)g.k, (int)g.Nw_eff, srows * g.k, h->smallM.as<cplx>(), h->gram_partial.as<double>(),
+                                 h->small.as<cplx>(), h->stream));
+            h->launches += 2;
+            RS(dist_allreduce(h, h->small.p, 2 * g.Nw_eff * g.k * g.k));
+            RS(chol_ok(&ok));
+            if (!ok) return fail(h, RSVDT_ERR_NUMERIC, "QR breakdown in the second CholeskyQR pass: numerically rank-deficient block");
+            CU(launch_apply_dmma(Yo, h->yhat_rows, (int)g.k, (int)g.Nw_eff, srows * g.k, h->smallM.as<cplx>(), nullptr, nullptr, h->stream));
+            h->launches += 1;
+            CU(cudaStreamSynchronize(h->stream));
+            return RSVDT_OK;
+        }
+    }
     int npass = 2;
     bool shifted = false;
     for (int pass = 0; pass < npass; pass++) {
@@ -2536,6 +2581,8 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "use_banded")) h->use_banded = value;
     else if (!strcmp(name, "tma_variant")) h->tma_variant = value;
     else if (!strcmp(name, "use_bcsr")) h->use_bcsr = value;
+    else if (!strcmp(name, "gram_variant")) h->gram_variant = value;
+    else if (!strcmp(name, "qr_fused")) h->qr_fused = value;
     else if (!strcmp(name, "use_tiled")) h->use_tiled = value;
     else if (!strcmp(name, "tiled_stages")) h->tiled_stages = value;
     else if (!strcmp(name, "tiled_cv")) h->tiled_cv = value;

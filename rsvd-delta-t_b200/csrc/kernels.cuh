@@ -157,6 +157,10 @@ int gram_dmma_num_blocks(int64_t nrows);
 size_t gram_dmma_partial_doubles(int64_t nrows, int k, int nw);
 cudaError_t launch_gram_dmma(const cplx *Y, int64_t nrows, int k, int nw, int64_t slot_stride, const cplx *M, double *partial,
                              cplx *G, cudaStream_t s);
+// Y_w <- Y_w * M_w in place on FP64 tensor cores (even k <= 16); G != null: also the Gram matrices of the rounded product
+// (partial as for launch_gram_dmma) -- the apply of CholeskyQR2's first pass fused with the Gram of its second
+cudaError_t launch_apply_dmma(cplx *Y, int64_t nrows, int k, int nw, int64_t slot_stride, const cplx *M, double *partial, cplx *G,
+                              cudaStream_t s);
 // C_w = A_w * B_w, k x k each
 cudaError_t launch_small_matmul(const cplx *A, const cplx *B, int k, int nw, cplx *C, cudaStream_t s);
 

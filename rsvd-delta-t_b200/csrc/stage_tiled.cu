@@ -426,14 +426,14 @@ cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, c
     const size_t budget = std::min(smem_max, (size_t)(228 * 1024) / ctas_per_sm - 1024) - 256;
     const size_t xslot = ((size_t)B * nv * sizeof(cplx) + 16) * (size_t)Op.wmax;
     int nsx = 0, nsa = 0;
-    if (Op.win_ptr && Op.wmax > 0 && 2 * xslot + 3 * chunk > budget && ctas_per_sm == 3) return launch_t<B, NCW, CV>(Op, nv, mode, a, hf, 2, nsa_req, s);
-    if (Op.win_ptr && Op.wmax > 0 && 2 * xslot + 3 * chunk <= budget) nsx = 2;
+    if (Op.win_ptr && Op.wmax > 0 && 2 * xslot + 2 * chunk > budget && ctas_per_sm == 3) return launch_t<B, NCW, CV>(Op, nv, mode, a, hf, 2, nsa_req, s);
+    if (Op.win_ptr && Op.wmax > 0 && 2 * xslot + 2 * chunk <= budget) nsx = 2;
     TbcsrDev op = Op;
     if (!nsx) { op.win_ptr = nullptr; op.win = nullptr; }   // the x windows do not fit next to the operator ring: gather mode
     nsa = (int)((budget - (size_t)nsx * xslot) / chunk);
     if (nsa > 12) nsa = 12;
-    if (nsa_req >= 3 && nsa_req < nsa) nsa = nsa_req;
-    if (nsa < 3) return cudaErrorInvalidValue;
+    if (nsa_req >= 2 && nsa_req < nsa) nsa = nsa_req;
+    if (nsa < 2) return cudaErrorInvalidValue;
     const size_t smem = 128 * ((2 * (size_t)(nsa + nsx) * 8 + 127) / 128) + (size_t)nsa * chunk + (size_t)nsx * xslot;
     const int threads = (NCW + 1) * 32;
     const unsigned grid = (unsigned)std::min<int64_t>(Op.ntiles, (int64_t)n_sm * ctas_per_sm);

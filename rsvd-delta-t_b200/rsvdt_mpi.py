@@ -546,10 +546,12 @@ class Run:
             self.log(f"Time-stepping parameters:\n@ TransientLength = {v['TransientLength']:g}\n@ dt              = {dt:g}\n"
                      f"@ Ns              = {Ns}\n@ Nt              = {Nt}")
             self.log("Transient removal strategy is requested\n" if v["TransientRemoval"] else "Transient removal strategy is NOT requested\n")
+        t_start = time.time()
         self.lns_structure(v)
         if not v["TransRun"]:
             self.read_weight_mats(v)
             self.create_random_mat(v)
+        t_setup = time.time() - t_start
         self.create_results_dir(v, "TransientSnapshots_" if v["TransRun"] else "ResolventModes_")
         r = self.r
         if v["TransRun"]:                                                             # main.c:119-124
@@ -591,7 +593,20 @@ class Run:
         timed("\n*** Reduced SVD begins! ***", r.SVDAllFreqs, "*** Reduced SVD elapsed time = ")               # :144
         c0, c1 = pkg.dist.split_ownership(v["Nc"], self.world, self.rank)
         b0, b1 = pkg.dist.split_ownership(v["Nb"], self.world, self.rank)
-        self.save_results(v, r.get_S_hat(), r.get_U_hat(c1 - c0), r.get_V_hat(b1 - b0))                        # :146
+        t_solve = time.time() - t_start - t_setup
+        t0 = time.time()
+        gains_only = os.environ.get("RSVDT_MPI_SAVE") == "gains"      # (then the 2 x 10 GB per GPU of modes stay on the device)
+        self.save_results(v, r.get_S_hat(), None if gains_only else r.get_U_hat(c1 - c0),
+                          None if gains_only else r.get_V_hat(b1 - b0))                                          # :146
+        if os.environ.get("RSVDT_MPI_TIMINGS") and self.rank == 0:   # not in the reference: the record of the run, as JSON
+            import json
+            with open(os.environ["RSVDT_MPI_TIMINGS"], "w") as f:
+                json.dump({"N": v["N"], "k": v["k"], "Nw": v["Nw"], "q": v["q"], "TransientRemoval": bool(v["TransientRemoval"]),
+                           "n_gpus": self.world, "dt": v["dt"], "Ns": v["Ns"], "Nt": v["Nt"], "ResRatio": v["ResRatio"],
+                           "rk4_steps_per_action": rend, "setup_s (operator, weights, forcing)": t_setup,
+                           "solve_s (main.c:134-144)": t_solve, "save_s": time.time() - t0,
+                           "phases_s": [[n, s] for n, s in self.phase_times],
+                           "kernel_launches_rank0": int(r.kernel_launches())}, f, indent=1)
         return 0
 
 
@@ -621,6 +636,13 @@ def main(argv=None):
         if int(os.environ.get("RANK", "0")) == 0:
             print(f"[0]RSVDt ERROR: {e}", file=sys.stderr, flush=True)
         rc = ERR_USER
+    except Exception as e:
+        # a library error on ONE rank (e.g. a QR breakdown in its rows, a peer that stopped answering): the other ranks sit in
+        # collectives, so this process leaves at once -- the launcher (torchrun, like mpiexec) then takes the other ranks down
+        print(f"[{os.environ.get('RANK', '0')}]RSVDt ERROR: {e}", file=sys.stderr, flush=True)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            os._exit(getattr(e, "code", 1) or 1)
+        rc = getattr(e, "code", 1) or 1
     finally:
         if run is not None and run.r is not None:
             run.r.close()
