@@ -318,10 +318,12 @@ def rel_err(a, b):
 # ---------------------------------------------------------------------------------------------------------------------
 def parity_section(cx: Ctx):
     pkg, world, rank = cx.pkg, cx.world, cx.rank
+    host_threads()
     from oracle import oracle as O
     O.build()
     S, D = pkg.synthetic, pkg.dist
     out = {}
+    ref_cache = {}   # the csr-upload and device-generated cases share operator, forcing and hence the oracle's answer
 
     def oracle_action(A, v, F, direct):
         vv = O.Vars(**{**v.__dict__, "DirAdj": direct})
@@ -347,12 +349,18 @@ def parity_section(cx: Ctx):
                 if rank == 0:
                     A = O.Csr(N, N, rp, ci, va)
                     if weights is None:
-                        ref = oracle_action(A, v, F, direct)
+                        key = (N, k, Nw, len(va), direct)
+                        if key not in ref_cache:
+                            ref_cache[key] = oracle_action(A, v, F, direct)
+                        ref = ref_cache[key]
                     else:
                         d = WEIGHT_DIAG(N)
                         Fin = F * (d[:, None] if direct else (1.0 / d)[:, None])
                         ref = oracle_action(A, v, np.asfortranarray(Fin), direct) * ((1.0 / d)[:, None] if direct else d[:, None])
                     errs.append(rel_err(got, ref))
+                # rank 0 has just spent seconds on the host inside the oracle: the ranks start the next action together, or their
+                # stage kernels would sit in the halo wait for that long (and give up: the wait is bounded)
+                cx.barrier()
         finally:
             r.close()
         if rank == 0:
@@ -375,7 +383,7 @@ def parity_section(cx: Ctx):
     run_case("layout1_gl_band", Ngl, (rp, ci, va), 4, 4, 2.0, 0.25, h_gl)
 
     # ---- layout 0 (general sparsity, one exchange per stage, fused into the tiled stage kernel): 3-D block stencil ----------
-    shape = (4 * max(world, 1), 6, 5)
+    shape = ((4 if world <= 2 else 2) * max(world, 1), 6, 5)   # (the oracle on rank 0 is serial: keep its share of the run small)
     Nl, rpl, cil, val_ = S.lns_stencil(shape, nvar=5)
     bw = (6 * 5 + 5 + 1) * 5 + 5
 

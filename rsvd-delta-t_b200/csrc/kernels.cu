@@ -1443,16 +1443,23 @@ cudaError_t launch_chol_inverse(const cplx *G, int k, int nw, cplx *M, int *stat
 
 // Cross-product SVD of a tall block through its Gram matrix (SLEPc's default SVD type, SVDAllFreqs.c:36-40):
 // cyclic complex Jacobi on G_w; sigma = sqrt(lambda) sorted descending; M = V diag(1/sigma) so that U = Y M.
-__global__ void cross_svd_small_kernel(const cplx *__restrict__ Gin, int k, int nw, cplx *__restrict__ M,
-                                       double *__restrict__ sigma)
+// One warp per frequency, G and V in shared memory (k <= 32: 2 x 16 KB): lane r owns row r in the column updates and
+// column r in the row update, so a rotation is three conflict-light passes of one element pair per lane instead of 3k
+// serial ones; the rotation angles and the order (p, q) are those of the serial sweep, so the result does not depend on
+// the lane count.  (Round 1 ran one THREAD per frequency with 32 KB of local stack: 0.3-3.3 ms per call at Nw = 32.)
+__global__ void __launch_bounds__(32)
+cross_svd_small_kernel(const cplx *__restrict__ Gin, int k, int nw, cplx *__restrict__ M, double *__restrict__ sigma)
 {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nw) return;
-    cplx G[32 * 32], V[32 * 32];  // row-major
-    for (int t = 0; t < k * k; t++) { G[t] = Gin[(int64_t)w * k * k + t]; V[t] = make_double2(0.0, 0.0); }
-    for (int i = 0; i < k; i++) V[i * k + i] = make_double2(1.0, 0.0);
+    extern __shared__ cplx jsm[];
+    cplx *G = jsm, *V = jsm + k * k;   // row-major
+    __shared__ int ord[32];
+    const int w = blockIdx.x, lane = threadIdx.x;
+    for (int t = lane; t < k * k; t += 32) { G[t] = Gin[(int64_t)w * k * k + t]; V[t] = make_double2(0.0, 0.0); }
+    __syncwarp();
+    if (lane < k) V[lane * k + lane] = make_double2(1.0, 0.0);
+    __syncwarp();
     for (int sweep = 0; sweep < 60; sweep++) {
-        double off = 0.0, dg = 0.0;
+        double off = 0.0, dg = 0.0;   // (every lane sums all entries in the same order: one decision for the warp)
         for (int r = 0; r < k; r++)
             for (int c = 0; c < k; c++) {
                 const double a2 = G[r * k + c].x * G[r * k + c].x + G[r * k + c].y * G[r * k + c].y;
@@ -1463,7 +1470,7 @@ __global__ void cross_svd_small_kernel(const cplx *__restrict__ Gin, int k, int 
             for (int q = p + 1; q < k; q++) {
                 const cplx gpq = G[p * k + q];
                 const double apq = sqrt(gpq.x * gpq.x + gpq.y * gpq.y);
-                if (apq == 0.0) continue;
+                if (apq == 0.0) continue;   // (uniform over the warp)
                 const double app = G[p * k + p].x, aqq = G[q * k + q].x;
                 const cplx ph = make_double2(gpq.x / apq, gpq.y / apq);  // e^{i phi}
                 const double tau = (aqq - app) / (2.0 * apq);
@@ -1471,40 +1478,46 @@ __global__ void cross_svd_small_kernel(const cplx *__restrict__ Gin, int k, int 
                 const double c = 1.0 / sqrt(1.0 + t * t), sn = t * c;
                 const cplx sph = make_double2(sn * ph.x, sn * ph.y);    // s e^{i phi}
                 const cplx sphc = make_double2(sn * ph.x, -sn * ph.y);  // s e^{-i phi}
-                for (int r = 0; r < k; r++) {  // G <- G J : col p = c*gp - s e^{-i phi} gq ; col q = s e^{i phi} gp + c gq
+                __syncwarp();
+                if (lane < k) {  // G <- G J : col p = c*gp - s e^{-i phi} gq ; col q = s e^{i phi} gp + c gq
+                    const int r = lane;
                     const cplx gp = G[r * k + p], gq = G[r * k + q];
                     const cplx a = cmul(sphc, gq), b = cmul(sph, gp);
                     G[r * k + p] = make_double2(c * gp.x - a.x, c * gp.y - a.y);
                     G[r * k + q] = make_double2(b.x + c * gq.x, b.y + c * gq.y);
                 }
-                for (int cc = 0; cc < k; cc++) {  // G <- J^H G : row p = c*gp - s e^{i phi} gq ; row q = s e^{-i phi} gp + c gq
+                __syncwarp();
+                if (lane < k) {  // G <- J^H G : row p = c*gp - s e^{i phi} gq ; row q = s e^{-i phi} gp + c gq
+                    const int cc = lane;
                     const cplx gp = G[p * k + cc], gq = G[q * k + cc];
                     const cplx a = cmul(sph, gq), b = cmul(sphc, gp);
                     G[p * k + cc] = make_double2(c * gp.x - a.x, c * gp.y - a.y);
                     G[q * k + cc] = make_double2(b.x + c * gq.x, b.y + c * gq.y);
-                }
-                for (int r = 0; r < k; r++) {  // V <- V J
+                    const int r = lane;   // V <- V J
                     const cplx vp = V[r * k + p], vq = V[r * k + q];
-                    const cplx a = cmul(sphc, vq), b = cmul(sph, vp);
-                    V[r * k + p] = make_double2(c * vp.x - a.x, c * vp.y - a.y);
-                    V[r * k + q] = make_double2(b.x + c * vq.x, b.y + c * vq.y);
+                    const cplx a2 = cmul(sphc, vq), b2 = cmul(sph, vp);
+                    V[r * k + p] = make_double2(c * vp.x - a2.x, c * vp.y - a2.y);
+                    V[r * k + q] = make_double2(b2.x + c * vq.x, b2.y + c * vq.y);
                 }
+                __syncwarp();
             }
     }
     // sort descending (selection sort on indices)
-    int ord[32];
-    for (int i = 0; i < k; i++) ord[i] = i;
-    for (int i = 0; i < k; i++)
-        for (int j = i + 1; j < k; j++)
-            if (G[ord[j] * k + ord[j]].x > G[ord[i] * k + ord[i]].x) { int tt = ord[i]; ord[i] = ord[j]; ord[j] = tt; }
+    if (lane == 0) {
+        for (int i = 0; i < k; i++) ord[i] = i;
+        for (int i = 0; i < k; i++)
+            for (int j = i + 1; j < k; j++)
+                if (G[ord[j] * k + ord[j]].x > G[ord[i] * k + ord[i]].x) { int tt = ord[i]; ord[i] = ord[j]; ord[j] = tt; }
+    }
+    __syncwarp();
     for (int mI = 0; mI < k; mI++) {
         const double lam = G[ord[mI] * k + ord[mI]].x;
         const double sg = sqrt(lam > 0.0 ? lam : 0.0);
-        sigma[(int64_t)w * k + mI] = sg;
+        if (lane == 0) sigma[(int64_t)w * k + mI] = sg;
         const double inv = sg > 0.0 ? 1.0 / sg : 0.0;
-        for (int r = 0; r < k; r++) {
-            const cplx v = V[r * k + ord[mI]];
-            M[(int64_t)w * k * k + r * k + mI] = make_double2(v.x * inv, v.y * inv);
+        if (lane < k) {
+            const cplx v = V[lane * k + ord[mI]];
+            M[(int64_t)w * k * k + lane * k + mI] = make_double2(v.x * inv, v.y * inv);
         }
     }
 }
@@ -1512,7 +1525,8 @@ __global__ void cross_svd_small_kernel(const cplx *__restrict__ Gin, int k, int 
 cudaError_t launch_cross_svd_small(const cplx *G, int k, int nw, cplx *M, double *sigma, cudaStream_t s)
 {
     if (k > 32) return cudaErrorInvalidValue;
-    cross_svd_small_kernel<<<(nw + 31) / 32, 32, 0, s>>>(G, k, nw, M, sigma);
+    if (nw <= 0) return cudaSuccess;
+    cross_svd_small_kernel<<<nw, 32, 2 * (size_t)k * k * sizeof(cplx), s>>>(G, k, nw, M, sigma);
     return cudaGetLastError();
 }
 

@@ -140,7 +140,8 @@ DEVFN void st_release_sys(unsigned long long *p, unsigned long long v)
     asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
 
-constexpr long long HALO_SPIN_LIMIT = 40000000ll;   // tens of seconds of polling: a dead peer must not hang the node
+constexpr long long HALO_SPIN_LIMIT = 600000000ll;   // minutes of polling (a rank may be busy on its host for a while), but a
+                                                      // dead peer must not hang the node for good
 
 // ---------------------------------------------------------------------------------------------------------------------
 // NCW consumer warps (TB * nv/2 threads, thread = (block row of the tile, pair of test vectors)) + 1 producer warp.

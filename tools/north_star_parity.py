@@ -35,22 +35,38 @@ ap.add_argument("--shape", type=int, nargs=3, default=[16, 10, 12])
 ap.add_argument("--k", type=int, default=8)
 ap.add_argument("--Nw", type=int, default=8)
 ap.add_argument("--json", default="")
+ap.add_argument("--prepare", action="store_true", help="write the case and run the reference executable only (CPU; e.g. into "
+                "oracle/_ref/ns_parity_case, which travels to the GPU box), so that the multi-GPU box time goes to the GPU runs")
+ap.add_argument("--prepared", action="store_true", help="--out holds a case made by --prepare: skip the reference executable")
 a = ap.parse_args()
 
 pkg = entry.load_package()
 io = pkg.petsc_io
-if os.path.exists(a.out):
-    shutil.rmtree(a.out)
-info = make_case.write_case(pkg, a.out, "lns3d", shape=a.shape, k=a.k, Nw=a.Nw, w=2.0, dt=0.003, TL=0.5, TR=True, q=1, opt=2,
-                            forcing=True)
-from oracle import ref as R  # noqa: E402
-if not R.available():
-    raise SystemExit("oracle/_ref is not built: the reference executable is the checker of this script")
-t0 = time.time()
-out = R.run_executable(a.out, threads=os.cpu_count())
-t_ref = time.time() - t0
-if out.returncode != 0:
-    raise SystemExit("RSVDt_ref failed:\n" + out.stdout[-2000:] + out.stderr[-2000:])
+meta_path = os.path.join(a.out, "ns_parity_meta.json")
+if a.prepared:
+    meta = json.load(open(meta_path))
+    info, t_ref = meta["info"], meta["reference_executable_s"]
+    a.shape, a.k, a.Nw = meta["shape"], meta["k"], meta["Nw"]
+    for d in os.listdir(os.path.join(a.out, "results")):        # results of earlier GPU runs: the executable numbers its directories
+        if d != "ResolventModes_0":
+            shutil.rmtree(os.path.join(a.out, "results", d))
+else:
+    if os.path.exists(a.out):
+        shutil.rmtree(a.out)
+    info = make_case.write_case(pkg, a.out, "lns3d", shape=a.shape, k=a.k, Nw=a.Nw, w=2.0, dt=0.003, TL=0.5, TR=True, q=1, opt=2,
+                                forcing=True)
+    from oracle import ref as R  # noqa: E402
+    if not R.available():
+        raise SystemExit("oracle/_ref is not built: the reference executable is the checker of this script")
+    t0 = time.time()
+    out = R.run_executable(a.out, threads=os.cpu_count())
+    t_ref = time.time() - t0
+    if out.returncode != 0:
+        raise SystemExit("RSVDt_ref failed:\n" + out.stdout[-2000:] + out.stderr[-2000:])
+    json.dump({"info": info, "reference_executable_s": t_ref, "shape": list(a.shape), "k": a.k, "Nw": a.Nw}, open(meta_path, "w"))
+    if a.prepare:
+        print(f"prepared {a.out}: reference executable took {t_ref:.1f} s")
+        sys.exit(0)
 
 
 def read(res):
