@@ -190,6 +190,8 @@ struct rsvdt_context {
     int64_t tiled_order = 8;  // grid lines per group of the z-fastest tile order of 3-D stencil operators (0: row order)
     int64_t tiled_cv = 0;     // test vectors per consumer thread of the tiled stage kernel (0: automatic)
     int64_t tiled_stages = 0; // operator ring depth of the tiled stage kernel; 0 = what shared memory holds
+    int64_t tiled_variant = 37; // compile-time variant of the tiled stage kernel (stage_tiled.cu VAR_*; B = 5, k = 8 only): batched epilogue
+                                // loads + setmaxnreg + single-copy x windows, the fastest of profiles/r2_lns3d_stage_variants.json
     int64_t tiled_ctas = 2;   // resident CTAs per SM of the tiled stage kernel (ring depth follows from the shared memory left)
     int64_t use_small = 1;    // single-CTA persistent kernel when the whole block vector fits in one SM's shared memory
 
@@ -447,8 +449,8 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
                     const std::vector<int64_t> &dg = tile_diags[(size_t)t];
                     for (int64_t pch = 0; pch < nch; pch++) {
                         unsigned char *base = chunks.data() + (size_t)(tptr[(size_t)t] + pch) * cb;
-                        cplx *cv = reinterpret_cast<cplx *>(base);
-                        int32_t *cc = reinterpret_cast<int32_t *>(base + (size_t)B * B * TB * sizeof(cplx));
+                        cplx *cv = reinterpret_cast<cplx *>(base + tbcsr_vals_offset(TB));
+                        int32_t *cc = reinterpret_cast<int32_t *>(base + tbcsr_cols_offset());
                         for (int tbi = 0; tbi < TB; tbi++) {
                             const int64_t br = t * TB + tbi;
                             int64_t q = -1;   // the block of row br that belongs to this chunk
@@ -473,11 +475,11 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
             {
                 std::vector<int32_t> ccols((size_t)std::max<int64_t>(nchunks, 1) * TB);
                 for (int64_t pch = 0; pch < nchunks; pch++)
-                    memcpy(ccols.data() + (size_t)pch * TB, chunks.data() + (size_t)pch * cb + (size_t)B * B * TB * sizeof(cplx), (size_t)TB * sizeof(int32_t));
+                    memcpy(ccols.data() + (size_t)pch * TB, chunks.data() + (size_t)pch * cb + tbcsr_cols_offset(), (size_t)TB * sizeof(int32_t));
                 TbcsrPlan plan;
                 tbcsr_plan_windows(ntiles, tptr.data(), ccols.data(), nbrows, out_cols / B, TB, TBCSR_WMAX, plan);
                 for (int64_t pch = 0; pch < nchunks; pch++)
-                    memcpy(chunks.data() + (size_t)pch * cb + (size_t)B * B * TB * sizeof(cplx) + (size_t)TB * sizeof(int32_t), plan.hdr.data() + (size_t)pch * 4, 16);
+                    memcpy(chunks.data() + (size_t)pch * cb + tbcsr_cols_offset() + (size_t)TB * sizeof(int32_t), plan.hdr.data() + (size_t)pch * 4, 16);
                 CU(dst.t_winptr.alloc(plan.win_ptr.size() * sizeof(int64_t)));
                 CU(dst.t_win.alloc(std::max<size_t>(plan.win.size(), 1) * sizeof(TbcsrWindow)));
                 CU(cudaMemcpy(dst.t_winptr.p, plan.win_ptr.data(), plan.win_ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -719,7 +721,7 @@ cudaError_t launch_stage_any(rsvdt_handle h, const CsrOwned &Op, int nv, int mod
             D.fz_last_out = mode == 2 ? a.acc_out : a.xout;
             D.fz_last_nv = nv;
         }
-        return launch_rk4_stage_tbcsr(top, nv, mode, a, hf, (int)h->tiled_ctas, (int)h->tiled_stages, (int)h->tiled_cv, h->stream);
+        return launch_rk4_stage_tbcsr(top, nv, mode, a, hf, (int)h->tiled_ctas, (int)h->tiled_stages, (int)h->tiled_cv, (int)h->tiled_variant, h->stream);
     }
     if (Op.stencil_only) return cudaErrorNotSupported;   // device-generated operators exist in the tiled form only (even nv)
     if (h->use_bcsr && Op.bcsr_valid && bcsr_stage_supported(Op.bcsr.B, nv))
@@ -1578,7 +1580,7 @@ int build_stencil_operator(rsvdt_handle h, CsrOwned &Op, StencilSpec sp, int64_t
     CU(cudaStreamSynchronize(h->stream));
     {   // x windows: the chunk columns come back (4 B per block), the plan goes into the chunk headers
         std::vector<int32_t> ccols((size_t)std::max<int64_t>(nchunks, 1) * TB);
-        const size_t coff = (size_t)B * B * TB * sizeof(cplx);
+        const size_t coff = tbcsr_cols_offset();
         if (nchunks) CU(cudaMemcpy2D(ccols.data(), (size_t)TB * sizeof(int32_t), Op.t_chunks.as<unsigned char>() + coff, cb,
                                      (size_t)TB * sizeof(int32_t), (size_t)nchunks, cudaMemcpyDeviceToHost));
         TbcsrPlan plan;
@@ -1658,6 +1660,7 @@ int rsvdt_create(int device, rsvdt_handle *hout)
     if (!h) return RSVDT_ERR_MEM;
     h->device = device;
     if (const char *e = getenv("RSVDT_TILED_ORDER")) h->tiled_order = atoll(e);   // measurement hook (set before the operator)
+    if (const char *e = getenv("RSVDT_TILED_VARIANT")) h->tiled_variant = atoll(e);   // (the same, for runs of the test suite under a variant)
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -2586,6 +2589,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "use_tiled")) h->use_tiled = value;
     else if (!strcmp(name, "tiled_stages")) h->tiled_stages = value;
     else if (!strcmp(name, "tiled_cv")) h->tiled_cv = value;
+    else if (!strcmp(name, "tiled_variant")) h->tiled_variant = value;
     else if (!strcmp(name, "tiled_flags")) h->tiled_flags = value;
     else if (!strcmp(name, "tiled_order")) h->tiled_order = value;
     else if (!strcmp(name, "tiled_ctas")) { if (value < 1 || value > 3) return fail(h, RSVDT_ERR_ARG, "tiled_ctas out of range"); h->tiled_ctas = value; }

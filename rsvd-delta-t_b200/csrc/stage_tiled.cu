@@ -79,6 +79,13 @@ template <int CV> DEVFN VecC<CV> axpyv(double c, const VecC<CV> &s, const VecC<C
 }
 
 DEVFN unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// shared-memory load that keeps its place among the barrier operations (volatile, no memory clobber: FMAs may move around it)
+DEVFN cplx lds_c(unsigned addr)
+{
+    cplx v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
 DEVFN void mbar_init(unsigned long long *bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -147,7 +154,7 @@ constexpr long long HALO_SPIN_LIMIT = 600000000ll;   // minutes of polling (a ra
 // NCW consumer warps (TB * nv/2 threads, thread = (block row of the tile, pair of test vectors)) + 1 producer warp.
 //
 // Shared memory: [mbarriers][operator ring: NSA chunks][x ring: NSX windows of WMAX padded block rows].
-// Chunk = [B*B][TB] entries, [TB] block columns, header {xoff, flags, -, -}:
+// Chunk = [TB] block columns, header {xoff, flags, -, -}, [B*B][TB] entries:
 //   xoff != TBCSR_GATHER: the block columns of the chunk are affine in the block row (col = base + tb) and their rows of the
 //     stage vector sit in the current x window at block (xoff + tb); flags bit0: first chunk of its window (wait for it),
 //     bit1: last chunk of its window (release it).  The window [start, start + n) -- one contiguous range of the stage
@@ -157,29 +164,45 @@ constexpr long long HALO_SPIN_LIMIT = 600000000ll;   // minutes of polling (a ra
 //     block: 2.8x fewer bytes than per-thread gathers for the 27-point stencil, and no load latency in the FMA loop.
 //   xoff == TBCSR_GATHER: general sparsity -- per-thread 256-bit gathers straight from global memory.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int B, int NCW, int MINB, int CV>
-__global__ void __launch_bounds__((NCW + 1) * 32, MINB)
+// VAR (compile-time variant bits; 0 = the kernel as profiled in profiles/r2_lns3d_stage_windows_ncu.txt):
+//   1  epilogue: all loads of the tile's block vectors first, then the arithmetic and the stores
+//   2  tile bookkeeping and the forcing rows fetched one tile ahead
+//   4  setmaxnreg: 8 warps (3 leave at once), the producer warpgroup hands registers to the consumer warpgroup (NCW == 4)
+//   8  the operator ring is released and refilled piece by piece (block column j of the TB blocks of a chunk)
+//  16  operator entries / x values of block column j + 1 fetched from shared memory before the FMAs of column j
+//  32  an x window is ONE bulk copy (unpadded rows; the two vectors of a thread are read in an order that depends on the parity
+//      of its block row, which keeps the 128-bit shared-memory reads conflict-free without the 16-byte row padding): the copy
+//      engine handles ~one request per 50 cycles whatever its size, and 34 row copies per window kept it busy half of the time
+constexpr int VAR_EPI = 1, VAR_NEXT = 2, VAR_SMR = 4, VAR_PIECE = 8, VAR_LDS = 16, VAR_XBULK = 32;
+
+template <int B, int NCW, int MINB, int CV, int VAR>
+__global__ void __launch_bounds__((VAR & VAR_SMR) ? 256 : (NCW + 1) * 32, MINB)
 rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int mode, const int nsa, const int nsx,
                        const int wmax, const StageArgs a, const HaloFuse hf)
 {
     constexpr int TB = TBCSR_TB;
     constexpr int BB = B * B;
     constexpr unsigned CHUNK = BB * TB * sizeof(cplx) + TB * sizeof(int32_t) + 4 * sizeof(int32_t);
+    constexpr int NP = (VAR & VAR_PIECE) ? B : 1;                        // release granularity: pieces per chunk
+    constexpr unsigned PIECE = B * TB * sizeof(cplx);                    // block column j of the TB blocks of a chunk
+    constexpr unsigned HEAD = TB * sizeof(int32_t) + 4 * sizeof(int32_t);  // block columns + header ride with the first piece
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);
-    unsigned long long *empty = full + nsa;
-    unsigned long long *xfull = empty + nsa;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem);   // [nsa][NP] piece landed
+    unsigned long long *empty = full + nsa * NP;                                 // [nsa][NP] piece released by all consumer warps
+    unsigned long long *xfull = empty + nsa * NP;
     unsigned long long *xempty = xfull + nsx;
-    unsigned char *ring = smem + 128 * ((2 * (nsa + nsx) * 8 + 127) / 128);
-    const unsigned xstride = (unsigned)(B * nv) * sizeof(cplx) + 16u;   // padded block row of the stage vector
+    unsigned char *ring = smem + 128 * (((2 * nsa * NP + 2 * nsx) * 8 + 127) / 128);
+    const unsigned xstride = (unsigned)(B * nv) * sizeof(cplx) + ((VAR & VAR_XBULK) ? 0u : 16u);   // (padded) block row of the stage vector
     const unsigned xslot = xstride * (unsigned)wmax;
     unsigned char *xring = ring + (size_t)nsa * CHUNK;
 
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < nsa; s++) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, NCW);
+            for (int j = 0; j < NP; j++) {
+                mbar_init(full + s * NP + j, 1);
+                mbar_init(empty + s * NP + j, NCW);
+            }
         }
         for (int s = 0; s < nsx; s++) {
             mbar_init(xfull + s, 1);
@@ -191,8 +214,16 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
 
     const int64_t ntiles = op.ntiles;
     const int lane = tid & 31;
+    if (VAR & VAR_SMR) {
+        if (tid >= NCW * 32) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;\n");
+        if (tid >= (NCW + 1) * 32) return;
+    }
     if (tid >= NCW * 32) {
         // ---------------- producer warp: keeps both rings full, running ahead over tile boundaries -------------------------
+        // ONE stream of copies in the order the consumers need them (an x window right before the first chunk that reads it):
+        // the copy engine of an SM serves its queue in order, so a window requested behind queued operator chunks would arrive
+        // after the chunks that need it (measured with a separate window producer: the consumers then wait for windows).
         unsigned s = 0, ph = 0, xs = 0, xph = 0;
         const unsigned long long pol_first = policy_evict_first(), pol_last = policy_evict_last();
         for (int64_t i = blockIdx.x; i < ntiles; i += gridDim.x) {
@@ -232,6 +263,13 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
                     __syncwarp();
                     const cplx *src = (wd.start < op.nbcols_own) ? a.xin + (int64_t)wd.start * B * nv
                                                                   : hf.ghost_src + ((int64_t)wd.start - op.nbcols_own) * B * nv;
+                    if (VAR & VAR_XBULK) {
+                        if (lane == 0) {
+                            const unsigned bytes = (unsigned)wd.nblocks * (unsigned)(B * nv) * (unsigned)sizeof(cplx);
+                            if (op.flags & 2) tma_load_1d_hint(xring + (size_t)xs * xslot, src, bytes, xfull + xs, pol_last);
+                            else tma_load_1d(xring + (size_t)xs * xslot, src, bytes, xfull + xs);
+                        }
+                    } else
                     for (int b = lane; b < wd.nblocks; b += 32) {
                         if (op.flags & 2)
                             tma_load_1d_hint(xring + (size_t)xs * xslot + (size_t)b * xstride, src + (int64_t)b * B * nv,
@@ -244,11 +282,26 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
                     w++;
                 }
                 if (lane == 0) {
-                    mbar_wait(empty + s, ph ^ 1u);
-                    mbar_expect_tx(full + s, CHUNK);
-                    if (op.flags & 1) tma_load_1d_hint(ring + (size_t)s * CHUNK, op.chunks + (size_t)c * CHUNK, CHUNK, full + s, pol_first);
-                    else tma_load_1d(ring + (size_t)s * CHUNK, op.chunks + (size_t)c * CHUNK, CHUNK, full + s);
+                    const unsigned char *src = op.chunks + (size_t)c * CHUNK;
+                    unsigned char *dst = ring + (size_t)s * CHUNK;
+                    if (VAR & VAR_PIECE) {
+#pragma unroll 1
+                        for (int j = 0; j < B; j++) {
+                            // piece 0 = columns + header + block column 0, piece j = block column j
+                            const unsigned off = j ? HEAD + j * PIECE : 0u, bytes = j ? PIECE : HEAD + PIECE;
+                            mbar_wait(empty + s * NP + j, ph ^ 1u);
+                            mbar_expect_tx(full + s * NP + j, bytes);
+                            if (op.flags & 1) tma_load_1d_hint(dst + off, src + off, bytes, full + s * NP + j, pol_first);
+                            else tma_load_1d(dst + off, src + off, bytes, full + s * NP + j);
+                        }
+                    } else {
+                        mbar_wait(empty + s, ph ^ 1u);
+                        mbar_expect_tx(full + s, CHUNK);
+                        if (op.flags & 1) tma_load_1d_hint(dst, src, CHUNK, full + s, pol_first);
+                        else tma_load_1d(dst, src, CHUNK, full + s);
+                    }
                 }
+                if (VAR & VAR_PIECE) __syncwarp();
                 if (++s == (unsigned)nsa) { s = 0; ph ^= 1u; }
             }
         }
@@ -260,90 +313,179 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
     const int iv0 = (tid - tb * nvp) * CV;
     const bool lane_on = tb < TB;
     const int tbs = lane_on ? tb : 0;
-    const bool has_f = a.f != nullptr;
+    const bool has_f = a.f != nullptr && !(op.flags & 16);
+    const unsigned sw = (VAR & VAR_XBULK) ? (unsigned)(tbs & 1) : 0u;   // odd block rows read their second vector first
     unsigned s = 0, ph = 0, xs = 0, xph = 0;
 
+    auto tile_of = [&](int64_t i) -> int64_t { return op.tile_order ? (int64_t)op.tile_order[i] : i; };
+    // VAR_NEXT: tile bookkeeping (order, chunk count, halo flags) and the forcing rows are fetched one tile ahead of their use
+    int64_t t_n = 0;
+    int nchunk_n = 0;
+    unsigned char tflags_n = 0;
+    VecC<CV> fnext[B];
+    if ((VAR & VAR_NEXT) && (int64_t)blockIdx.x < ntiles) {
+        t_n = tile_of(blockIdx.x);
+        nchunk_n = (int)(op.tile_ptr[t_n + 1] - op.tile_ptr[t_n]);
+        if (hf.enabled) tflags_n = hf.tile_flags[t_n];
+        const int64_t brn = t_n * TB + tbs;
+        if (has_f && lane_on && brn < op.nbrows) {
+#pragma unroll
+            for (int r = 0; r < B; r++) fnext[r] = lds<CV>(a.f + brn * B * nv + iv0 + r * nv);
+        }
+    }
+
     for (int64_t i = blockIdx.x; i < ntiles; i += gridDim.x) {
-        const int64_t t = op.tile_order ? op.tile_order[i] : i;
-        const int nchunk = (int)(op.tile_ptr[t + 1] - op.tile_ptr[t]);
+        int64_t t;
+        int nchunk;
+        unsigned char tflags = 0;
+        const int64_t inext = i + gridDim.x;
+        if (VAR & VAR_NEXT) {
+            t = t_n;
+            nchunk = nchunk_n;
+            tflags = tflags_n;
+            if (inext < ntiles) {
+                t_n = tile_of(inext);
+                nchunk_n = (int)(op.tile_ptr[t_n + 1] - op.tile_ptr[t_n]);
+                if (hf.enabled) tflags_n = hf.tile_flags[t_n];
+            }
+        } else {
+            t = tile_of(i);
+            nchunk = (int)(op.tile_ptr[t + 1] - op.tile_ptr[t]);
+            if (hf.enabled) tflags = hf.tile_flags[t];
+        }
         const int64_t br = t * TB + tbs;
         const bool row_on = lane_on && br < op.nbrows;
         const int64_t u0 = br * B * nv + iv0;
 
-        unsigned char tflags = 0;
-        if (hf.enabled) {
-            tflags = hf.tile_flags[t];
-            if (tflags && hf.epoch > 1) {
-                // wait until every incoming peer has published epoch E-1 (their rows of the previous stage are in my mailbox,
-                // and they are done reading the slot this launch's senders overwrite)
-                if (lane == 0) {
-                    for (int q = 0; q < hf.n_in; q++) {
-                        long long spins = 0;
-                        while (ld_acquire_sys(hf.in_flag[q]) < hf.epoch - 1) {
-                            if (++spins > HALO_SPIN_LIMIT) { *hf.timeout_flag = 1ull; break; }
-                        }
+        if (hf.enabled && tflags && hf.epoch > 1) {
+            // wait until every incoming peer has published epoch E-1 (their rows of the previous stage are in my mailbox,
+            // and they are done reading the slot this launch's senders overwrite)
+            if (lane == 0) {
+                for (int q = 0; q < hf.n_in; q++) {
+                    long long spins = 0;
+                    while (ld_acquire_sys(hf.in_flag[q]) < hf.epoch - 1) {
+                        if (++spins > HALO_SPIN_LIMIT) { *hf.timeout_flag = 1ull; break; }
                     }
                 }
-                __syncwarp();
-                asm volatile("fence.acq_rel.sys;\n" ::: "memory");
             }
+            __syncwarp();
+            asm volatile("fence.acq_rel.sys;\n" ::: "memory");
         }
 
         VecC<CV> acc[B];
 #pragma unroll
         for (int r = 0; r < B; r++) {
 #pragma unroll
-            for (int i = 0; i < CV; i++) acc[r].v[i] = make_double2(0.0, 0.0);
-            if (has_f && row_on && !(op.flags & 16)) acc[r] = lds<CV>(a.f + u0 + r * nv);
+            for (int q = 0; q < CV; q++) acc[r].v[q] = make_double2(0.0, 0.0);
+            if (has_f && row_on) {
+                if (VAR & VAR_NEXT) acc[r] = fnext[r];
+                else acc[r] = lds<CV>(a.f + u0 + r * nv);
+            }
         }
 
         for (int c = 0; c < nchunk; c++) {
-            mbar_wait(full + s, ph);
+            mbar_wait(full + s * NP, ph);
+            unsigned long long *ful = full + s * NP;    // (pieces 1.. are awaited right before their use)
             const unsigned char *chunk = ring + (size_t)s * CHUNK;
-            const int32_t *cols = reinterpret_cast<const int32_t *>(chunk + (size_t)BB * TB * sizeof(cplx));
+            const int32_t *cols = reinterpret_cast<const int32_t *>(chunk);
             const int xoff = nsx ? cols[TB] : TBCSR_GATHER, cflags = cols[TB + 1];   // (no x ring: every chunk gathers)
             const int col = (row_on && !(op.flags & 8)) ? cols[tbs] : -1;   // (flag 8: measurement of the memory pipeline alone)
-            const cplx *av = reinterpret_cast<const cplx *>(chunk) + tbs;
+            const cplx *av = reinterpret_cast<const cplx *>(chunk + HEAD) + tbs;
+            const unsigned avs = smem_u32(chunk) + HEAD + (unsigned)tbs * 16u;      // entry e of my block: avs + e * TB * 16
+            unsigned long long *rel = empty + s * NP;
+            const bool on = col >= 0;
             if (xoff != TBCSR_GATHER) {
                 if (cflags & 1) mbar_wait(xfull + xs, xph);
-                if (col >= 0) {
-                    const unsigned char *xw = xring + (size_t)xs * xslot + (size_t)(xoff + tbs) * xstride + (size_t)iv0 * sizeof(cplx);
+                const unsigned char *xw = xring + (size_t)xs * xslot + (size_t)(xoff + tbs) * xstride + (size_t)iv0 * sizeof(cplx);
+                if (VAR & VAR_LDS) {
+                    // ordered shared-memory loads, one block column ahead of the FMAs
+                    const unsigned xws = smem_u32(xw);
+                    cplx e[2][B], xv[2][CV];
+                    if (on) {
+#pragma unroll
+                        for (int r = 0; r < B; r++) e[0][r] = lds_c(avs + (unsigned)(r * TB) * 16u);
+#pragma unroll
+                        for (int q = 0; q < CV; q++) xv[0][q] = lds_c(xws + ((unsigned)q ^ sw) * 16u);
+                    }
 #pragma unroll
                     for (int j = 0; j < B; j++) {
-                        const cplx *xp = reinterpret_cast<const cplx *>(xw + (size_t)j * nv * sizeof(cplx));
-                        cplx xv[CV];
+                        if ((VAR & VAR_PIECE) && j + 1 < B) mbar_wait(ful + j + 1, ph);
+                        if (on) {
+                            if (j + 1 < B) {
 #pragma unroll
-                        for (int i = 0; i < CV; i++) xv[i] = xp[i];
+                                for (int r = 0; r < B; r++) e[(j + 1) & 1][r] = lds_c(avs + (unsigned)(((j + 1) * B + r) * TB) * 16u);
+#pragma unroll
+                                for (int q = 0; q < CV; q++) xv[(j + 1) & 1][q] = lds_c(xws + ((unsigned)((j + 1) * nv + q) ^ sw) * 16u);
+                            }
+                            cplx xq[CV];
+#pragma unroll
+                            for (int q = 0; q < CV; q++) xq[q] = xv[j & 1][q];
+                            if ((VAR & VAR_XBULK) && CV == 2 && sw) { const cplx t0 = xq[0]; xq[0] = xq[CV - 1]; xq[CV - 1] = t0; }
+#pragma unroll
+                            for (int r = 0; r < B; r++) {
+#pragma unroll
+                                for (int q = 0; q < CV; q++) cfma(acc[r].v[q], e[j & 1][r], xq[q]);
+                            }
+                        }
+                        if (VAR & VAR_PIECE) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(rel + j);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < B; j++) {
+                        if ((VAR & VAR_PIECE) && j > 0) mbar_wait(ful + j, ph);
+                        if (on) {
+                            const cplx *xp = reinterpret_cast<const cplx *>(xw + (size_t)j * nv * sizeof(cplx));
+                            cplx xv[CV];
+#pragma unroll
+                            for (int q = 0; q < CV; q++) xv[q] = xp[(unsigned)q ^ sw];
+                            if ((VAR & VAR_XBULK) && CV == 2 && sw) { const cplx t0 = xv[0]; xv[0] = xv[CV - 1]; xv[CV - 1] = t0; }
+#pragma unroll
+                            for (int r = 0; r < B; r++) {
+                                const cplx e = av[(j * B + r) * TB];
+#pragma unroll
+                                for (int q = 0; q < CV; q++) cfma(acc[r].v[q], e, xv[q]);
+                            }
+                        }
+                        if (VAR & VAR_PIECE) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(rel + j);
+                        }
+                    }
+                }
+            } else {
+                VecC<CV> xr[B];
+                if (on) {
+                    const cplx *xp = (col < op.nbcols_own) ? a.xin + (int64_t)col * B * nv + iv0
+                                                           : hf.ghost_src + ((int64_t)col - op.nbcols_own) * B * nv + iv0;
+#pragma unroll
+                    for (int j = 0; j < B; j++) xr[j] = ldx<CV>(xp + j * nv);
+                }
+#pragma unroll
+                for (int j = 0; j < B; j++) {
+                    if ((VAR & VAR_PIECE) && j > 0) mbar_wait(ful + j, ph);
+                    if (on) {
 #pragma unroll
                         for (int r = 0; r < B; r++) {
                             const cplx e = av[(j * B + r) * TB];
 #pragma unroll
-                            for (int i = 0; i < CV; i++) cfma(acc[r].v[i], e, xv[i]);
+                            for (int q = 0; q < CV; q++) cfma(acc[r].v[q], e, xr[j].v[q]);
                         }
                     }
-                }
-            } else if (col >= 0) {
-                const cplx *xp = (col < op.nbcols_own) ? a.xin + (int64_t)col * B * nv + iv0
-                                                       : hf.ghost_src + ((int64_t)col - op.nbcols_own) * B * nv + iv0;
-                VecC<CV> xr[B];
-#pragma unroll
-                for (int j = 0; j < B; j++) xr[j] = ldx<CV>(xp + j * nv);
-#pragma unroll
-                for (int j = 0; j < B; j++) {
-#pragma unroll
-                    for (int r = 0; r < B; r++) {
-                        const cplx e = av[(j * B + r) * TB];
-#pragma unroll
-                        for (int i = 0; i < CV; i++) cfma(acc[r].v[i], e, xr[j].v[i]);
+                    if (VAR & VAR_PIECE) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(rel + j);
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(empty + s);
-                if (xoff != TBCSR_GATHER && (cflags & 2)) mbar_arrive(xempty + xs);
+            if (!(VAR & VAR_PIECE)) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + s);
             }
             if (xoff != TBCSR_GATHER && (cflags & 2)) {
+                if (lane == 0) mbar_arrive(xempty + xs);   // (after a __syncwarp: the whole warp is done with the window)
                 if (++xs == (unsigned)nsx) { xs = 0; xph ^= 1u; }
             }
             if (++s == (unsigned)nsa) { s = 0; ph ^= 1u; }
@@ -357,24 +499,36 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
             dest[1] = hf.send_dest[(si * 2 + 1) * TB + tbs];
         }
         if (row_on && !(op.flags & 16)) {
+            VecC<CV> yv[B], av2[B];
+            if (VAR & VAR_EPI) {
+                // all loads of the tile's block vectors first (one exposed latency instead of B), then the arithmetic and the stores
+                if (mode != 2) {
+#pragma unroll
+                    for (int r = 0; r < B; r++) yv[r] = lds<CV>(a.ybase + u0 + r * nv);
+                }
+                if (mode != 0) {
+#pragma unroll
+                    for (int r = 0; r < B; r++) av2[r] = lds<CV>(a.acc_in + u0 + r * nv);
+                }
+            }
 #pragma unroll
             for (int r = 0; r < B; r++) {
                 const int64_t u = u0 + r * nv;
+                if (!(VAR & VAR_EPI)) {
+                    if (mode != 2) yv[r] = lds<CV>(a.ybase + u);
+                    if (mode != 0) av2[r] = lds<CV>(a.acc_in + u);
+                }
                 VecC<CV> o;   // the vector the next stage gathers (xout, or y_{n+1} in the last stage)
                 if (mode == 0) {
-                    const VecC<CV> y = lds<CV>(a.ybase + u);
-                    o = axpyv<CV>(a.cx, acc[r], y);
+                    o = axpyv<CV>(a.cx, acc[r], yv[r]);
                     stv<CV>(a.xout + u, o);
-                    stv<CV>(a.acc_out + u, axpyv<CV>(a.ca, acc[r], y));
+                    stv<CV>(a.acc_out + u, axpyv<CV>(a.ca, acc[r], yv[r]));
                 } else if (mode == 1) {
-                    const VecC<CV> y = lds<CV>(a.ybase + u);
-                    const VecC<CV> ac = lds<CV>(a.acc_in + u);
-                    o = axpyv<CV>(a.cx, acc[r], y);
+                    o = axpyv<CV>(a.cx, acc[r], yv[r]);
                     stv<CV>(a.xout + u, o);
-                    stv<CV>(a.acc_out + u, axpyv<CV>(a.ca, acc[r], ac));
+                    stv<CV>(a.acc_out + u, axpyv<CV>(a.ca, acc[r], av2[r]));
                 } else {
-                    const VecC<CV> ac = lds<CV>(a.acc_in + u);
-                    o = axpyv<CV>(a.ca, acc[r], ac);
+                    o = axpyv<CV>(a.ca, acc[r], av2[r]);
                     stv<CV>(a.acc_out + u, o);
                     if (a.snap) stv<CV>(a.snap + u, o);
                 }
@@ -385,6 +539,14 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
                         const int64_t grow = dest[d] & 0xFFFFFFFFFFFFll;   // first ghost row (on the peer) of this block row
                         stv<CV>(hf.out_mail[slot] + (grow + r) * nv + iv0, o);
                     }
+            }
+        }
+        if ((VAR & VAR_NEXT) && has_f && inext < ntiles) {
+            // the forcing rows of the next tile: in flight while this tile's sends are counted and the next chunk is awaited
+            const int64_t brn = t_n * TB + tbs;
+            if (lane_on && brn < op.nbrows) {
+#pragma unroll
+                for (int r = 0; r < B; r++) fnext[r] = lds<CV>(a.f + brn * B * nv + iv0 + r * nv);
             }
         }
         if (hf.enabled && (tflags & 2)) {
@@ -406,9 +568,12 @@ rk4_stage_tbcsr_kernel(const TbcsrDev op, const int nv, const int nvp, const int
     }
 }
 
+// variants built for the B = 5, k = 8 shape (the 3-D LNS configuration of BASELINE.json); every other shape runs variant 0
+#define TBCSR_VARIANTS(X) X(1) X(4) X(8) X(16) X(17) X(32) X(33) X(37) X(40) X(41) X(44) X(45) X(49) X(53) X(57) X(61)
+
 template <int B, int NCW, int CV>
 cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm, int nsa_req,
-                     cudaStream_t s)
+                     int variant, cudaStream_t s)
 {
     static int n_sm = 0;
     static size_t smem_max = 0;
@@ -420,14 +585,17 @@ cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, c
         cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         smem_max = (size_t)v;
     }
+    constexpr bool has_variants = B == 5 && NCW == 4 && CV == 2;
+    if (!has_variants) variant = 0;
     if (ctas_per_sm < 1 || ctas_per_sm > 3) ctas_per_sm = 2;
+    if ((variant & VAR_SMR) && ctas_per_sm != 2) variant &= ~VAR_SMR;
     const size_t chunk = tbcsr_chunk_bytes(B, TBCSR_TB);
     if (chunk != Op.chunk_bytes) return cudaErrorInvalidValue;
-    // shared memory per SM: 228 KB, 1 KB reserved per CTA
-    const size_t budget = std::min(smem_max, (size_t)(228 * 1024) / ctas_per_sm - 1024) - 256;
-    const size_t xslot = ((size_t)B * nv * sizeof(cplx) + 16) * (size_t)Op.wmax;
+    // shared memory per SM: 228 KB, 1 KB reserved per CTA; the last KB of the CTA's share: mbarriers
+    const size_t budget = std::min(smem_max, (size_t)(228 * 1024) / ctas_per_sm - 1024) - 1024;
+    const size_t xslot = ((size_t)B * nv * sizeof(cplx) + ((variant & VAR_XBULK) ? 0 : 16)) * (size_t)Op.wmax;
     int nsx = 0, nsa = 0;
-    if (Op.win_ptr && Op.wmax > 0 && 2 * xslot + 2 * chunk > budget && ctas_per_sm == 3) return launch_t<B, NCW, CV>(Op, nv, mode, a, hf, 2, nsa_req, s);
+    if (Op.win_ptr && Op.wmax > 0 && 2 * xslot + 2 * chunk > budget && ctas_per_sm == 3) return launch_t<B, NCW, CV>(Op, nv, mode, a, hf, 2, nsa_req, variant, s);
     if (Op.win_ptr && Op.wmax > 0 && 2 * xslot + 2 * chunk <= budget) nsx = 2;
     TbcsrDev op = Op;
     if (!nsx) { op.win_ptr = nullptr; op.win = nullptr; }   // the x windows do not fit next to the operator ring: gather mode
@@ -435,55 +603,65 @@ cudaError_t launch_t(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, c
     if (nsa > 12) nsa = 12;
     if (nsa_req >= 2 && nsa_req < nsa) nsa = nsa_req;
     if (nsa < 2) return cudaErrorInvalidValue;
-    const size_t smem = 128 * ((2 * (size_t)(nsa + nsx) * 8 + 127) / 128) + (size_t)nsa * chunk + (size_t)nsx * xslot;
-    const int threads = (NCW + 1) * 32;
+    const int np = (variant & VAR_PIECE) ? B : 1;
+    const size_t smem = 128 * (((size_t)(2 * nsa * np + 2 * nsx) * 8 + 127) / 128) + (size_t)nsa * chunk + (size_t)nsx * xslot;
+    const int threads = (variant & VAR_SMR) ? 256 : (NCW + 1) * 32;
     const unsigned grid = (unsigned)std::min<int64_t>(Op.ntiles, (int64_t)n_sm * ctas_per_sm);
     if (grid == 0) return cudaSuccess;
     const int nvp = nv / CV;
     cudaError_t e;
-#define GO(MINB)                                                                                                              \
+#define GO(MINB, VAR)                                                                                                         \
     do {                                                                                                                      \
-        e = cudaFuncSetAttribute(rk4_stage_tbcsr_kernel<B, NCW, MINB, CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        e = cudaFuncSetAttribute(rk4_stage_tbcsr_kernel<B, NCW, MINB, CV, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                                                       \
-        rk4_stage_tbcsr_kernel<B, NCW, MINB, CV><<<grid, threads, smem, s>>>(op, nv, nvp, mode, nsa, nsx, Op.wmax, a, hf);      \
+        rk4_stage_tbcsr_kernel<B, NCW, MINB, CV, VAR><<<grid, threads, smem, s>>>(op, nv, nvp, mode, nsa, nsx, Op.wmax, a, hf);  \
     } while (0)
-    if (ctas_per_sm <= 2) GO(2);   // (1 CTA/SM runs the 2-CTA build: same registers, deeper ring)
-    else GO(3);
+    if (has_variants && variant != 0 && ctas_per_sm <= 2) {
+        switch (variant) {
+#define CASE(V) case V: GO(2, (has_variants ? V : 0)); break;
+            TBCSR_VARIANTS(CASE)
+#undef CASE
+            default: return cudaErrorInvalidValue;
+        }
+    } else if (ctas_per_sm <= 2) GO(2, 0);   // (1 CTA/SM runs the 2-CTA build: same registers, deeper ring)
+    else GO(3, 0);
 #undef GO
     return cudaGetLastError();
 }
 
+#ifndef TBCSR_DEV_ONE
 template <int B>
-cudaError_t launch_b(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int cps, int nsa, int cv, cudaStream_t s)
+cudaError_t launch_b(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int cps, int nsa, int cv, int var, cudaStream_t s)
 {
     // consumer warps: TB block rows x (nv / CV) threads each.  CV = 1 doubles the warps per CTA at twice the shared-memory reads
     // per FMA (measured slower: 1.67 vs 1.58 ms on the 3-D operator); it serves odd vector counts and is there on request.
     if (cv == 1 || nv % 2) {
         switch (nv) {
-            case 1: return launch_t<B, 1, 1>(Op, nv, mode, a, hf, cps, nsa, s);
-            case 2: return launch_t<B, 2, 1>(Op, nv, mode, a, hf, cps, nsa, s);
-            case 3: return launch_t<B, 3, 1>(Op, nv, mode, a, hf, cps, nsa, s);
-            case 4: return launch_t<B, 4, 1>(Op, nv, mode, a, hf, cps, nsa, s);
-            case 5: return launch_t<B, 5, 1>(Op, nv, mode, a, hf, cps, nsa, s);
-            case 6: return launch_t<B, 6, 1>(Op, nv, mode, a, hf, cps, nsa, s);
-            case 7: return launch_t<B, 7, 1>(Op, nv, mode, a, hf, cps, nsa, s);
-            case 8: return launch_t<B, 8, 1>(Op, nv, mode, a, hf, cps, nsa, s);
+            case 1: return launch_t<B, 1, 1>(Op, nv, mode, a, hf, cps, nsa, var, s);
+            case 2: return launch_t<B, 2, 1>(Op, nv, mode, a, hf, cps, nsa, var, s);
+            case 3: return launch_t<B, 3, 1>(Op, nv, mode, a, hf, cps, nsa, var, s);
+            case 4: return launch_t<B, 4, 1>(Op, nv, mode, a, hf, cps, nsa, var, s);
+            case 5: return launch_t<B, 5, 1>(Op, nv, mode, a, hf, cps, nsa, var, s);
+            case 6: return launch_t<B, 6, 1>(Op, nv, mode, a, hf, cps, nsa, var, s);
+            case 7: return launch_t<B, 7, 1>(Op, nv, mode, a, hf, cps, nsa, var, s);
+            case 8: return launch_t<B, 8, 1>(Op, nv, mode, a, hf, cps, nsa, var, s);
             default: break;
         }
         if (nv % 2) return cudaErrorInvalidValue;
     }
     switch (nv / 2) {
-        case 1: return launch_t<B, 1, 2>(Op, nv, mode, a, hf, cps, nsa, s);
-        case 2: return launch_t<B, 2, 2>(Op, nv, mode, a, hf, cps, nsa, s);
-        case 3: return launch_t<B, 3, 2>(Op, nv, mode, a, hf, cps, nsa, s);
-        case 4: return launch_t<B, 4, 2>(Op, nv, mode, a, hf, cps, nsa, s);
-        case 5: return launch_t<B, 5, 2>(Op, nv, mode, a, hf, cps, nsa, s);
-        case 6: return launch_t<B, 6, 2>(Op, nv, mode, a, hf, cps, nsa, s);
-        case 7: return launch_t<B, 7, 2>(Op, nv, mode, a, hf, cps, nsa, s);
-        case 8: return launch_t<B, 8, 2>(Op, nv, mode, a, hf, cps, nsa, s);
+        case 1: return launch_t<B, 1, 2>(Op, nv, mode, a, hf, cps, nsa, var, s);
+        case 2: return launch_t<B, 2, 2>(Op, nv, mode, a, hf, cps, nsa, var, s);
+        case 3: return launch_t<B, 3, 2>(Op, nv, mode, a, hf, cps, nsa, var, s);
+        case 4: return launch_t<B, 4, 2>(Op, nv, mode, a, hf, cps, nsa, var, s);
+        case 5: return launch_t<B, 5, 2>(Op, nv, mode, a, hf, cps, nsa, var, s);
+        case 6: return launch_t<B, 6, 2>(Op, nv, mode, a, hf, cps, nsa, var, s);
+        case 7: return launch_t<B, 7, 2>(Op, nv, mode, a, hf, cps, nsa, var, s);
+        case 8: return launch_t<B, 8, 2>(Op, nv, mode, a, hf, cps, nsa, var, s);
         default: return cudaErrorInvalidValue;
     }
 }
+#endif
 
 }  // namespace
 
@@ -494,15 +672,19 @@ bool tbcsr_stage_supported(int B, int nv)
 }
 
 cudaError_t launch_rk4_stage_tbcsr(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm,
-                                   int ring_stages, int vectors_per_thread, cudaStream_t s)
+                                   int ring_stages, int vectors_per_thread, int variant, cudaStream_t s)
 {
     if (!tbcsr_stage_supported(Op.B, nv)) return cudaErrorInvalidValue;
+#ifdef TBCSR_DEV_ONE   // development aid: build the B = 5, k = 8 instances alone (ptxas -v / SASS in seconds)
+    return launch_t<5, 4, 2>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, variant, s);
+#else
     switch (Op.B) {
-        case 3: return launch_b<3>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, vectors_per_thread, s);
-        case 4: return launch_b<4>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, vectors_per_thread, s);
-        case 5: return launch_b<5>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, vectors_per_thread, s);
+        case 3: return launch_b<3>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, vectors_per_thread, variant, s);
+        case 4: return launch_b<4>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, vectors_per_thread, variant, s);
+        case 5: return launch_b<5>(Op, nv, mode, a, hf, ctas_per_sm, ring_stages, vectors_per_thread, variant, s);
         default: return cudaErrorInvalidValue;
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -4,9 +4,10 @@
 // Tiled block-CSR ("TBCSR"): the block rows are cut into tiles of TB consecutive block rows.  Tile t owns the chunks
 // [tile_ptr[t], tile_ptr[t+1]); chunk p of a tile holds the p-th block of every block row of the tile (block rows with
 // fewer blocks are padded, column -1), laid out for one bulk copy and conflict-free shared-memory reads:
-//     cplx  val[B*B][TB]      entry e = j*B + r of the block (column-major inside the block), block row tb fastest
 //     int32 col[TB]           block column of that block, or -1 (padding: skipped, no arithmetic)
 //     int32 hdr[4]            {xoff, flags, 0, 0}: where the chunk's rows of the stage vector sit in the x window (below)
+//     cplx  val[B*B][TB]      entry e = j*B + r of the block (column-major inside the block), block row tb fastest
+// (columns and header first: they ride with block column 0 when the kernel brings a chunk in piece by piece)
 // chunk_bytes = B*B*TB*16 + TB*4 + 16.  Per nonzero this is 16 B + ~4/(B*B) B -- the floor of a complex-double block format.
 // When the blocks of a tile line up on block diagonals (col - block row constant along a chunk: stencils), the chunks are
 // cut by diagonal instead of by position in the row (missing neighbours padded in place), and runs of neighbouring
@@ -43,6 +44,8 @@ struct TbcsrDev {
                                               // tile's block vectors; measurement only: 8 no FMAs, 16 no block-vector loads / stores
 };
 __host__ __device__ inline size_t tbcsr_chunk_bytes(int B, int TB) { return (size_t)B * B * TB * sizeof(cplx) + (size_t)TB * sizeof(int32_t) + 16; }
+__host__ __device__ inline size_t tbcsr_cols_offset() { return 0; }                                             // col[TB], then hdr[4]
+__host__ __device__ inline size_t tbcsr_vals_offset(int TB) { return (size_t)TB * sizeof(int32_t) + 16; }      // val[B*B][TB]
 
 // The halo exchange done by the stage kernel itself (row-partitioned runs, layout 0).
 //   Every fused stage has an epoch E (1, 2, ...).  Tiles whose rows a peer needs store them, next to the local store,
@@ -72,9 +75,10 @@ struct HaloFuse {
 bool tbcsr_stage_supported(int B, int nv);
 // mode / StageArgs as for the other stage kernels (kernels.cuh)
 // ring_stages: 0 = as many operator chunks as shared memory holds (up to 12), else at most that many;
-// vectors_per_thread: 0 = automatic, 1 or 2 test vectors per consumer thread
+// vectors_per_thread: 0 = automatic, 1 or 2 test vectors per consumer thread;
+// variant: compile-time variant bits of the kernel (stage_tiled.cu, VAR_*), honoured for the B = 5, k = 8 shape
 cudaError_t launch_rk4_stage_tbcsr(const TbcsrDev &Op, int nv, int mode, const StageArgs &a, const HaloFuse &hf, int ctas_per_sm,
-                                   int ring_stages, int vectors_per_thread, cudaStream_t s);
+                                   int ring_stages, int vectors_per_thread, int variant, cudaStream_t s);
 
 // Host-side plan of the x windows from the chunk columns (cols: [nchunks][TB] as stored): fills hdr ([nchunks][4]) and the
 // window lists.  nb_own: block columns below it are rows of the stage vector, the others ghost rows (separate source).

@@ -82,8 +82,8 @@ __global__ void stencil_fill_kernel(Geo g, StencilSpec sp, int TB, int64_t ntile
         if (!(mask & (1u << b))) continue;
         unsigned char *base = chunks + (size_t)(tile_ptr[t] + p) * cb;
         p++;
-        cplx *cv = reinterpret_cast<cplx *>(base);
-        int32_t *cc = reinterpret_cast<int32_t *>(base + (size_t)B * B * TB * sizeof(cplx));
+        cplx *cv = reinterpret_cast<cplx *>(base + tbcsr_vals_offset(TB));
+        int32_t *cc = reinterpret_cast<int32_t *>(base + tbcsr_cols_offset());
         if (i >= n || bidx[i] != b) {
             cc[tb] = -1;
             for (int e = 0; e < B * B; e++) cv[(size_t)e * TB + tb] = make_double2(0.0, 0.0);
