@@ -78,7 +78,11 @@ int rsvdt_setup_time_freq_grid(double w, int64_t Nw, double dt_in, double Transi
 int rsvdt_set_operator_csr(rsvdt_handle h, int64_t N, const int64_t *rowptr, const int64_t *col,
                            const double *val_re_im, int disc_flg, double beta, int *real_operator);
 
-/* CreateDFTiDFTMats.c:5-96 + Variables.h: fixes k, Nw, Ns, ... ; twiddles are generated on the device. */
+/* CreateDFTiDFTMats.c:5-96 + Variables.h: fixes k, Nw, Ns, ... ; twiddles are generated on the device.
+ * LIMIT (not in the reference): k <= RSVDT_MAX_K -- the per-frequency k x k factorisations (Cholesky, Jacobi) keep a k x k
+ * matrix per warp in shared memory; a larger k returns RSVDT_ERR_ARG here.  The host drivers check k (from variables.yaml
+ * or from the column count of the forcing file) before they load the operator. */
+#define RSVDT_MAX_K 32
 int rsvdt_set_grid(rsvdt_handle h, const rsvdt_grid *g);
 
 /* ReadWeightMats.c:26-99 : optional sparse B (N x Nb), C (Nc x N), W_f_sqrt_inv (Nb x Nb), W_q_sqrt (Nc x Nc),

@@ -293,6 +293,35 @@ int upload_csr(rsvdt_handle h, CsrOwned &dst, int64_t nrows, int64_t ncols, cons
                const cplx *val, bool hermitian_transpose, double shift)
 {
     dst.release();
+    if (shift != 0.0) {
+        // MatShift(A, -beta) (LNSStructure.c:53-56) inserts diagonal entries the matrix does not store: rows without one get a
+        // zero entry at its sorted place first (local layouts: the diagonal of owned row r is column r as well)
+        int64_t missing = 0;
+        for (int64_t r = 0; r < nrows && r < ncols; r++) {
+            bool has = false;
+            for (int64_t p = rowptr[r]; p < rowptr[r + 1] && !has; p++) has = col[p] == r;
+            missing += has ? 0 : 1;
+        }
+        if (missing) {
+            std::vector<int64_t> rp2((size_t)nrows + 1, 0), ci2;
+            std::vector<cplx> va2;
+            ci2.reserve((size_t)(rowptr[nrows] + missing));
+            va2.reserve((size_t)(rowptr[nrows] + missing));
+            for (int64_t r = 0; r < nrows; r++) {
+                bool has = r >= ncols;
+                for (int64_t p = rowptr[r]; p < rowptr[r + 1]; p++) has = has || col[p] == r;
+                bool put = has;
+                for (int64_t p = rowptr[r]; p < rowptr[r + 1]; p++) {
+                    if (!put && col[p] > r) { ci2.push_back(r); va2.push_back(make_double2(0.0, 0.0)); put = true; }
+                    ci2.push_back(col[p]);
+                    va2.push_back(val[p]);
+                }
+                if (!put) { ci2.push_back(r); va2.push_back(make_double2(0.0, 0.0)); }
+                rp2[(size_t)r + 1] = (int64_t)ci2.size();
+            }
+            return upload_csr(h, dst, nrows, ncols, rp2.data(), ci2.data(), va2.data(), hermitian_transpose, shift);
+        }
+    }
     const int64_t nnz = rowptr[nrows];
     if (ncols > (int64_t)INT32_MAX) return fail(h, RSVDT_ERR_ARG, "more than 2^31-1 columns not supported");
     std::vector<int64_t> rp;
@@ -1795,7 +1824,7 @@ int rsvdt_set_grid(rsvdt_handle h, const rsvdt_grid *g)
     if (!g) return fail(h, RSVDT_ERR_ARG, "null grid");
     if (g->k <= 0 || g->Nw <= 0 || g->Nw_eff <= 0 || g->Ns <= 0 || g->Nt < 0 || g->ResRatio <= 0 || !(g->dt > 0))
         return fail(h, RSVDT_ERR_ARG, "grid parameters out of range");
-    if (g->k > 32) return fail(h, RSVDT_ERR_ARG, "k > 32 is not supported by the per-frequency QR/SVD kernels");
+    if (g->k > RSVDT_MAX_K) return fail(h, RSVDT_ERR_ARG, "k > %d is not supported by the per-frequency QR/SVD kernels", RSVDT_MAX_K);
     if (g->Nw_eff != (g->RealOperator ? g->Nw / 2 : g->Nw)) return fail(h, RSVDT_ERR_ARG, "Nw_eff inconsistent with RealOperator (LNSStructure.c:44)");
     h->g = *g;
     h->grid_set = true;

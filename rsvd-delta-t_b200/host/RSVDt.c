@@ -115,8 +115,10 @@ static int options_insert_file_yaml(const char *file)
     if (!f) return seterr(ERR_USER, "Unable to open YAML options file %s", file);
     char line[2 * MAX_PATH_LEN];
     while (fgets(line, sizeof line, f)) {
-        char *hash = strchr(line, '#'); /* comment (the reference's files never contain '#' inside values) */
-        if (hash) *hash = 0;
+        /* a comment starts at a '#' that opens the line or follows white space (the same rule as rsvdt_mpi.py: a '#' inside a
+           value, e.g. a directory name, is kept) */
+        for (char *c = line; *c; c++)
+            if (*c == '#' && (c == line || isspace((unsigned char)c[-1]))) { *c = 0; break; }
         char *colon = strchr(line, ':');
         if (!colon) continue;
         *colon = 0;
@@ -178,7 +180,8 @@ static int opt_bool(const char *key, int *v, int *set)
 {
     const char *s = opt_find(key);
     *set = 0;
-    if (!s || !s[0]) return 0;
+    if (!s) return 0;
+    if (!s[0]) { *v = 1; *set = 1; return 0; }   /* `Flag:` without a value is true, PETSc's rule (PetscOptionsGetBool) */
     if (!strcasecmp(s, "true") || !strcmp(s, "1") || !strcasecmp(s, "yes") || !strcasecmp(s, "on")) *v = 1;
     else if (!strcasecmp(s, "false") || !strcmp(s, "0") || !strcasecmp(s, "no") || !strcasecmp(s, "off")) *v = 0;
     else return seterr(ERR_USER, "Unknown logical value '%s' for '%s'", s, key);
@@ -251,6 +254,8 @@ static int ReadUserInput(int argc, char **argv, RSVDt_vars *RSVDt, Weight_matric
     if (!set) return seterr(ERR_USER, "Must specify 'OperatorDir'");
     CHK(opt_int("k", &RSVDt->RSVD.k, &set));
     if (!set) { RSVDt->RSVD.k = 3; printf("Warning: 'k' variable not found. Setting 'k' to default value: %d\n", 3); }
+    if (RSVDt->RSVD.k > RSVDT_MAX_K)   /* (not in the reference: a limit of this build, include/rsvdt.h; said before anything is loaded) */
+        return seterr(ERR_USER, "'k' = %d: this build supports at most %d test vectors", RSVDt->RSVD.k, RSVDT_MAX_K);
     CHK(opt_int("q", &RSVDt->RSVD.q, &set));
     if (!set) { RSVDt->RSVD.q = 0; printf("Warning: 'q' variable not found. Setting 'q' to default value: %d\n", 0); }
     CHK(opt_int("Nw", &RSVDt->RSVD.Nw, &set));
@@ -403,6 +408,7 @@ static int CreateRandomMat(RSVDt_vars *RSVDt, Directories *dirs)
         if (pb_read_mat_dense(dirs->IO_dir, &row, &col, &Y)) return seterr(ERR_USER, "%s", pb_error());
         if (row != Nb) { free(Y); return seterr(ERR_USER, "Input forcing must be have %d rows, current size = %d x %d", (int)Nb, (int)row, (int)col); }
         RSVDt->RSVD.k = col / RSVDt->RSVD.Nw_eff;                                                            /* :30 */
+        if (RSVDt->RSVD.k > RSVDT_MAX_K) { free(Y); return seterr(ERR_USER, "the input forcing holds k = %d test vectors: this build supports at most %d", RSVDt->RSVD.k, RSVDT_MAX_K); }
         printf("Based on the input forcing: k = %d\n", (int)RSVDt->RSVD.k);
         if (RSVDt->RSVD.k * RSVDt->RSVD.Nw_eff != col) { free(Y); return seterr(ERR_USER, "Input forcing columns (%d) must be a multiple of Nw_eff (%d)", (int)col, (int)RSVDt->RSVD.Nw_eff); }
     } else {

@@ -39,6 +39,7 @@ class UserError(Exception):
 
 
 ERR_USER = 83
+MAX_K = 32          # include/rsvdt.h RSVDT_MAX_K
 
 
 # ---------------------------------------------------------------------------------------------------- options database
@@ -154,6 +155,8 @@ def read_user_input(argv, log):
     v["ResultsDir"] = need(o.string, "ResultsDir")
     v["OperatorDir"] = need(o.string, "OperatorDir")
     v["k"] = o.default(o.int, "k", 3)
+    if v["k"] > MAX_K:     # (not in the reference: a limit of this build, include/rsvdt.h RSVDT_MAX_K; said before anything is loaded)
+        raise UserError(f"'k' = {v['k']}: this build supports at most {MAX_K} test vectors")
     v["q"] = o.default(o.int, "q", 0)
     v["Nw"] = need(o.int, "Nw")
     v["RandSeed"] = o.default(o.int, "RandSeed", 1373)
@@ -269,6 +272,8 @@ class Run:
             except (OSError, ValueError) as e:
                 raise UserError(f"cannot read the input forcing {v['RootDir'] + v['InputForcingDir']}: {e}")
             v["k"] = max(fr.N // (v["Nw"] // 2 if real else v["Nw"]), 1)
+            if v["k"] > MAX_K:
+                raise UserError(f"the input forcing holds k = {v['k']} test vectors: this build supports at most {MAX_K}")
         max_bw = max(lo, hi, 1)
         min_rows = N // self.world
         layout = 1 if (max_bw <= 8 and 8 * max_bw < min_rows) else 0

@@ -148,6 +148,30 @@ def test_discounting(pkg, O, A_GL):
     r.close()
 
 
+def test_discounting_inserts_missing_diagonal_entries(pkg, O, A_GL):
+    # MatShift(A, -beta) (LNSStructure.c:53-56) creates diagonal entries the file does not store: rows 7, 8 and 499 lose theirs here
+    keep = np.ones(A_GL.val.size, dtype=bool)
+    for r in (7, 8, 499):
+        for p in range(A_GL.rowptr[r], A_GL.rowptr[r + 1]):
+            if A_GL.col[p] == r:
+                keep[p] = False
+    rowptr = np.concatenate([[0], np.cumsum(np.add.reduceat(keep.astype(np.int64), A_GL.rowptr[:-1]))]).astype(np.int64)
+    A0 = O.Csr(500, 500, rowptr, A_GL.col[keep].copy(), A_GL.val[keep].copy())
+    dense = np.zeros((500, 500), dtype=np.complex128)
+    for r in range(500):
+        dense[r, A0.col[A0.rowptr[r]:A0.rowptr[r + 1]]] = A0.val[A0.rowptr[r]:A0.rowptr[r + 1]]
+    dense -= 0.25 * np.eye(500)
+    rr, cc = np.nonzero(dense)
+    rp = np.concatenate([[0], np.cumsum(np.bincount(rr, minlength=500))]).astype(np.int64)
+    shifted = O.Csr(500, 500, rp, cc.astype(np.int64), dense[rr, cc])
+    v = make_vars(O, pkg, 500, 2, 4, 1.0, 0.003, 1.0)
+    F = _forcing(500, 8, 5)
+    r = _handle(pkg, A0, v, DiscFlg=True, beta=0.25)
+    for direct in (True, False):
+        assert rel_err(r.TSActionRK4(F, direct=direct), _oracle_action(O, shifted, v, F, direct)) < ACTION_TOL
+    r.close()
+
+
 @pytest.mark.parametrize("k,opts", [(10, {}), (8, {}), (3, {}), (16, {}), (20, {}), (10, dict(qr_fused=0)),
                                     (10, dict(qr_fused=0, gram_variant=0)), (8, dict(gram_variant=0)), (32, {})])
 def test_qr_all_freqs(pkg, O, k, opts):
