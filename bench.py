@@ -432,7 +432,7 @@ def WEIGHT_DIAG(N):
 # ---------------------------------------------------------------------------------------------------------------------
 # LNS block-stencil sections (device-generated operator, tiled block-CSR stage kernel)
 # ---------------------------------------------------------------------------------------------------------------------
-def lns_section(cx: Ctx, name, shape, k, Nw, scaling, note, cpu_sample_shape=None):
+def lns_section(cx: Ctx, name, shape, k, Nw, scaling, note, cpu_sample_shape=None, with_adjoint=False):
     pkg, world, rank, args = cx.pkg, cx.world, cx.rank, cx.args
     nvar = 5
     shape = tuple(int(s) for s in shape)
@@ -443,11 +443,11 @@ def lns_section(cx: Ctx, name, shape, k, Nw, scaling, note, cpu_sample_shape=Non
     t0 = time.time()
     if world == 1:
         r = pkg.capi.RSVDt(cx.local_rank)
-        r.set_operator_stencil(shape, nvar, with_adjoint=False)
+        r.set_operator_stencil(shape, nvar, with_adjoint=with_adjoint)
         r.set_grid(k, Nw, Ns, Nt, RR, dt, 0.05, False)
         n_own, row0 = N_total, 0
     else:
-        r, plan = pkg.dist.setup_rank_stencil(pkg, cx.local_rank, shape, nvar, grid, with_adjoint=False)
+        r, plan = pkg.dist.setup_rank_stencil(pkg, cx.local_rank, shape, nvar, grid, with_adjoint=with_adjoint)
         n_own, row0 = plan.n_own, plan.r0
     for opt in args.option:
         nm, value = opt.split("=")
@@ -474,6 +474,22 @@ def lns_section(cx: Ctx, name, shape, k, Nw, scaling, note, cpu_sample_shape=Non
     del l0
     dev_ms_max, stage_ms_max = cx.max_over_ranks(dev_ms, stage_ms)
     (launch_sum,) = cx.sum_over_ranks(launches)
+    adj = None
+    if with_adjoint:
+        # the adjoint pass (AdjointActionRK4.c:24-28 -> TSActionRK4 on A^H): the same stage kernel on the stored A^H
+        r.time_forced_steps(S, direct=False)
+        cx.barrier()
+        a_ms = a_stage = 0.0
+        a_n = 0
+        for _ in range(args.steps):
+            a_ms += r.time_forced_steps(S, direct=False)
+            ms, n = r.last_kernel_ms("stage")
+            a_stage += ms
+            a_n += n
+        cx.barrier()
+        a_ms_max, a_stage_max = cx.max_over_ranks(a_ms, a_stage)
+        adj = {"value": float(N_total) * k * S * args.steps / (a_ms_max * 1e-3), "unit": UNIT,
+               "avg_launch_ms": a_stage_max / max(a_n, 1), "what": "forced RK4 steps on A^H (the adjoint pass), same operator and size"}
     r.close()
     units = float(N_total) * k * S * args.steps
     value = units / (dev_ms_max * 1e-3)
@@ -497,6 +513,8 @@ def lns_section(cx: Ctx, name, shape, k, Nw, scaling, note, cpu_sample_shape=Non
                         "traffic": traffic, "frac": frac_meas, "traffic_note": why or "ncu dram bytes per launch (profiles/traffic.json), scaled by rows",
                         "share_of_step": stage_ms_max / dev_ms_max if dev_ms_max else None,
                         "idft_share_of_step": idft_ms / dev_ms if dev_ms else None}}
+    if adj is not None:
+        sec["adjoint"] = adj
     if rank == 0 and world == 1 and cpu_sample_shape is not None and not args.no_cpu:
         # the reference's own TSRK4.c on the same operator at a size the host finishes in seconds (rate is DRAM-bound, size-independent)
         S_ = pkg.synthetic
@@ -692,7 +710,8 @@ def main():
              "BASELINE.json configs[3] per-GPU load: 3-D block stencil 5 vars x 27 points (complex), %d x 200 x 200 grid; "
              "N = 8 GPUs is the 2e7-DOF configuration" % nz, (12, 40, 40)),
             ("lns3d_strong", (100, 100, 100), 8, 32, "strong",
-             "the same operator at a fixed 100 x 100 x 100 grid (5e6 DOF) on every GPU count", None),
+             "the same operator at a fixed 100 x 100 x 100 grid (5e6 DOF) on every GPU count (BASELINE.json configs[4]'s strong-scaling "
+             "sweep: direct and adjoint stepping; the weights add < 2 % to a solve, profiles/r2_north_star)", None),
             ("lns2d", (1000, 1000), 10, 32, "strong",
              "BASELINE.json configs[2]: 2-D block stencil 5 vars x 9 points, 1000 x 1000 grid (5e6 DOF), k = 10, fixed size", (200, 200)),
         ]
@@ -700,7 +719,7 @@ def main():
             if not want(name):
                 continue
             try:
-                sec = lns_section(cx, name, shape, kk, nw, scaling, note, cpu_shape)
+                sec = lns_section(cx, name, shape, kk, nw, scaling, note, cpu_shape, with_adjoint=(name == "lns3d_strong"))
             except Exception as e:
                 sec = {"error": f"{type(e).__name__}: {e}"}
                 if world > 1:

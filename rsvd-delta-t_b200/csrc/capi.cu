@@ -186,6 +186,7 @@ struct rsvdt_context {
     int64_t qr_fused = 1;     // CholeskyQR2 in 5 passes over Y_hat (first apply fused with the second Gram, FP64 tensor cores) instead of 6
     int64_t use_bcsr = 1;     // block-CSR stage kernel when the operator has dense B x B blocks
     int64_t use_tiled = 1;    // ... and its TMA-staged tiled form (stage_tiled.cu) when the number of vectors is even
+    int64_t use_small_exchange = 1; // halo exchanges of a few rows per neighbour: one launch instead of three
     int64_t tiled_flags = -1; // stage_tiled.cuh TbcsrDev::flags (-1: the default)
     int64_t tiled_order = 8;  // grid lines per group of the z-fastest tile order of 3-D stencil operators (0: row order)
     int64_t tiled_cv = 0;     // test vectors per consumer thread of the tiled stage kernel (0: automatic)
@@ -697,6 +698,17 @@ int dist_exchange(rsvdt_handle h, cplx *buf, int nvec)
 {
     if (!h->dist.on) return RSVDT_OK;
     h->dist.fz_last_out = nullptr;   // the ghost rows of `buf` are (re)filled in place: the next fused stage gathers them from there
+    auto &D = h->dist;
+    if (h->use_small_exchange && D.connected && nvec <= D.nvec_max && (int64_t)std::max(D.max_out, D.max_in) * nvec <= 8192 &&
+        D.out.size() <= 16 && D.in.size() <= 16) {
+        // a few rows per neighbour (layout 1): the whole exchange in one launch
+        D.epoch++;
+        unsigned long long *tflag = D.flags.p ? D.flags.as<unsigned long long>() + 2 * D.nranks + 1 : nullptr;
+        CU(launch_halo_exchange_small(buf, nvec, D.msgs_dev.p, (int)D.out.size(), D.peer_flags_dev.p, D.ins_dev.p, (int)D.in.size(),
+                                      (int)(D.epoch & 1ull), D.nvec_max, D.epoch, tflag, h->stream));
+        h->launches += 1;
+        return RSVDT_OK;
+    }
     RS(dist_push(h, buf, nvec, h->stream));
     return dist_wait_unpack(h, buf, nvec);
 }
@@ -1573,7 +1585,7 @@ int build_fused(rsvdt_handle h)
 int check_halo_timeout(rsvdt_handle h)
 {
     auto &D = h->dist;
-    if (!D.on || !D.fz_ready || !D.flags.p) return RSVDT_OK;
+    if (!D.on || !D.flags.p) return RSVDT_OK;
     unsigned long long v = 0;
     CU(cudaMemcpy(&v, D.flags.as<unsigned long long>() + 2 * D.nranks + 1, sizeof v, cudaMemcpyDeviceToHost));
     if (v) return fail(h, RSVDT_ERR_CUDA, "halo exchange: a peer GPU did not publish its boundary rows (rank %d gave up waiting)", D.rank);
@@ -2618,6 +2630,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "use_tiled")) h->use_tiled = value;
     else if (!strcmp(name, "tiled_stages")) h->tiled_stages = value;
     else if (!strcmp(name, "tiled_cv")) h->tiled_cv = value;
+    else if (!strcmp(name, "use_small_exchange")) h->use_small_exchange = value;
     else if (!strcmp(name, "tiled_variant")) h->tiled_variant = value;
     else if (!strcmp(name, "tiled_flags")) h->tiled_flags = value;
     else if (!strcmp(name, "tiled_order")) h->tiled_order = value;

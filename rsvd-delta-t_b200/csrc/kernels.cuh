@@ -177,6 +177,10 @@ cudaError_t launch_spmm_stack(const CsrDev &M, const cplx *in, cplx *out, int na
 // device-side descriptors (layout must match kernels.cu)
 struct HaloMsgHost { cplx *peer_mailbox; const int32_t *rows; int count; int pad; };
 struct HaloInHost { const cplx *mailbox; const unsigned long long *flag; int64_t dest_row0; int count; int pad; };
+// push + signal + wait + unpack in one launch of one CTA (small messages)
+cudaError_t launch_halo_exchange_small(cplx *buf, int nvec, const void *msgs_dev, int nout, void *peer_flags_dev, const void *ins_dev,
+                                       int nin, int parity, int nvec_max, unsigned long long epoch, unsigned long long *timeout_flag,
+                                       cudaStream_t s);
 cudaError_t launch_halo_push(const cplx *src, int nvec, const void *msgs_dev, int nmsgs, int max_count, int parity,
                              int nvec_max, cudaStream_t s);
 cudaError_t launch_halo_signal(void *peer_flags_dev, int npeers, unsigned long long epoch, cudaStream_t s);

@@ -104,6 +104,34 @@ def test_action_lns_stencil(pkg, O, shape, cplx, nvar, k, opts):
     r.close()
 
 
+def test_lns_3d_million_rows_against_oracle(pkg, O):
+    # BASELINE.json configs[3] kind of operator at a bandwidth-bound size (10^6 rows, 1.3e8 stored entries, k = 8: the tiled
+    # stage kernel in the variant the 2e7-DOF run uses, 6250 tiles, 64-bit offsets into the 2.5 GB of chunks): the state after
+    # three forced RK4 steps against the oracle for two of the eight test vectors, every row
+    shape, nvar, k, Nw = (20, 100, 100), 5, 8, 4
+    N, rp, ci, va = pkg.synthetic.lns_stencil(shape, nvar=nvar)
+    assert N == 1_000_000
+    v = make_vars(O, pkg, N, k, Nw, 2.0, 0.003, 0.25)
+    rng = np.random.default_rng(3)
+    F = np.asfortranarray(rng.random((N, k * Nw)) + 1j * rng.random((N, k * Nw)))
+    _, idft = O.create_dft_idft_mats(v.Nw, v.Nw_eff, v.Ns, v.RealOperator, False)
+    ref = O.forced_state(O.Csr(N, N, rp, ci, va), v, idft, F, 3, ncols=2)
+    for dev in (True, False):       # operator generated on the device / uploaded as CSR (what MatLoad feeds)
+        r = pkg.capi.RSVDt(0)
+        if dev:
+            r.set_operator_stencil(shape, nvar, with_adjoint=False)
+        else:
+            r.LNSStructure(N, rp, ci, va)
+        r.set_grid(v.k, v.Nw, v.Ns, v.Nt, v.ResRatio, v.dt, v.w, False)
+        assert r.operator_info(True, k)["format"] == "tiled-bcsr"
+        r.set_Y_hat(F)
+        r.time_forced_steps(3)
+        y = r.get_state()
+        r.close()
+        assert rel_err(y[:, :2], ref) < 1e-12
+        assert np.isfinite(y).all() and np.abs(y[-5:]).max() > 0      # the last tile did its rows
+
+
 def test_lns_stage_kernels_bit_identical(pkg, O):
     # CSR, block-CSR and tiled block-CSR stage kernels sum every row in the same order: identical bits, both directions,
     # on a grid whose block rows do not fill the last tile and whose boundary rows have fewer blocks (padded chunks)
