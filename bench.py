@@ -100,7 +100,7 @@ class ClockSampler(threading.Thread):
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,clocks.mem,clocks.max.mem")
 
     def __init__(self, gpu_index=0):
         super().__init__(daemon=True)
@@ -129,12 +129,18 @@ class ClockSampler(threading.Thread):
                 pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, mem, mem_mx, pw = [], [], set(), [], [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                try:
+                    pw.append(float(r[3]))
+                    mem.append(float(r[9]))
+                    mem_mx.append(float(r[10]))
+                except (ValueError, IndexError):
+                    pass
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
@@ -142,8 +148,10 @@ class ClockSampler(threading.Thread):
                 continue
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if mem:
+            out.update({"mem_mhz": float(np.median(mem)), "mem_max_mhz": float(max(mem_mx)), "power_w": float(np.median(pw))})
+        return out
 
 
 # ======================================================================================================================
@@ -459,6 +467,10 @@ def lns_section(cx: Ctx, name, shape, k, Nw, scaling, note, cpu_sample_shape=Non
     S = LNS_STEPS_PER_PASS
     for _ in range(2):
         r.time_forced_steps(S)
+    sampler = ClockSampler(cx.local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
     cx.barrier()
     dev_ms = stage_ms = idft_ms = 0.0
     stage_n = 0
@@ -470,6 +482,8 @@ def lns_section(cx: Ctx, name, shape, k, Nw, scaling, note, cpu_sample_shape=Non
         stage_n += n
         idft_ms += r.last_kernel_ms("idft")[0]
     cx.barrier()
+    if rank == 0:
+        sampler.stop()
     launches = r.kernel_launches()
     del l0
     dev_ms_max, stage_ms_max = cx.max_over_ranks(dev_ms, stage_ms)
@@ -515,6 +529,8 @@ def lns_section(cx: Ctx, name, shape, k, Nw, scaling, note, cpu_sample_shape=Non
                         "idft_share_of_step": idft_ms / dev_ms if dev_ms else None}}
     if adj is not None:
         sec["adjoint"] = adj
+    if rank == 0:
+        sec["clocks"] = sampler.summary()
     if rank == 0 and world == 1 and cpu_sample_shape is not None and not args.no_cpu:
         # the reference's own TSRK4.c on the same operator at a size the host finishes in seconds (rate is DRAM-bound, size-independent)
         S_ = pkg.synthetic
