@@ -93,6 +93,8 @@ struct CsrOwned {
     std::vector<int32_t> base_order;              // processing order of the tiles chosen for L2 locality (empty: row order)
     int plan_nv = -1, plan_variant = -1, plan_mode = -1, ntiles = 0, nslow = 0;
     bool plan_ok = false;
+    int plan_TR = 0;                              // rows per tile of the plan; whether its first / last tile is a regular one
+    bool first_ok = false, last_ok = false;
     void release()
     {
         rowptr.release(); col.release(); val.release(); dia.release(); tile_ok.release(); slow_ranges.release();
@@ -115,6 +117,12 @@ struct rsvdt_context {
     rsvdt_group_ctx *group = nullptr;     // != null: this handle stands for P member handles, one per GPU (group.inc)
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // runs the few irregular tiles of a fused step next to the main kernel
+    cudaStream_t xstream = nullptr;       // layout 1: the halo exchange of step n runs here, under the interior tiles of step n
+    cudaEvent_t ev_ex = nullptr;          // ... recorded after it; the main stream waits for it before anything reads ghost rows
+    bool ex_pending = false;
+    DevBuf bnd_flag;                      // counter of finished boundary tiles (rk4_dia_tma_kernel)
+    unsigned long long bnd_target = 0;
+    int64_t use_overlap1 = 1;             // layout 1: exchange overlapped with the step kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t synth_stream = nullptr;  // low priority: forcing synthesis of the next chunk, overlapped with the RK4 steps
     cudaEvent_t ev_step0 = nullptr, ev_synth = nullptr;
@@ -243,11 +251,21 @@ int fail(rsvdt_handle h, int code, const char *fmt, ...)
         if (r__ != RSVDT_OK) return r__; \
     } while (0)
 
+// the main stream waits for a halo exchange still running on the exchange stream (layout 1, overlapped with the step kernel)
+int settle_exchange(rsvdt_handle h)
+{
+    if (h->ex_pending) {
+        CU(cudaStreamWaitEvent(h->stream, h->ev_ex, 0));
+        h->ex_pending = false;
+    }
+    return RSVDT_OK;
+}
+
 int bind(rsvdt_handle h)
 {
     if (!h) return RSVDT_ERR_ARG;
     CU(cudaSetDevice(h->device));
-    return RSVDT_OK;
+    return settle_exchange(h);
 }
 
 // event bracketing of one kernel family while profiling
@@ -618,6 +636,9 @@ int plan_dia(rsvdt_handle h, CsrOwned &Op, int nv, int mode)
     }
     Op.ntiles = (int)ntiles;
     Op.nslow = (int)(ranges.size() / 2);
+    Op.plan_TR = TR;
+    Op.first_ok = ntiles > 0 && ok[0];
+    Op.last_ok = ntiles > 0 && ok[(size_t)ntiles - 1];
     Op.plan_ok = true;
     return RSVDT_OK;
 }
@@ -676,6 +697,7 @@ int dist_push(rsvdt_handle h, const cplx *buf, int nvec, cudaStream_t s)
     auto &D = h->dist;
     if (!D.connected) return fail(h, RSVDT_ERR_STATE, "row-partitioned run: peers not connected (rsvdt_dist_ipc_import)");
     if (nvec > D.nvec_max) return fail(h, RSVDT_ERR_ARG, "halo exchange of %d vectors exceeds the mailbox (%d)", nvec, D.nvec_max);
+    RS(settle_exchange(h));
     D.epoch++;
     const int parity = (int)(D.epoch & 1ull);
     CU(launch_halo_push(buf, nvec, D.msgs_dev.p, (int)D.out.size(), D.max_out, parity, D.nvec_max, s));
@@ -699,13 +721,14 @@ int dist_exchange(rsvdt_handle h, cplx *buf, int nvec)
     if (!h->dist.on) return RSVDT_OK;
     h->dist.fz_last_out = nullptr;   // the ghost rows of `buf` are (re)filled in place: the next fused stage gathers them from there
     auto &D = h->dist;
+    RS(settle_exchange(h));
     if (h->use_small_exchange && D.connected && nvec <= D.nvec_max && (int64_t)std::max(D.max_out, D.max_in) * nvec <= 8192 &&
         D.out.size() <= 16 && D.in.size() <= 16) {
         // a few rows per neighbour (layout 1): the whole exchange in one launch
         D.epoch++;
         unsigned long long *tflag = D.flags.p ? D.flags.as<unsigned long long>() + 2 * D.nranks + 1 : nullptr;
         CU(launch_halo_exchange_small(buf, nvec, D.msgs_dev.p, (int)D.out.size(), D.peer_flags_dev.p, D.ins_dev.p, (int)D.in.size(),
-                                      (int)(D.epoch & 1ull), D.nvec_max, D.epoch, tflag, h->stream));
+                                      (int)(D.epoch & 1ull), D.nvec_max, D.epoch, tflag, nullptr, 0ull, h->stream));
         h->launches += 1;
         return RSVDT_OK;
     }
@@ -893,13 +916,42 @@ int step_path(rsvdt_handle h, CsrOwned &Op, int nv, int *path)
     return RSVDT_OK;
 }
 
+// Layout 1 (narrow band, TMA-staged step kernel): can the exchange of y_{n+1}'s halo rows run under the interior tiles of the
+// step that produces them?  Needs the rows every neighbour wants to come out of the first / last tile of the rank, both
+// regular tiles; returns the number of tiles that will count themselves (0: not eligible).
+int overlap1_tiles(rsvdt_handle h, const CsrOwned &Op, int nv, int path, int nbatch)
+{
+    const auto &D = h->dist;
+    if (!D.on || D.layout != 1 || !D.connected || !h->use_overlap1 || !h->use_small_exchange || path != 3 || nbatch != 1) return 0;
+    if (!Op.plan_ok || Op.ntiles < 2 || Op.plan_TR <= 0 || nv > D.nvec_max) return 0;
+    if ((int64_t)std::max(D.max_out, D.max_in) * nv > 8192 || D.out.size() > 16 || D.in.size() > 16 || D.out.empty()) return 0;
+    const int64_t lo_end = Op.plan_TR, hi_begin = (int64_t)(Op.ntiles - 1) * Op.plan_TR;
+    for (const auto &m : D.out)
+        for (int32_t r : m.rows_h) {
+            const int64_t o = (int64_t)r - h->own0;
+            if (o < 0 || o >= h->N) return 0;
+            if (o < lo_end) { if (!Op.first_ok) return 0; }
+            else if (o >= hi_begin) { if (!Op.last_ok) return 0; }
+            else return 0;
+        }
+    return (Op.first_ok ? 1 : 0) + (Op.last_ok ? 1 : 0);
+}
+
 // one whole RK4 step, dispatching between the fused kernels (y ping-pongs between *ycur and *ynext) and the
 // stage-by-stage kernels (in place on *ycur)
 int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **ycur, cplx **ynext, const cplx *f_prev,
                  const cplx *f_half, const cplx *f_next, cplx *snap, int nbatch = 1, int64_t batch_stride = 0)
 {
+    RS(settle_exchange(h));   // (the ghost rows of *ycur come from the exchange of the previous step)
     if (path == 0)
         return rk4_step(h, Op, nv, *ycur, h->xa.as<cplx>(), h->xb.as<cplx>(), h->acc.as<cplx>(), f_prev, f_half, f_next, snap);
+    const int ov_tiles = overlap1_tiles(h, Op, nv, path, nbatch);
+    if (ov_tiles && !h->bnd_flag.p) {
+        CU(h->bnd_flag.alloc(sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(h->bnd_flag.p, 0, sizeof(unsigned long long), h->stream));
+        CU(cudaStreamSynchronize(h->stream));   // (once: the exchange stream must never see the counter before it is zero)
+        h->bnd_target = 0;
+    }
     Bracket br(h, &h->ev_stage);
     BandedStepArgs a;
     a.y_in = *ycur; a.y_out = *ynext; a.f_prev = f_prev; a.f_half = f_half; a.f_next = f_next; a.snap = snap; a.dt = h->g.dt;
@@ -907,6 +959,7 @@ int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **yc
     a.own_end = h->own0 + h->N;
     a.nbatch = nbatch;
     a.batch_stride = batch_stride;
+    a.bnd_flag = ov_tiles ? h->bnd_flag.as<unsigned long long>() : nullptr;
     if (path >= 2) {
         const bool fork = Op.nslow > 0;
         if (Op.nslow > 0) {
@@ -931,6 +984,23 @@ int rk4_step_any(rsvdt_handle h, const CsrOwned &Op, int nv, int path, cplx **yc
         h->launches += 1;
     }
     std::swap(*ycur, *ynext);
+    if (ov_tiles) {
+        // the exchange of y_{n+1}'s halo rows, on its own stream: it starts as soon as the boundary tiles of the step kernel
+        // above have counted themselves and runs under the interior tiles; the next step (or whatever reads ghost rows
+        // next) waits for ev_ex.  Exchanges follow each other in stream order, as their epochs require.
+        auto &D = h->dist;
+        D.fz_last_out = nullptr;
+        D.epoch++;
+        h->bnd_target += (unsigned long long)ov_tiles;
+        unsigned long long *tflag = D.flags.p ? D.flags.as<unsigned long long>() + 2 * D.nranks + 1 : nullptr;
+        CU(launch_halo_exchange_small(*ycur, nv, D.msgs_dev.p, (int)D.out.size(), D.peer_flags_dev.p, D.ins_dev.p, (int)D.in.size(),
+                                      (int)(D.epoch & 1ull), D.nvec_max, D.epoch, tflag, h->bnd_flag.as<unsigned long long>(),
+                                      h->bnd_target, h->xstream));
+        CU(cudaEventRecord(h->ev_ex, h->xstream));
+        h->ex_pending = true;
+        h->launches += 1;
+        return RSVDT_OK;
+    }
     RS(dist_exchange(h, *ycur, nv));
     return RSVDT_OK;
 }
@@ -1704,6 +1774,8 @@ int rsvdt_create(int device, rsvdt_handle *hout)
     if (const char *e = getenv("RSVDT_TILED_VARIANT")) h->tiled_variant = atoll(e);   // (the same, for runs of the test suite under a variant)
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_ex, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_step0, cudaEventDisableTiming) != cudaSuccess ||
@@ -1784,6 +1856,8 @@ int rsvdt_destroy(rsvdt_handle h)
     cudaEventDestroy(h->ev_synth);
     cudaStreamDestroy(h->synth_stream);
     cudaStreamDestroy(h->side);
+    cudaEventDestroy(h->ev_ex);
+    cudaStreamDestroy(h->xstream);
     cudaStreamDestroy(h->stream);
     delete h;
     return RSVDT_OK;
@@ -2631,6 +2705,7 @@ int rsvdt_set_option(rsvdt_handle h, const char *name, int64_t value)
     else if (!strcmp(name, "tiled_stages")) h->tiled_stages = value;
     else if (!strcmp(name, "tiled_cv")) h->tiled_cv = value;
     else if (!strcmp(name, "use_small_exchange")) h->use_small_exchange = value;
+    else if (!strcmp(name, "use_overlap1")) h->use_overlap1 = value;
     else if (!strcmp(name, "tiled_variant")) h->tiled_variant = value;
     else if (!strcmp(name, "tiled_flags")) h->tiled_flags = value;
     else if (!strcmp(name, "tiled_order")) h->tiled_order = value;

@@ -683,7 +683,9 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
                    int TR, BandedStepArgs a)
 {
     constexpr int ND = LO + HI + 1, WN = R + LO + HI;
-    if (!tile_ok[blockIdx.x]) return;
+    int tile = (int)blockIdx.x;
+    if (a.bnd_flag && gridDim.x > 1) tile = blockIdx.x == 0 ? 0 : (blockIdx.x == 1 ? (int)gridDim.x - 1 : (int)blockIdx.x - 1);
+    if (!tile_ok[tile]) return;
     a.y_in += (int64_t)blockIdx.y * a.batch_stride;
     a.y_out += (int64_t)blockIdx.y * a.batch_stride;
     extern __shared__ __align__(128) cplx sm[];
@@ -694,7 +696,7 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
     cplx *Fp = At + E0 * ND, *Fh = Fp + n_e, *Fn = Fh + n_e;   // forcing tiles (FORCED only)
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(FORCED ? (Fn + n_e) : Fp);
     const int64_t own_end = a.own_end < 0 ? N : a.own_end;
-    const int64_t base = a.own_begin + (int64_t)blockIdx.x * TR - 4 * LO;
+    const int64_t base = a.own_begin + (int64_t)tile * TR - 4 * LO;
     const int lr_lo = (int)max((int64_t)0, -base), lr_hi = (int)min((int64_t)E0, N - base);   // tile rows inside [0, N)
     const double dt = a.dt;
     const double c_half = dt / 2, c_full = dt, w1 = dt / 6, w2 = dt / 6 * 2;
@@ -824,6 +826,11 @@ rk4_dia_tma_kernel(const cplx *__restrict__ dia, const unsigned char *__restrict
             tma_store_1d(a.y_out + g, BA + o_lo * nv, ob);
             if (a.snap) tma_store_1d(a.snap + g, BA + o_lo * nv, ob);
             tma_store_commit_wait();
+        }
+        if (a.bnd_flag && (tile == 0 || tile == (int)gridDim.x - 1)) {
+            asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // the rows are written, not only read out of shared memory
+            __threadfence();
+            atomicAdd(a.bnd_flag, 1ull);
         }
     }
 }
@@ -1694,15 +1701,28 @@ halo_wait_unpack_kernel(cplx *__restrict__ dst, int nvec, const HaloInDev *__res
 __global__ void __launch_bounds__(512)
 halo_exchange_small_kernel(cplx *__restrict__ buf, int nvec, const HaloMsgDev *__restrict__ msgs, int nout,
                            unsigned long long *const *__restrict__ peer_flags, const HaloInDev *__restrict__ ins, int nin, int parity,
-                           int nvec_max, unsigned long long epoch, unsigned long long *timeout_flag)
+                           int nvec_max, unsigned long long epoch, unsigned long long *timeout_flag,
+                           const unsigned long long *ready, unsigned long long ready_target)
 {
+    if (ready) {
+        // launched next to the step kernel that produces `buf`: wait until its boundary tiles have counted themselves
+        if (threadIdx.x == 0) {
+            unsigned long long v;
+            long long spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(ready) : "memory");
+                if (++spins > 600000000ll) { if (timeout_flag) *timeout_flag = 1ull; break; }
+            } while (v < ready_target);
+        }
+        __syncthreads();
+    }
     for (int i = 0; i < nout; i++) {
         const HaloMsgDev m = msgs[i];
         const int64_t n = (int64_t)m.count * nvec;
         cplx *dst = m.peer_mailbox + (int64_t)parity * m.count * nvec_max;
         for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
             const int64_t r = e / nvec;
-            dst[e] = buf[(int64_t)m.rows[r] * nvec + (int)(e - r * nvec)];
+            dst[e] = __ldcg(buf + (int64_t)m.rows[r] * nvec + (int)(e - r * nvec));   // (written by a kernel that may still be running)
         }
     }
     __threadfence_system();
@@ -1729,12 +1749,13 @@ halo_exchange_small_kernel(cplx *__restrict__ buf, int nvec, const HaloMsgDev *_
 
 cudaError_t launch_halo_exchange_small(cplx *buf, int nvec, const void *msgs_dev, int nout, void *peer_flags_dev, const void *ins_dev,
                                        int nin, int parity, int nvec_max, unsigned long long epoch, unsigned long long *timeout_flag,
-                                       cudaStream_t s)
+                                       const unsigned long long *ready, unsigned long long ready_target, cudaStream_t s)
 {
     if (nout == 0 && nin == 0) return cudaSuccess;
     if (nout > 512 || nin > 512) return cudaErrorInvalidValue;
     halo_exchange_small_kernel<<<1, 512, 0, s>>>(buf, nvec, (const HaloMsgDev *)msgs_dev, nout, (unsigned long long *const *)peer_flags_dev,
-                                                 (const HaloInDev *)ins_dev, nin, parity, nvec_max, epoch, timeout_flag);
+                                                 (const HaloInDev *)ins_dev, nin, parity, nvec_max, epoch, timeout_flag, ready,
+                                                 ready_target);
     return cudaGetLastError();
 }
 

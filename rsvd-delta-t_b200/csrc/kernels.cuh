@@ -72,6 +72,10 @@ struct BandedStepArgs {
     // batch of independent block vectors advanced by one launch (blockIdx.y): vector b lives at y_in/y_out + b*batch_stride
     int nbatch = 1;
     int64_t batch_stride = 0;
+    // row-partitioned runs (TMA-staged kernel, nbatch == 1): the first and the last tile of the rank -- the ones whose rows the
+    // neighbours need -- are given to blocks 0 and 1, and count themselves in *bnd_flag once their rows are in global memory,
+    // so that the halo exchange (a kernel on another stream polling the counter) runs under the interior tiles
+    unsigned long long *bnd_flag = nullptr;
 };
 bool banded_step_supported(const CsrDev &Op, int64_t lo_bw, int64_t hi_bw, int nv, int variant);
 int banded_tile_rows(int64_t lo_bw, int64_t hi_bw, int nv, int variant);
@@ -180,7 +184,7 @@ struct HaloInHost { const cplx *mailbox; const unsigned long long *flag; int64_t
 // push + signal + wait + unpack in one launch of one CTA (small messages)
 cudaError_t launch_halo_exchange_small(cplx *buf, int nvec, const void *msgs_dev, int nout, void *peer_flags_dev, const void *ins_dev,
                                        int nin, int parity, int nvec_max, unsigned long long epoch, unsigned long long *timeout_flag,
-                                       cudaStream_t s);
+                                       const unsigned long long *ready, unsigned long long ready_target, cudaStream_t s);
 cudaError_t launch_halo_push(const cplx *src, int nvec, const void *msgs_dev, int nmsgs, int max_count, int parity,
                              int nvec_max, cudaStream_t s);
 cudaError_t launch_halo_signal(void *peer_flags_dev, int npeers, unsigned long long epoch, cudaStream_t s);
