@@ -144,6 +144,15 @@ typedef int (*rsvdt_snapshot_cb)(int64_t pos, const double *q_host, int64_t N, v
 int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t rend, int64_t TransSaveMod,
                             double TransDivVal, double TransConVal, double *norms_out, int64_t *steps_done,
                             int *reason, rsvdt_snapshot_cb snapshot_cb, void *user);
+/* The same with a second, independent cadence for TransientRemovalEst.c (TransientRunRK4.c:174-184 fills the N x Nw matrix
+ * Q_all every Nt_period/Nw steps): est_cb(pos, q_host, N, est_user) is called after every est_mod-th step (pos = step /
+ * est_mod), after the stop tests of that step if it is also a multiple of TransSaveMod.  est_mod <= 0 or est_cb == NULL:
+ * exactly rsvdt_transient_run_rk4.  The estimate itself is host arithmetic on Nw snapshots per period and lives in the host
+ * drivers (host/RSVDt.c TransientRemovalEst, transient_est.py). */
+int rsvdt_transient_run_rk4_est(rsvdt_handle h, int direct, double *q0_host, int64_t rend, int64_t TransSaveMod,
+                                double TransDivVal, double TransConVal, double *norms_out, int64_t *steps_done,
+                                int *reason, rsvdt_snapshot_cb snapshot_cb, void *user, int64_t est_mod,
+                                rsvdt_snapshot_cb est_cb, void *est_user);
 
 /* ---- row partition across GPUs (one process per GPU) ----------------------------------------------------
  * Replaces PETSc's MPIAIJ distribution (LNSStructure.c:24-26: MatSetType MATMPIAIJ; CreateTSMats.c:15-17: VECMPI with

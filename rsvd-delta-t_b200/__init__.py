@@ -11,8 +11,8 @@ The product is the C-ABI shared library `librsvdt_b200.so` (csrc/, include/rsvdt
 The directory name contains '-' (it is the name the task prescribes), so import it through
 `__graft_entry__.load_package()` which registers it as the module `rsvdt_b200`.
 """
-from . import petsc_io, synthetic  # noqa: F401
+from . import petsc_io, synthetic, transient_est  # noqa: F401
 from . import capi  # noqa: F401
 from . import dist  # noqa: F401
 
-__all__ = ["capi", "dist", "petsc_io", "synthetic"]
+__all__ = ["capi", "dist", "petsc_io", "synthetic", "transient_est"]

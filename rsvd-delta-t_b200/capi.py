@@ -277,26 +277,30 @@ class RSVDt:
         self._ck(lib().rsvdt_ts_exp_a_deltat(self._h, C.c_int(int(direct)), _p(Uc), C.c_int64(Uc.shape[1])))
         return Uc
 
-    def TransientRunRK4(self, q0, rend, TransSaveMod, TransDivVal=1e3, TransConVal=1e-8, direct=True, on_snapshot=None):
+    def TransientRunRK4(self, q0, rend, TransSaveMod, TransDivVal=1e3, TransConVal=1e-8, direct=True, on_snapshot=None,
+                        est_mod=0, on_est=None):
+        """on_snapshot(pos, q) every TransSaveMod steps; on_est(pos, q) every est_mod steps (TransientRemovalEst.c's cadence)"""
         q = np.ascontiguousarray(q0, c128).copy()
         norms = np.zeros(rend // TransSaveMod + 1, np.float64)
         steps, reason = C.c_int64(), C.c_int()
-        N = self.N
 
-        def _cb(pos, ptr, n, user):
-            try:
-                arr = np.ctypeslib.as_array(ptr, shape=(2 * n,)).view(c128).copy()
-                on_snapshot(int(pos), arr)
-                return 0
-            except Exception:
-                return 1
+        def wrap(fn):
+            def _cb(pos, ptr, n, user):
+                try:
+                    fn(int(pos), np.ctypeslib.as_array(ptr, shape=(2 * n,)).view(c128).copy())
+                    return 0
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            return SNAPSHOT_CB(_cb)
 
-        cb = SNAPSHOT_CB(_cb) if on_snapshot is not None else C.cast(None, SNAPSHOT_CB)
-        self._ck(lib().rsvdt_transient_run_rk4(self._h, C.c_int(int(direct)), _p(q), C.c_int64(rend),
-                                               C.c_int64(TransSaveMod), C.c_double(TransDivVal),
-                                               C.c_double(TransConVal), _p(norms), C.byref(steps), C.byref(reason),
-                                               cb, None))
-        del N
+        cb = wrap(on_snapshot) if on_snapshot is not None else C.cast(None, SNAPSHOT_CB)
+        ecb = wrap(on_est) if (on_est is not None and est_mod > 0) else C.cast(None, SNAPSHOT_CB)
+        self._ck(lib().rsvdt_transient_run_rk4_est(self._h, C.c_int(int(direct)), _p(q), C.c_int64(rend),
+                                                   C.c_int64(TransSaveMod), C.c_double(TransDivVal),
+                                                   C.c_double(TransConVal), _p(norms), C.byref(steps), C.byref(reason),
+                                                   cb, None, C.c_int64(est_mod), ecb, None))
         return q, norms, steps.value, reason.value
 
     # ---- test / measurement hooks -------------------------------------------------------------------------

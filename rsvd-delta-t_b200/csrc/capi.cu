@@ -2240,7 +2240,18 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
                             double TransDivVal, double TransConVal, double *norms_out, int64_t *steps_done, int *reason,
                             rsvdt_snapshot_cb cb, void *user)
 {
-    if (h && h->group) return group_transient_run(h, direct, q0_host, rend, TransSaveMod, TransDivVal, TransConVal, norms_out, steps_done, reason, cb, user);
+    return rsvdt_transient_run_rk4_est(h, direct, q0_host, rend, TransSaveMod, TransDivVal, TransConVal, norms_out, steps_done, reason,
+                                       cb, user, 0, nullptr, nullptr);
+}
+
+int rsvdt_transient_run_rk4_est(rsvdt_handle h, int direct, double *q0_host, int64_t rend, int64_t TransSaveMod,
+                                double TransDivVal, double TransConVal, double *norms_out, int64_t *steps_done, int *reason,
+                                rsvdt_snapshot_cb cb, void *user, int64_t est_mod, rsvdt_snapshot_cb est_cb, void *est_user)
+{
+    if (!est_cb || est_mod <= 0) { est_cb = nullptr; est_mod = 0; }
+    if (h && h->group)
+        return group_transient_run(h, direct, q0_host, rend, TransSaveMod, TransDivVal, TransConVal, norms_out, steps_done, reason, cb,
+                                   user, est_mod, est_cb, est_user);
     RS(bind(h));
     if (!h->A.set) return fail(h, RSVDT_ERR_STATE, "operator not set");
     if (!h->grid_set) return fail(h, RSVDT_ERR_STATE, "grid not set (dt)");
@@ -2265,7 +2276,8 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
     int64_t i = 1;
     std::vector<double> snap_host;
     for (; i <= rend;) {
-        const int64_t next_stop = std::min(rend, ((i - 1) / TransSaveMod + 1) * TransSaveMod);
+        int64_t next_stop = std::min(rend, ((i - 1) / TransSaveMod + 1) * TransSaveMod);
+        if (est_mod > 0) next_stop = std::min(next_stop, ((i - 1) / est_mod + 1) * est_mod);
         int rc = unforced_steps(h, direct != 0, 1, q.as<cplx>(), next_stop - i + 1);   // :128-130
         if (rc != RSVDT_OK) { q.release(); return rc; }
         i = next_stop + 1;
@@ -2288,6 +2300,13 @@ int rsvdt_transient_run_rk4(rsvdt_handle h, int direct, double *q0_host, int64_t
                 if (crc != 0) { q.release(); return fail(h, RSVDT_ERR_USER, "snapshot callback failed (%d)", crc); }
             }
             norms_out[pos] = norm;                                           // :166
+        }
+        if (est_mod > 0 && next_stop % est_mod == 0) {                       // :174-184 (after the stop tests of this step)
+            snap_host.resize((size_t)2 * N);
+            CU(cudaMemcpyAsync(snap_host.data(), q_own, (size_t)N * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            int crc = est_cb(next_stop / est_mod, snap_host.data(), N, est_user);
+            if (crc != 0) { q.release(); return fail(h, RSVDT_ERR_USER, "transient-removal estimate callback failed (%d)", crc); }
         }
     }
     if (steps_done) *steps_done = why ? i : rend;

@@ -467,6 +467,130 @@ static int snapshot_cb(int64_t pos, const double *q, int64_t N, void *user)
     return pb_write_vec(c->dirs->IO_dir, N, q);
 }
 
+/* ---- TransientRemovalEst.c: how well could the transient be removed, period by period (diagnostic, `TransRemovalEst`) ---------
+ * The transient run keeps the last Nw snapshots, one every Nt_period / Nw steps, in Q_all (TransientRunRK4.c:174-184; here
+ * through the second callback cadence of rsvdt_transient_run_rk4_est) and at the end of every period computes
+ *   "initial" norms  || Q_all dft[:, i] / Nw ||                        (TransientRemovalEst.c:58-71)
+ *   "updated" norms  || q_ss - U U^H q_ss || / || q_ss ||,  U = orth(q_ss e^{i w_i s dT} + Q_all[:, s])     (:75-119)
+ * for the non-negative frequencies w_i = i w, q_ss = -q0.  Host arithmetic on Nw vectors (complex as (re, im) pairs). */
+typedef struct {
+    int64_t N, Nw, Nw_eff, Nt_period, est_mod;
+    double w;
+    double *Q_all, *qss;      /* N x Nw column-major, N */
+    Directories *dirs;
+    char *text[64];           /* what the estimate of a period prints, shown in step order after the run */
+    int64_t text_step[64];
+    int ntext;
+} est_ctx;
+
+static void est_printf(char **buf, size_t *len, size_t *cap, const char *fmt, ...)
+{
+    va_list ap;
+    char line[256];
+    va_start(ap, fmt);
+    int n = vsnprintf(line, sizeof line, fmt, ap);
+    va_end(ap);
+    if (n < 0) return;
+    if (*len + (size_t)n + 1 > *cap) {
+        *cap = 2 * (*cap + (size_t)n + 1);
+        *buf = (char *)realloc(*buf, *cap);
+    }
+    memcpy(*buf + *len, line, (size_t)n + 1);
+    *len += (size_t)n;
+}
+
+static double cnorm2(const double *x, int64_t n)
+{
+    double s = 0;
+    for (int64_t i = 0; i < 2 * n; i++) s += x[i] * x[i];
+    return s;
+}
+
+static int TransientRemovalEst(est_ctx *c, int64_t period_index, int64_t step)
+{
+    const int64_t N = c->N, Nw = c->Nw, nhalf = Nw / 2;
+    const double PI = 3.14159265358979323846264338327950288;
+    const double deltaT = 2 * PI / c->w / (double)Nw;                                                         /* :26 */
+    const int64_t skip = period_index == 1 ? 1 : 0, Ns = Nw - skip;                                           /* :28 */
+    char *buf = NULL;
+    size_t len = 0, cap = 0;
+    est_printf(&buf, &len, &cap, "**** deltaT = %g ****\n", deltaT);
+    est_printf(&buf, &len, &cap, "**** Subspace dim = %d ****\n", (int)Ns);
+    est_printf(&buf, &len, &cap, "**** period index = %d ****\n", (int)period_index);
+    est_printf(&buf, &len, &cap, "**** Displaying transient norms for (positive) frequencies ****\n");
+    double *init = (double *)calloc((size_t)nhalf * 2, sizeof(double)), *upd = (double *)calloc((size_t)nhalf * 2, sizeof(double));
+    double *Y = (double *)malloc((size_t)N * (size_t)Ns * 16), *d = (double *)malloc((size_t)N * 16);
+    if (!init || !upd || !Y || !d) { free(init); free(upd); free(Y); free(d); free(buf); return seterr(RSVDT_ERR_MEM, "out of memory"); }
+    for (int64_t i = 0; i < nhalf && i < c->Nw_eff; i++) {                                                    /* :58-71 */
+        memset(d, 0, (size_t)N * 16);
+        for (int64_t s = 0; s < Nw; s++) {
+            const double ph = -2 * PI * (double)s * (double)i / (double)Nw, cr = cos(ph) / (double)Nw, ci = sin(ph) / (double)Nw;
+            const double *q = c->Q_all + (size_t)s * (size_t)N * 2;
+            for (int64_t r = 0; r < N; r++) {
+                d[2 * r] += q[2 * r] * cr - q[2 * r + 1] * ci;
+                d[2 * r + 1] += q[2 * r] * ci + q[2 * r + 1] * cr;
+            }
+        }
+        init[2 * i] = sqrt(cnorm2(d, N));
+        est_printf(&buf, &len, &cap, "**** Norm of the ratio norm(qt)/norm(qs): %g @ w = %g ****\n", init[2 * i], c->w * (double)i);
+    }
+    est_printf(&buf, &len, &cap, "**** Displaying updated transient norms for (positive) frequencies ****\n");
+    const double qn = sqrt(cnorm2(c->qss, N));
+    for (int64_t i = 0; i < nhalf; i++) {
+        const double wi = c->w * (double)i;
+        for (int64_t s = 0; s < Ns; s++) {                                                                    /* :86-98 */
+            const double ph = wi * (double)s * deltaT, cr = cos(ph), ci = sin(ph);
+            const double *q = c->Q_all + (size_t)(s + skip) * (size_t)N * 2;
+            double *y = Y + (size_t)s * (size_t)N * 2;
+            for (int64_t r = 0; r < N; r++) {
+                y[2 * r] = q[2 * r] + c->qss[2 * r] * cr - c->qss[2 * r + 1] * ci;
+                y[2 * r + 1] = q[2 * r + 1] + c->qss[2 * r] * ci + c->qss[2 * r + 1] * cr;
+            }
+        }
+        /* orthonormal basis of the columns (QRDecomposition.c: BVOrthogonalize): Gram-Schmidt, every column swept twice */
+        for (int64_t s = 0; s < Ns; s++) {
+            double *y = Y + (size_t)s * (size_t)N * 2;
+            for (int pass = 0; pass < 2; pass++)
+                for (int64_t t = 0; t < s; t++) {
+                    const double *u = Y + (size_t)t * (size_t)N * 2;
+                    double pr = 0, pi = 0;   /* u^H y */
+                    for (int64_t r = 0; r < N; r++) { pr += u[2 * r] * y[2 * r] + u[2 * r + 1] * y[2 * r + 1]; pi += u[2 * r] * y[2 * r + 1] - u[2 * r + 1] * y[2 * r]; }
+                    for (int64_t r = 0; r < N; r++) { y[2 * r] -= u[2 * r] * pr - u[2 * r + 1] * pi; y[2 * r + 1] -= u[2 * r] * pi + u[2 * r + 1] * pr; }
+                }
+            const double nr = sqrt(cnorm2(y, N));
+            const double inv = nr > 0 ? 1.0 / nr : 0.0;
+            for (int64_t r = 0; r < 2 * N; r++) y[r] *= inv;
+        }
+        memcpy(d, c->qss, (size_t)N * 16);                                                                    /* :106-111: q_ss - U U^H q_ss */
+        for (int pass = 0; pass < 2; pass++)
+            for (int64_t t = 0; t < Ns; t++) {
+                const double *u = Y + (size_t)t * (size_t)N * 2;
+                double pr = 0, pi = 0;
+                for (int64_t r = 0; r < N; r++) { pr += u[2 * r] * d[2 * r] + u[2 * r + 1] * d[2 * r + 1]; pi += u[2 * r] * d[2 * r + 1] - u[2 * r + 1] * d[2 * r]; }
+                for (int64_t r = 0; r < N; r++) { d[2 * r] -= u[2 * r] * pr - u[2 * r + 1] * pi; d[2 * r + 1] -= u[2 * r] * pi + u[2 * r + 1] * pr; }
+            }
+        upd[2 * i] = sqrt(cnorm2(d, N)) / qn;
+        est_printf(&buf, &len, &cap, "**** Norm of the ratio norm(qt_up)/norm(qs): %g @ w = %g ****\n", upd[2 * i], wi);
+    }
+    int e = 0;
+    snprintf(c->dirs->IO_dir, sizeof c->dirs->IO_dir, "%s%s%d", c->dirs->FolderDir, "Initial_transient_norm_period_", (int)period_index);   /* :123 */
+    e = pb_write_vec(c->dirs->IO_dir, nhalf, init);
+    snprintf(c->dirs->IO_dir, sizeof c->dirs->IO_dir, "%s%s%d", c->dirs->FolderDir, "Updated_transient_norm_period_", (int)period_index);   /* :127 */
+    if (!e) e = pb_write_vec(c->dirs->IO_dir, nhalf, upd);
+    free(init); free(upd); free(Y); free(d);
+    if (c->ntext < 64) { c->text[c->ntext] = buf; c->text_step[c->ntext] = step; c->ntext++; } else free(buf);
+    return e;
+}
+
+static int est_cb(int64_t pos_e, const double *q, int64_t N, void *user)
+{
+    est_ctx *c = (est_ctx *)user;
+    const int64_t step = pos_e * c->est_mod, pos = pos_e % c->Nw;                                             /* TransientRunRK4.c:176-183 */
+    if (pos == 0 && TransientRemovalEst(c, step / c->Nt_period, step)) return 1;
+    memcpy(c->Q_all + (size_t)pos * (size_t)N * 2, q, (size_t)N * 16);
+    return 0;
+}
+
 static int TransientRunRK4(TransRun_vars *TR_vars, RSVDt_vars *RSVDt, Directories *dirs)
 {
     printf("\n********************************************\n************** Transient run ***************\n********************************************\n\n");
@@ -480,8 +604,6 @@ static int TransientRunRK4(TransRun_vars *TR_vars, RSVDt_vars *RSVDt, Directorie
     printf("Total integration time = %g = %d x %g with dt = %g\n", RSVDt->TS.dt * rend, (int)TR_vars->TransPeriods, TSS, RSVDt->TS.dt);
     if (TR_vars->TransSave) printf("Total snapshots to be saved = %d\n", (int)Nt_saved);
     else printf("Saving snapshots is not requested\n");
-    if (TR_vars->TransRemovalEst)
-        printf("Warning: 'TransRemovalEst' (a diagnostic of TransientRemovalEst.c) is not provided by this build; continuing without it\n");
     /* the grid is only needed for dt here */
     RSVDt->RSVD.Nw_eff = RSVDt->TS.RealOperator ? RSVDt->RSVD.Nw / 2 : RSVDt->RSVD.Nw;
     RSVDt->TS.Ns = Nt_period; RSVDt->TS.Nt = 0; RSVDt->TS.ResRatio = Nt_period / Ns > 0 ? Nt_period / Ns : 1;
@@ -510,14 +632,30 @@ static int TransientRunRK4(TransRun_vars *TR_vars, RSVDt_vars *RSVDt, Directorie
     if (TR_vars->TransSave) { int e = snapshot_cb(0, q0, N, &ctx); if (e) { free(q0); free(norms); return seterr(ERR_USER, "%s", pb_error()); } }   /* :116-120 */
     int64_t steps_done = 0;
     int reason = 0;
+    est_ctx ec;
+    memset(&ec, 0, sizeof ec);
+    if (TR_vars->TransRemovalEst) {                                                                           /* :56-65, :96-99, :110-114 */
+        ec.N = N; ec.Nw = Ns; ec.Nw_eff = RSVDt->RSVD.Nw_eff; ec.Nt_period = Nt_period; ec.est_mod = Nt_period / Ns;
+        ec.w = RSVDt->RSVD.w; ec.dirs = dirs;
+        ec.Q_all = (double *)calloc((size_t)N * (size_t)Ns * 2, sizeof(double));
+        ec.qss = (double *)malloc((size_t)N * 16);
+        if (!ec.Q_all || !ec.qss || ec.est_mod <= 0) { free(ec.Q_all); free(ec.qss); free(q0); free(norms); return seterr(RSVDT_ERR_MEM, "out of memory"); }
+        for (int64_t i = 0; i < 2 * N; i++) ec.qss[i] = -q0[i];
+        memcpy(ec.Q_all, q0, (size_t)N * 16);
+    }
     double t1 = wtime();
-    int rc = rsvdt_transient_run_rk4(H, 1, q0, rend, TR_vars->TransSaveMod, TR_vars->TransDivVal, TR_vars->TransConVal, norms,
-                                     &steps_done, &reason, snapshot_cb, &ctx);
-    if (rc) { free(q0); free(norms); CHK(rc); }
+    int rc = rsvdt_transient_run_rk4_est(H, 1, q0, rend, TR_vars->TransSaveMod, TR_vars->TransDivVal, TR_vars->TransConVal, norms,
+                                         &steps_done, &reason, snapshot_cb, &ctx, ec.est_mod, TR_vars->TransRemovalEst ? est_cb : NULL, &ec);
+    free(ec.Q_all); free(ec.qss);
+    if (rc) { for (int i = 0; i < ec.ntext; i++) free(ec.text[i]); free(q0); free(norms); CHK(rc); }
     printf("Norm of the initial snapshot: %f @ t = %d\n", norms[0], 0);
     const int64_t nchecks = steps_done / TR_vars->TransSaveMod;
-    for (int64_t p = 1; p <= nchecks; p++)
+    int it = 0;   /* the estimate of a step follows the norm line of that step (TransientRunRK4.c:137-184) */
+    for (int64_t p = 1; p <= nchecks; p++) {
+        for (; it < ec.ntext && ec.text_step[it] < p * TR_vars->TransSaveMod; it++) { fputs(ec.text[it], stdout); free(ec.text[it]); }
         if (!(reason && p == nchecks)) printf("Norm of the snapshot: %f @ t = %f\n", norms[p], (double)(p * TR_vars->TransSaveMod) * RSVDt->TS.dt);
+    }
+    for (; it < ec.ntext; it++) { fputs(ec.text[it], stdout); free(ec.text[it]); }
     if (reason == 1) printf("Stopped! The norm of the last snapshot is NAN!\n");
     if (reason == 2) printf("Diverged! The norm of the last snapshot exceeds the divergence threshold = %g\n", TR_vars->TransDivVal);
     if (reason == 3) printf("Converged! The norm of the last snapshot is smaller than the convergence threshold = %g\n", TR_vars->TransConVal);

@@ -458,8 +458,6 @@ class Run:
         Nt_saved = rend // v["TransSaveMod"] + 1                                      # :46
         self.log(f"Total integration time = {v['dt'] * rend:g} = {v['TransPeriods']} x {TSS:g} with dt = {v['dt']:g}")
         self.log(f"Total snapshots to be saved = {Nt_saved}" if v["TransSave"] else "Saving snapshots is not requested")
-        if v["TransRemovalEst"]:
-            self.log("Warning: 'TransRemovalEst' (a diagnostic of TransientRemovalEst.c) is not provided by this build; continuing without it")
         v["Ns"], v["Nt"], v["ResRatio"] = Nt_period, 0, max(Nt_period // Ns, 1)
         v["k"] = max(v["k"], 1)
         v["TransientRemoval"] = False
@@ -485,16 +483,57 @@ class Run:
         def on_snapshot(pos, q):                                                      # :116-120, :160-164 (collective)
             self.write_vec(f"{folder}q_transient_{pos}", N, r0, q)
 
+        # TransientRemovalEst.c (TransientRunRK4.c:56-65,96-114,174-184): the last Nw snapshots, one every Nt_period / Nw steps, and
+        # at the end of every period the estimate of how well the transient could be removed (transient_est.py); each rank
+        # holds its rows, the sums run over the ranks
+        est_mod, est_msgs, on_est = 0, [], None
+        if v["TransRemovalEst"]:
+            transient_est = self.pkg.transient_est
+            est_mod = Nt_period // Ns
+            Q_all = np.zeros((r1 - r0, Ns), np.complex128)
+            Q_all[:, 0] = q0
+            qss = -np.asarray(q0, np.complex128)
+            torch, dist = self.torch, self.dist
+
+            def allreduce(x):
+                x = np.ascontiguousarray(x)
+                t = torch.from_numpy(x.view(np.float64).copy()).to(self.dev)
+                dist.all_reduce(t)
+                return t.cpu().numpy().view(x.dtype).reshape(x.shape)
+
+            def allgather(x):
+                parts = [None] * self.world
+                dist.all_gather_object(parts, x)
+                return parts
+            allgather.rank = self.rank
+
+            def on_est(pos_e, q):
+                step = pos_e * est_mod
+                pos = pos_e % Ns
+                if pos == 0:
+                    period = step // Nt_period
+                    lines = []
+                    init, upd = transient_est.transient_removal_est(Q_all, qss, period, v["w"], v["Nw_eff"], lines.append,
+                                                                    allreduce, allgather)
+                    est_msgs.append((step, lines))
+                    if self.rank == 0:                                                # TransientRemovalEst.c:123-129
+                        self.io.write_vec(f"{folder}Initial_transient_norm_period_{period}", init.astype(np.complex128))
+                        self.io.write_vec(f"{folder}Updated_transient_norm_period_{period}", upd.astype(np.complex128))
+                Q_all[:, pos] = q
+
         if v["TransSave"]:
             on_snapshot(0, q0)
         t1 = time.time()
         q, norms, steps, reason = self.r.TransientRunRK4(q0, rend, v["TransSaveMod"], v["TransDivVal"], v["TransConVal"], True,
-                                                         on_snapshot if v["TransSave"] else None)
+                                                         on_snapshot if v["TransSave"] else None, est_mod, on_est)
         self.log(f"Norm of the initial snapshot: {norms[0]:f} @ t = 0")
         nchecks = steps // v["TransSaveMod"]
-        for p in range(1, nchecks + 1):
-            if not (reason and p == nchecks):
-                self.log(f"Norm of the snapshot: {norms[p]:f} @ t = {p * v['TransSaveMod'] * v['dt']:f}")
+        msgs = [(p * v["TransSaveMod"], 0, [f"Norm of the snapshot: {norms[p]:f} @ t = {p * v['TransSaveMod'] * v['dt']:f}"])
+                for p in range(1, nchecks + 1) if not (reason and p == nchecks)]
+        msgs += [(step, 1, lines) for step, lines in est_msgs]                        # (the estimate of a step follows its norm line)
+        for _, _, lines in sorted(msgs, key=lambda m: (m[0], m[1])):
+            for ln in lines:
+                self.log(ln)
         if reason == 1:
             self.log("Stopped! The norm of the last snapshot is NAN!")
         if reason == 2:

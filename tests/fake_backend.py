@@ -127,24 +127,30 @@ class FakeHandle:
         assert rows is None or rows == out.shape[0]
         return out
 
-    def TransientRunRK4(self, q0, rend, mod, div, con, direct=True, on_snapshot=None):
+    def TransientRunRK4(self, q0, rend, mod, div, con, direct=True, on_snapshot=None, est_mod=0, on_est=None):
         q = np.concatenate(_gather(np.asarray(q0)))
         Op = self.A if direct else self.AH
         norms = np.zeros(rend // mod + 1)
         norms[0] = np.linalg.norm(q)
-        steps, reason = 0, 0
-        for p in range(1, rend // mod + 1):
-            q, nr, _, reason = self.O.transient_run_rk4(Op, self.v.dt, mod, mod, div, con, q)
-            steps += mod
-            norms[p] = nr[1]
-            if reason:
-                break
-            if on_snapshot is not None:
-                on_snapshot(p, self._local(q[:, None])[:, 0])
-        if not reason and rend % mod:
-            q, _, _, _ = self.O.transient_run_rk4(Op, self.v.dt, rend % mod, rend % mod + 1, div, con, q)
-            steps = rend
-        return self._local(q[:, None])[:, 0], norms, steps, reason
+        i, reason = 0, 0
+        while i < rend and not reason:
+            stop = min(rend, (i // mod + 1) * mod)
+            if est_mod > 0 and on_est is not None:
+                stop = min(stop, (i // est_mod + 1) * est_mod)
+            q, _, _, _ = self.O.transient_run_rk4(Op, self.v.dt, stop - i, 10 ** 9, 1e300, 0.0, q)
+            i = stop
+            if i % mod == 0:
+                nr = np.linalg.norm(q)
+                p = i // mod
+                reason = 1 if np.isnan(nr) else (2 if nr > div else (3 if nr < con else 0))
+                if reason:
+                    break
+                if on_snapshot is not None:
+                    on_snapshot(p, self._local(q[:, None])[:, 0])
+                norms[p] = nr
+            if est_mod > 0 and on_est is not None and i % est_mod == 0:
+                on_est(i // est_mod, self._local(q[:, None])[:, 0])
+        return self._local(q[:, None])[:, 0], norms, i, reason
 
     def close(self):
         self.closed = True

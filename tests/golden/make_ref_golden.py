@@ -256,8 +256,35 @@ def case():
     print("written ref_lns_case.npz")
 
 
+# ---------------------------------------------------------------------------------------------- 7. TransientRemovalEst.c
+def transient_est():
+    """the transient run with `TransRemovalEst: true` (TransientRunRK4.c:56-65,96-114,174-184 + TransientRemovalEst.c) through the
+    reference executable: three periods on the tutorial operator, given initial vector; norms per period and the banner lines"""
+    import re
+    rng = np.random.default_rng(8)
+    q0 = rng.standard_normal(500) + 1j * rng.standard_normal(500)
+    q0 /= np.linalg.norm(q0)
+    files = {"A_GL": ("copy", os.path.join(HERE, "A_GL")), "F_hat": ("dense", np.zeros((500, 8), complex)), "results/q0": ("vec", q0)}
+    text = SMALL_YAML.replace("TransPeriods:       1", "TransPeriods:       3") + "TransRemovalEst:    true\n"
+    assert "TransPeriods:       3" in text
+    tmp, stdout = run_exe(text, files, autoinit=True, Nw=8, w=0.6, TL=1.0, TR="false", opt=1, transrun="true", q=1, disc="true",
+                          weights="false")
+    res = os.path.join(tmp, "results", "TransientSnapshots_0")
+    out = {"q0": q0, "Nw": 8, "w": 0.6, "periods": 3, "files": np.array(sorted(os.listdir(res))),
+           "norms": io.read_vec(f"{res}/q_transient_norms").real, "last": io.read_vec(f"{res}/q_transient_last_snapshot"),
+           "stdout": np.array([ln for ln in stdout.splitlines() if ln.startswith("****") or ln.startswith("Norm of")])}
+    for p in (1, 2, 3):
+        out[f"initial_{p}"] = io.read_vec(f"{res}/Initial_transient_norm_period_{p}").real
+        out[f"updated_{p}"] = io.read_vec(f"{res}/Updated_transient_norm_period_{p}").real
+    shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(HERE, "ref_gl_transient_est.npz"), **out)
+    print("written ref_gl_transient_est.npz")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "weighted", "executable", "tutorial", "lns", "case"]
+    which = sys.argv[1:] or ["functions", "weighted", "executable", "tutorial", "lns", "case", "transient_est"]
+    if "transient_est" in which:
+        transient_est()
     if "functions" in which:
         small_functions()
     if "weighted" in which:

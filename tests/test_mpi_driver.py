@@ -308,6 +308,26 @@ def test_executable_flow_transient_run_and_weights_on_cpu_ranks(pkg, tmp_path):
         assert principal_angle(V[:, iw, :1], gw["V_hat"][:, iw, :1]) <= 1e-6
 
 
+def test_executable_flow_transient_removal_estimate_on_cpu_ranks(pkg, tmp_path):
+    # `TransRemovalEst: true` (TransientRemovalEst.c) through rsvdt_mpi.py on 3 gloo ranks: the estimate's files against the
+    # reference executable's (norms summed over the ranks, orthonormal bases by TSQR over the row blocks)
+    io = pkg.petsc_io
+    g = np.load(os.path.join(GOLDEN, "ref_gl_transient_est.npz"))
+    tmp = _case_dir(tmp_path, "est", pkg, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")),
+                                           "F_hat": ("dense", np.zeros((500, 8), complex)), "results/q0": ("vec", g["q0"])},
+                    Nw=8, w=0.6, TL=1.0, TR="false", opt=1, transrun="true", q=1, disc="true", weights="false")
+    y = os.path.join(tmp, "variables.yaml")
+    text = open(y).read().replace("TransPeriods:       1", "TransPeriods:       3") + "TransRemovalEst:    true\n"
+    open(y, "w").write(text)
+    _run_flow(tmp, 3)
+    res = os.path.join(tmp, "results", "TransientSnapshots_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g["files"])
+    assert np.allclose(io.read_vec(f"{res}/q_transient_norms").real, g["norms"], rtol=1e-12)
+    for p in (1, 2, 3):
+        assert np.allclose(io.read_vec(f"{res}/Initial_transient_norm_period_{p}").real, g[f"initial_{p}"], rtol=1e-10)
+        assert np.allclose(io.read_vec(f"{res}/Updated_transient_norm_period_{p}").real, g[f"updated_{p}"], rtol=1e-6, atol=2e-14)
+
+
 def test_executable_random_forcing_does_not_depend_on_the_rank_count(pkg, tmp_path):
     # InputForcingFlg: false -> RandSeed-seeded forcing drawn per global row block: 2 and 3 ranks give the same gains
     io = pkg.petsc_io
@@ -445,6 +465,29 @@ def test_mpi_driver_two_gpus_transient_run_matches_reference_executable(pkg, tmp
     assert np.allclose(io.read_vec(f"{res}/q_transient_norms").real, g["trans_norms"], rtol=1e-11)
     assert rel_err(io.read_vec(f"{res}/q_transient_last_snapshot"), g["trans_last"]) < 1e-11
     assert rel_err(io.read_vec(f"{res}/q_transient_2"), g["trans_q2"]) < 1e-11
+
+
+@pytest.mark.gpu
+def test_mpi_driver_two_gpus_transient_removal_estimate_matches_reference_executable(pkg, tmp_path):
+    # TransRemovalEst: true through rsvdt_mpi.py on 2 GPUs: sums over the ranks, TSQR bases, against the reference executable
+    _need_two_gpus()
+    io = pkg.petsc_io
+    g = np.load(os.path.join(GOLDEN, "ref_gl_transient_est.npz"))
+    tmp = str(tmp_path)
+    os.makedirs(os.path.join(tmp, "results"))
+    write_case_files(io, tmp, {"A_GL": ("copy", os.path.join(GOLDEN, "A_GL")), "F_hat": ("dense", np.zeros((500, 8), complex)),
+                               "results/q0": ("vec", g["q0"])})
+    text = SMALL_YAML.replace("TransPeriods:       1", "TransPeriods:       3") + "TransRemovalEst:    true\n"
+    open(os.path.join(tmp, "variables.yaml"), "w").write(text.format(
+        root=tmp, Nw=8, w=0.6, TL=1.0, TR="false", opt=1, transrun="true", q=1, disc="true", weights="false"))
+    out = _torchrun(tmp, port=29546)
+    assert out.returncode == 0, _diag(out)
+    res = os.path.join(tmp, "results", "TransientSnapshots_0")
+    assert set(os.listdir(res)) == set(str(f) for f in g["files"])
+    assert np.allclose(io.read_vec(f"{res}/q_transient_norms").real, g["norms"], rtol=1e-11)
+    for p in (1, 2, 3):
+        assert np.allclose(io.read_vec(f"{res}/Initial_transient_norm_period_{p}").real, g[f"initial_{p}"], rtol=1e-9)
+        assert np.allclose(io.read_vec(f"{res}/Updated_transient_norm_period_{p}").real, g[f"updated_{p}"], rtol=1e-5, atol=5e-14)
 
 
 @pytest.mark.gpu
