@@ -116,13 +116,26 @@ def localize_banded(plan: Plan, rowptr, col_global, val):
 
 def transpose_slab(rowptr, col, val, row_offset: int, c_lo: int, c_hi: int):
     """rows [c_lo, c_hi) of A^H from a slab of rows of A (global row of slab row i is row_offset + i) that contains
-    every entry with a column in [c_lo, c_hi).  The entries arrive row by row, so one STABLE sort by column leaves every
-    row of A^H with ascending columns (a third of the time of a two-key sort at 3e8 entries)."""
+    every entry with a column in [c_lo, c_hi).  The entries arrive row by row, so one STABLE counting sort by column leaves
+    every row of A^H with ascending columns: scipy's CSR -> CSC conversion where scipy is installed (O(nnz); 3 s instead of
+    17 s for the 1.3e8 entries a rank of the 2e6-DOF 3-D case holds), else a stable argsort."""
     rowptr = np.asarray(rowptr, np.int64)
     col = np.asarray(col, np.int64)
-    rows = np.repeat(np.arange(rowptr.size - 1, dtype=np.int64), np.diff(rowptr)) + row_offset
+    val = np.asarray(val)
+    nrows = rowptr.size - 1
+    try:
+        from scipy import sparse
+    except ImportError:
+        sparse = None
+    if sparse is not None and col.size:
+        ncols = max(int(col.max()) + 1, c_hi)
+        T = sparse.csr_matrix((val, col, rowptr), shape=(nrows, ncols)).tocsc()
+        ip = np.asarray(T.indptr, np.int64)
+        a, b = ip[c_lo], ip[c_hi]
+        return ip[c_lo:c_hi + 1] - a, np.asarray(T.indices[a:b], np.int64) + row_offset, np.conj(T.data[a:b])
+    rows = np.repeat(np.arange(nrows, dtype=np.int64), np.diff(rowptr)) + row_offset
     sel = (col >= c_lo) & (col < c_hi)
-    r, c, v = rows[sel], col[sel], np.conj(np.asarray(val)[sel])
+    r, c, v = rows[sel], col[sel], np.conj(val[sel])
     order = np.argsort(c, kind="stable")
     r, c, v = r[order], c[order], v[order]
     rp = np.zeros(c_hi - c_lo + 1, np.int64)
