@@ -74,8 +74,16 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def source_sha(*names):
+def source_sha(*names, region=None):
+    """hash of kernel source files, or -- region = (file, start marker, end marker) -- of the text of one kernel inside a file
+    that holds many (an edit elsewhere in kernels.cu does not invalidate the capture of the fused step kernel)"""
     h = hashlib.sha256()
+    if region:
+        with open(os.path.join(ROOT, "rsvd-delta-t_b200", "csrc", region[0]), "r") as f:
+            text = f.read()
+        a = text.index(region[1])
+        h.update(text[a:text.index(region[2], a)].encode())
+        return h.hexdigest()[:16]
     for n in names:
         with open(os.path.join(ROOT, "rsvd-delta-t_b200", "csrc", n), "rb") as f:
             h.update(f.read())
@@ -88,7 +96,7 @@ def ncu_traffic(key):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         ent = json.load(open(tp))[key]
-        if ent.get("source_sha") and ent["source_sha"] != source_sha(*ent["source_files"]):
+        if ent.get("source_sha") and ent["source_sha"] != source_sha(*ent["source_files"], region=ent.get("source_region")):
             return None, "stale (kernel source changed since the ncu capture)"
         return ent, None
     except Exception:

@@ -1321,13 +1321,13 @@ int transient_removal(rsvdt_handle h, bool direct, const cplx *snaps, cplx *Yhat
         ALLRED(G.p, (int64_t)2 * nv * m * m);
         // shift of Fukaya et al. (2020): 11 (m n + n (n+1)) u ||X||_2^2, with ||X||_2^2 <= trace(G)
         const double shift = pass == 0 ? 11.0 * ((double)h->N_global * m + (double)m * (m + 1)) * 1.1e-16 : 0.0;
-        TRY(launch_chol_inverse_big(G.as<cplx>(), m, nv, shift, Minv.as<cplx>(), status.as<int>(), h->stream));
+        TRY(launch_chol_inverse_big(G.as<cplx>(), m, nv, shift, Minv.as<cplx>(), status.as<int>(), h->stream, 1));
         TRY(launch_stack_rmul(W.as<cplx>(), U, nullptr, 0, 0.0, V.as<cplx>(), U, m, Minv.as<cplx>(), m, 1.0, nv, rows, h->stream));
         h->launches += 4;
         TRY(cudaMemcpyAsync(st.data(), status.p, (size_t)nv * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         TRY(cudaStreamSynchronize(h->stream));
-        for (int z = 0; z < nv; z++)
-            if (st[(size_t)z]) { cleanup(); return fail(h, RSVDT_ERR_NUMERIC, "transient removal: QR breakdown for test vector %d (column %d, pass %d)", z, st[(size_t)z] - 1, pass); }
+        for (int z = 0; z < nv; z++)   // (negative: that many dependent snapshot columns were left out of the basis -- not an error)
+            if (st[(size_t)z] > 0) { cleanup(); return fail(h, RSVDT_ERR_NUMERIC, "transient removal: QR breakdown for test vector %d (column %d, pass %d)", z, st[(size_t)z] - 1, pass); }
         V.swap(W);
     }
     // ---- MV = exp(A dT) V (TSExpADeltaT.c:25-34), slot by slot with the fused step kernels ---------------------------

@@ -1919,8 +1919,16 @@ cudaError_t launch_stack_rmul(cplx *Out, int64_t os, const cplx *Z, int64_t zs, 
 // Cholesky G_z + shift_z*I = R^H R (upper R, positive diagonal) and Minv_z = R^{-1}; one CTA per z, matrices in global
 // memory (m up to a few hundred).  G is overwritten by R.  status[z] = failing column + 1, or 0.
 __global__ void __launch_bounds__(128)
-chol_inverse_big_kernel(cplx *__restrict__ G, int m, double shift_scale, cplx *__restrict__ Minv, int *__restrict__ status)
+chol_inverse_big_kernel(cplx *__restrict__ G, int m, double shift_scale, cplx *__restrict__ Minv, int *__restrict__ status,
+                        int drop_dependent)
 {
+    // drop_dependent: a column whose pivot is not positive (numerically inside the span of the columns before it) is left out
+    // -- its row of R and its column of R^{-1} are zero, so the basis simply has one vector fewer -- instead of being reported
+    // (status[z] = -(columns left out)).  The transient-removal basis uses it: once the transient has decayed to rounding
+    // level snapshot Nw + 1 repeats snapshot 1, and the projection only depends on the span (SLEPc's Gram-Schmidt carries
+    // on there with a vector of rounding noise).
+    __shared__ unsigned char s_drop[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_drop[i] = 0;
     const int z = blockIdx.x;
     cplx *g = G + (int64_t)z * m * m;
     cplx *mi = Minv + (int64_t)z * m * m;
@@ -1940,14 +1948,19 @@ chol_inverse_big_kernel(cplx *__restrict__ G, int m, double shift_scale, cplx *_
     for (int j = 0; j < m; j++) {
         if (threadIdx.x == 0) {
             double d = g[j * m + j].x;
-            if (!(d > 0.0)) { if (!s_bad) s_bad = j + 1; d = 1.0; }
+            if (!(d > 0.0)) {
+                if (drop_dependent && m <= 256) { s_drop[j] = 1; s_bad -= 1; }
+                else if (!s_bad) s_bad = j + 1;
+                d = 1.0;
+            }
             s_piv = sqrt(d);
         }
         __syncthreads();
         const double rjj = s_piv;
+        const bool dropped = s_drop[j < 256 ? j : 0] && j < 256;
         for (int c = j + threadIdx.x; c < m; c += blockDim.x) {   // row j of R
             const cplx v = g[j * m + c];
-            g[j * m + c] = (c == j) ? make_double2(rjj, 0.0) : make_double2(v.x / rjj, v.y / rjj);
+            g[j * m + c] = (c == j) ? make_double2(rjj, 0.0) : (dropped ? make_double2(0.0, 0.0) : make_double2(v.x / rjj, v.y / rjj));
         }
         __syncthreads();
         // trailing update: G[i][c] -= conj(R[j][i]) * R[j][c], i > j, c >= i
@@ -1975,13 +1988,16 @@ chol_inverse_big_kernel(cplx *__restrict__ G, int m, double shift_scale, cplx *_
             const double rr = g[r * m + r].x;
             mi[r * m + c] = make_double2(sacc.x / rr, sacc.y / rr);
         }
+        if (c < 256 && s_drop[c])
+            for (int r = 0; r < m; r++) mi[r * m + c] = make_double2(0.0, 0.0);   // a column left out contributes nothing
     }
     if (threadIdx.x == 0) status[z] = s_bad;
 }
 
-cudaError_t launch_chol_inverse_big(cplx *G, int m, int nz, double shift_scale, cplx *Minv, int *status, cudaStream_t s)
+cudaError_t launch_chol_inverse_big(cplx *G, int m, int nz, double shift_scale, cplx *Minv, int *status, cudaStream_t s,
+                                    int drop_dependent)
 {
-    chol_inverse_big_kernel<<<nz, 128, 0, s>>>(G, m, shift_scale, Minv, status);
+    chol_inverse_big_kernel<<<nz, 128, 0, s>>>(G, m, shift_scale, Minv, status, drop_dependent);
     return cudaGetLastError();
 }
 

@@ -201,7 +201,10 @@ cudaError_t launch_stack_gram2(const cplx *X, int64_t xs, int ma, const cplx *Y,
 cudaError_t launch_stack_rmul(cplx *Out, int64_t os, const cplx *Z, int64_t zs, double beta, const cplx *X, int64_t xs,
                               int ma, const cplx *M, int mb, double alpha, int nv, int64_t nrows, cudaStream_t s);
 // G_z + shift_scale*trace(G_z)*I = R^H R; Minv_z = R^{-1}; G overwritten; status[z] != 0 on breakdown
-cudaError_t launch_chol_inverse_big(cplx *G, int m, int nz, double shift_scale, cplx *Minv, int *status, cudaStream_t s);
+// drop_dependent != 0: columns with a non-positive pivot are left out of the basis (status[z] = -(their number)) instead of
+// being reported as a breakdown (status[z] = column + 1)
+cudaError_t launch_chol_inverse_big(cplx *G, int m, int nz, double shift_scale, cplx *Minv, int *status, cudaStream_t s,
+                                    int drop_dependent = 0);
 // C_z[:, iw] = (alpha_iw I - Mt_z)^{-1} (alpha_iw B1_z[:, iw] - B2_z[:, iw]); scratch: nz*nw*m*(m+1) elements
 cudaError_t launch_galerkin_solve(const cplx *Mt, const cplx *B1, const cplx *B2, const cplx *alpha, int m, int nw, int nz,
                                   cplx *scratch, cplx *C, int *status, cudaStream_t s);

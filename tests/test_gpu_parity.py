@@ -400,6 +400,21 @@ def test_transient_removal_action(pkg, O, A_GL, direct):
     r.close()
 
 
+def test_transient_removal_when_the_transient_has_already_decayed(pkg, O, A_GL):
+    # strong discounting + a long TransientLength: the snapshots are periodic to rounding, snapshot Nw + 1 repeats snapshot 1 and
+    # the snapshot matrices lose a rank.  SLEPc's Gram-Schmidt (and the oracle's) carries on; the CUDA path leaves the dependent
+    # column out of its CholeskyQR basis (it used to stop with "QR breakdown") -- the projection only depends on the span
+    k, Nw, w = 2, 8, 2.0
+    A = A_GL.shifted(12.0)
+    v = make_vars(O, pkg, 500, k, Nw, w, 0.003, 4.0, TR=True)
+    F = _forcing(500, k * Nw, 12)
+    ref = _oracle_action(O, A, v, F, True)
+    r = _handle(pkg, A, v)
+    got = r.TSActionRK4(F, direct=True)
+    r.close()
+    assert np.isfinite(got).all() and rel_err(got, ref) < 1e-9
+
+
 def test_tutorial_config_full_solve_with_transient_removal(pkg, O, A_GL):
     # BASELINE.json configs[0]: the tutorial as shipped (variables.yaml: w = 0.05, Nw = 42, dt = 0.003, TransientLength = 10,
     # TransientRemoval = true, q = 1), with k = 3 instead of 10 to keep the oracle run short; F_hat fed to both sides

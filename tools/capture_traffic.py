@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
+GL_REGION = ["kernels.cu", "// K1d: the DIA fused step with TMA-staged tiles", "inline int tma_R(int nv)"]   # the kernel's own text
 SECTIONS = [  # section, kernel regex, source files, launches to skip, launches to average
     ("gl", "rk4_dia_tma_kernel", ["kernels.cu"], 40, 16),
     ("lns3d", "rk4_stage_tbcsr_kernel", ["stage_tiled.cu", "stage_tiled.cuh"], 40, 16),
@@ -48,7 +49,8 @@ for sec, rx, files, skip, count in SECTIONS:
     ns = sum(v["gpu__time_duration.sum"] for v in by.values()) / n
     out[f"{sec}:{rx}"] = {"dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr, "launches_averaged": n,
                           "ncu_avg_launch_ms": ns / 1e6, "kernel": next(iter(by.values()))["name"][:120], "rows_per_gpu": rows_per_gpu,
-                          "source_files": files, "source_sha": bench.source_sha(*files),
+                          "source_files": files, "source_region": GL_REGION if sec == "gl" else None,
+                          "source_sha": bench.source_sha(*files, region=GL_REGION if sec == "gl" else None),
                           "capture": "tools/capture_traffic.py: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
                                      f"{n} launches after {skip} warm-up launches of `bench.py --only {sec}`"}
     print(sec, out[f"{sec}:{rx}"], flush=True)
