@@ -77,6 +77,25 @@ def test_read_user_input_conditionals(drv, tmp_path):
         drv.read_user_input(_yaml(tmp_path, BASE + "TransRun: true\nTransICFlg: true\n"), quiet)
 
 
+def test_row_cache_serves_a_containing_slab_from_the_block_already_read(drv, pkg):
+    N, rp, ci, va = pkg.synthetic.lns_stencil((6, 7, 8), nvar=5)
+    calls = []
+
+    def fn(a, b):
+        calls.append((a, b))
+        return pkg.dist.slice_rows(rp, ci, va, 0, a, b)
+    for a, b, c, d in ((100, 500, 40, 700), (0, 300, 0, 600), (300, N, 200, N), (100, 200, 100, 200), (100, 500, 200, 400)):
+        rc = drv.RowCache(fn)
+        rc.prime(a, b)
+        calls.clear()
+        got = rc(c, d)
+        assert all(np.array_equal(x, y) for x, y in zip(got, pkg.dist.slice_rows(rp, ci, va, 0, c, d)))
+        if c <= a and b <= d:
+            assert rc.have is None and all(not (x < b and y > a) for x, y in calls)      # the owned block was not read again
+        else:
+            assert calls == [(c, d)]
+
+
 def test_random_rows_do_not_depend_on_the_partition(drv):
     full = drv.random_rows(14, 0, 1000, 3, block=128)
     parts = [drv.random_rows(14, a, b, 3, block=128) for a, b in ((0, 77), (77, 640), (640, 1000))]
