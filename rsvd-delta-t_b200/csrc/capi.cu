@@ -1774,7 +1774,6 @@ int rsvdt_create(int device, rsvdt_handle *hout)
     if (const char *e = getenv("RSVDT_TILED_VARIANT")) h->tiled_variant = atoll(e);   // (the same, for runs of the test suite under a variant)
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_ex, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -1786,7 +1785,9 @@ int rsvdt_create(int device, rsvdt_handle *hout)
     {
         int lo = 0, hi = 0;   // numerically lower = higher priority; the synthesis stream gets the lowest
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&h->synth_stream, cudaStreamNonBlocking, lo) != cudaSuccess) {
+        // ... and the exchange stream the highest: its one CTA must get the first slot a step-kernel CTA frees, not the last
+        if (cudaStreamCreateWithPriority(&h->synth_stream, cudaStreamNonBlocking, lo) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&h->xstream, cudaStreamNonBlocking, hi) != cudaSuccess) {
             delete h;
             return RSVDT_ERR_CUDA;
         }
