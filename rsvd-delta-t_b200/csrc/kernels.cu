@@ -1398,56 +1398,6 @@ cudaError_t launch_gram(const cplx *Y, int64_t nrows, int k, int nw, int64_t slo
     return cudaGetLastError();
 }
 
-// Cholesky G = R^H R (R upper, positive real diagonal) and M = R^{-1}; one thread per frequency (k <= 32).
-__global__ void chol_inverse_kernel(const cplx *__restrict__ G, int k, int nw, cplx *__restrict__ M, int *status)
-{
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nw) return;
-    const cplx *g = G + (int64_t)w * k * k;
-    cplx *m = M + (int64_t)w * k * k;
-    cplx R[32 * 32];  // local memory; row-major upper triangular
-    int bad = 0;
-    for (int j = 0; j < k; j++) {
-        // diagonal
-        double d = g[j * k + j].x;
-        for (int p = 0; p < j; p++) d -= R[p * k + j].x * R[p * k + j].x + R[p * k + j].y * R[p * k + j].y;
-        if (!(d > 0.0)) { bad = j + 1; d = 1.0; }
-        const double rjj = sqrt(d);
-        R[j * k + j] = make_double2(rjj, 0.0);
-        for (int c = j + 1; c < k; c++) {
-            cplx sacc = g[j * k + c];  // G[j][c]
-            for (int p = 0; p < j; p++) {  // s -= conj(R[p][j]) * R[p][c]
-                const cplx a = R[p * k + j], b = R[p * k + c];
-                sacc.x -= a.x * b.x + a.y * b.y;
-                sacc.y -= a.x * b.y - a.y * b.x;
-            }
-            R[j * k + c] = make_double2(sacc.x / rjj, sacc.y / rjj);
-        }
-    }
-    // M = R^{-1}, upper triangular, by back substitution column by column
-    for (int c = 0; c < k; c++) {
-        for (int r = k - 1; r >= 0; r--) {
-            if (r > c) { m[r * k + c] = make_double2(0.0, 0.0); continue; }
-            cplx sacc = make_double2(r == c ? 1.0 : 0.0, 0.0);
-            for (int p = r + 1; p <= c; p++) {  // s -= R[r][p] * M[p][c]
-                const cplx a = R[r * k + p], b = m[p * k + c];
-                sacc.x -= a.x * b.x - a.y * b.y;
-                sacc.y -= a.x * b.y + a.y * b.x;
-            }
-            const double rr = R[r * k + r].x;
-            m[r * k + c] = make_double2(sacc.x / rr, sacc.y / rr);
-        }
-    }
-    status[w] = bad;
-}
-
-cudaError_t launch_chol_inverse(const cplx *G, int k, int nw, cplx *M, int *status, cudaStream_t s)
-{
-    if (k > 32) return cudaErrorInvalidValue;
-    chol_inverse_kernel<<<(nw + 31) / 32, 32, 0, s>>>(G, k, nw, M, status);
-    return cudaGetLastError();
-}
-
 // Cross-product SVD of a tall block through its Gram matrix (SLEPc's default SVD type, SVDAllFreqs.c:36-40):
 // cyclic complex Jacobi on G_w; sigma = sqrt(lambda) sorted descending; M = V diag(1/sigma) so that U = Y M.
 // One warp per frequency, G and V in shared memory (k <= 32: 2 x 16 KB): lane r owns row r in the column updates and

@@ -147,8 +147,6 @@ int gram_num_blocks(int64_t nrows);
 // Y_w starts at Y + w*slot_stride (complex elements); only the nrows rows given are summed (owned rows of a partition)
 cudaError_t launch_gram(const cplx *Y, int64_t nrows, int k, int nw, int64_t slot_stride, cplx *partial, cplx *G,
                         cudaStream_t s);
-// M[w] = R_w^{-1} with G_w = R_w^H R_w (Cholesky, upper R, positive diagonal); status[w] != 0 on breakdown
-cudaError_t launch_chol_inverse(const cplx *G, int k, int nw, cplx *M, int *status, cudaStream_t s);
 // eigen-decomposition of G_w (Hermitian Jacobi): sigma[w][m] = sqrt(lambda_m) descending, M[w] = V * diag(1/sigma)
 cudaError_t launch_cross_svd_small(const cplx *G, int k, int nw, cplx *M, double *sigma, cudaStream_t s);
 // Y_w <- Y_w * M_w in place (row tiles staged through shared memory)
